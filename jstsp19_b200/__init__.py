@@ -1,0 +1,18 @@
+"""jstsp19_b200 - B200-native batched channel-estimation engine for the hot path of
+vlaxose/jstsp19 (per-trial wideband hybrid-beamforming mmWave channel estimation).
+
+The package is a thin host layer over ``libjstsp_b200.so`` (hand-written sm_100a CUDA
+behind the C ABI of ``include/jstsp_b200.h``):
+
+* ``jstsp19_b200.api``    - functions with the reference's MATLAB names/signatures
+  (NumPy in, NumPy out; HOST-buffer C-ABI calls - what a MEX gateway does);
+* ``jstsp19_b200.engine`` - device-resident batched engine on torch tensors
+  (Monte-Carlo trials sharded over ranks, one NCCL reduction at the end).
+
+There is no CPU fallback: without the shared library the import raises, without a
+B200-class GPU every solver call raises.
+"""
+from . import _lib  # noqa: F401  (raises if the CUDA library is missing)
+from .api import (mc_admm, mc_svt, proposed_algorithm, proposed_algorithm_angles, svt)  # noqa: F401
+
+__all__ = ["proposed_algorithm", "proposed_algorithm_angles", "svt", "mc_svt", "mc_admm"]

@@ -1,0 +1,125 @@
+"""ctypes binding of ``libjstsp_b200.so`` (the C ABI in ``include/jstsp_b200.h``).
+
+There is deliberately no CPU fallback: importing works without a GPU (so the
+symbol table can be checked on a CPU box), but creating a handle raises unless a
+sm_100-class device is present, and a missing shared library raises at import.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libjstsp_b200.so")
+
+F32, F64 = 0, 1
+HOST, DEVICE = 0, 1
+APPROXIMATE, STD = 0, 1
+
+E_ARG, E_CUDA, E_UNSUPPORTED, E_NOMEM = -1, -2, -3, -4
+
+
+class JstspError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"jstsp error {code}: {msg}")
+        self.code = code
+
+
+class AdmmDesc(C.Structure):
+    _fields_ = [
+        ("N", C.c_int), ("M", C.c_int), ("G", C.c_int), ("P", C.c_int),
+        ("imax", C.c_int), ("type", C.c_int), ("batch", C.c_int),
+        ("ld_subY", C.c_longlong), ("ld_omega", C.c_longlong), ("ld_A", C.c_longlong), ("ld_B", C.c_longlong),
+        ("ld_S", C.c_longlong), ("ld_Y", C.c_longlong), ("ld_conv", C.c_longlong),
+        ("n_indx", C.c_int), ("ld_indx", C.c_longlong),
+    ]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing - build it with `make` (or `python -c 'import __graft_entry__ as g; g.build()'`); "
+            "jstsp19_b200 has no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    vp, i, ll, dp = C.c_void_p, C.c_int, C.c_longlong, C.POINTER(C.c_double)
+    lib.jstsp_version.restype = C.c_char_p
+    lib.jstsp_create.argtypes = [C.POINTER(vp), i]
+    lib.jstsp_destroy.argtypes = [vp]
+    lib.jstsp_destroy.restype = None
+    lib.jstsp_last_error.argtypes = [vp]
+    lib.jstsp_last_error.restype = C.c_char_p
+    lib.jstsp_set_stream.argtypes = [vp, vp]
+    lib.jstsp_synchronize.argtypes = [vp]
+    lib.jstsp_launch_count.argtypes = [vp]
+    lib.jstsp_launch_count.restype = ll
+    lib.jstsp_set_chunk.argtypes = [vp, i]
+    lib.jstsp_proposed_algorithm.argtypes = [vp, C.POINTER(AdmmDesc), i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.jstsp_proposed_algorithm_angles.argtypes = [vp, C.POINTER(AdmmDesc), i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.jstsp_svt.argtypes = [vp, i, i, i, i, i, vp, ll, vp, vp, ll]
+    lib.jstsp_mc_svt.argtypes = [vp, i, i, i, i, i, i, vp, ll, vp, ll, vp, vp, vp, ll]
+    lib.jstsp_mc_admm.argtypes = [vp, i, i, i, i, i, i, vp, ll, vp, ll, vp, ll, vp, vp, vp, ll, vp, ll]
+    return lib
+
+
+lib = _load()
+
+#: every symbol include/jstsp_b200.h declares (checked by tests/test_abi.py)
+EXPORTED = [
+    "jstsp_create", "jstsp_destroy", "jstsp_last_error", "jstsp_version", "jstsp_set_stream",
+    "jstsp_synchronize", "jstsp_launch_count", "jstsp_set_chunk",
+    "jstsp_proposed_algorithm", "jstsp_proposed_algorithm_angles",
+    "jstsp_svt", "jstsp_mc_svt", "jstsp_mc_admm",
+]
+
+
+class Handle:
+    """Owns one ``jstsp_handle`` (one CUDA context / stream / workspace)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        rc = lib.jstsp_create(C.byref(self._h), int(device))
+        if rc != 0:
+            raise JstspError(rc, "jstsp_create failed: no usable sm_100 CUDA device (there is no CPU fallback)")
+        self.device = device
+
+    def check(self, rc):
+        if rc < 0:
+            raise JstspError(rc, lib.jstsp_last_error(self._h).decode())
+        return rc
+
+    @property
+    def ptr(self):
+        return self._h
+
+    def set_stream(self, cuda_stream_ptr: int):
+        self.check(lib.jstsp_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        self.check(lib.jstsp_synchronize(self._h))
+
+    def set_chunk(self, n: int):
+        self.check(lib.jstsp_set_chunk(self._h, int(n)))
+
+    @property
+    def launches(self) -> int:
+        return int(lib.jstsp_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            lib.jstsp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default = {}
+
+
+def default_handle(device: int = 0) -> Handle:
+    if device not in _default:
+        _default[device] = Handle(device)
+    return _default[device]

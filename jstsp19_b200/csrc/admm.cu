@@ -1,0 +1,837 @@
+// admm.cu - proposed ADMM matrix-completion estimator, batched over independent trials.
+//
+// Replaces basic_system_functions/proposed_algorithm.m:1-73 and
+// proposed_algorithm_angles.m:1-85 with the Kronecker-free algebra of SURVEY.md A.1:
+//   K1 = diag(vec Omega)          -> element-wise divide            (.m:14-20,38-40)
+//   K2 s = vec(A S B)             -> Xs kept from the previous iteration (.m:22,38,58)
+//   K2' k = vec(A^H K B^H)        -> contract_cols + A^H            (.m:47)
+//   R v  = vec(A^H A V B B^H)     -> expand_cols with BBH + A^H A   (.m:25,47,48)
+//   'std': v = U\(L\k)            -> V = pinv(A) K pinv(B)          (.m:29,53)
+// Per iteration five kernels run on the main stream and the Jacobi eigen-solve of the
+// NEXT iteration's SVT runs on a side stream (its Gram matrix is already known once the
+// X / V1 update is done), so the sequential eigen-solve never sits on the critical path.
+#include "common.cuh"
+#include "gemm_cores.cuh"
+#include "jacobi.cuh"
+
+namespace jstsp {
+
+template <typename T> struct DT { static constexpr int CB = 2; static constexpr int KB = 2; };
+
+// ---------------------------------------------------------------------------------------
+// parameter block shared by all ADMM kernels
+// ---------------------------------------------------------------------------------------
+template <typename T>
+struct AdmmP {
+    int N, M, G, P, RP, NG, GP8, GNG;   // RP = round_up8(N), NG = RP/8 ; GP8/GNG same for G
+    int MC, nmc;                        // column chunk of the X-update/T1 kernel
+    int type, angles, n_indx;
+    int iter, imax;
+    const cx<T>* subY; long long ld_subY;
+    const T* omega;    long long ld_omega;
+    const cx<T>* A;    long long ld_A;
+    const cx<T>* B;    long long ld_B;
+    const int* indx;   long long ld_indx;
+    const double *rho, *tauY, *tauS;
+    cx<T> *X, *V1, *V2, *C, *Xs;        // N x M per trial
+    cx<T>* W;                           // N x N per trial (SVT spectral weights)
+    double* gram;                       // [b][nmc][2*N*N] partial Gram of the next SVT input
+    cx<T>* T1;                          // [b][nmc][N*P] partial K B^H
+    cx<T> *V, *Res, *S, *AS;            // G x P (AS: N x P)
+    cx<T>* AHA; long long ld_AHA;       // G x G
+    cx<T>* BBH; long long ld_BBH;       // P x P
+    cx<T>* pA;  long long ld_pA;        // 'std': pinv(A)  G x N
+    cx<T>* BBHinv;                      // 'std': inv(B B^H) P x P (stride ld_BBH)
+    double* dots; int npc;              // [b][npc][4] partial <Res,Res>, <Res,Q>, |V|^2
+    unsigned char* smask;               // angles: [b][G*P] support mask
+    cx<T>* Yout; long long ld_Y;
+    double* convd;                      // [b][imax][3] diagnostics in double (or null)
+    double* cgramA;                     // [b][2][nmc][2*N*N] partial Grams of V1 and X   (conv only)
+    double* cgramB; int nxc;            // [b][nxc][2*N*N]    partial Gram of V2           (conv only)
+};
+
+// ---------------------------------------------------------------------------------------
+// setup kernels
+// ---------------------------------------------------------------------------------------
+// AHA = A^H A  (G x G), one CTA per trial
+template <typename T>
+__global__ void k_aha(AdmmP<T> p) {
+    const int b = blockIdx.x;
+    const cx<T>* A = p.A + (long long)b * p.ld_A;
+    cx<T>* out = p.AHA + (long long)b * p.ld_AHA;
+    for (int t = threadIdx.x; t < p.G * p.G; t += blockDim.x) {
+        int i = t % p.G, j = t / p.G;
+        T re = 0, im = 0;
+        for (int n = 0; n < p.N; ++n) {
+            cx<T> a = A[n + (long long)p.N * i], c = A[n + (long long)p.N * j];
+            cmac<T>(re, im, a.re, -a.im, c.re, c.im);
+        }
+        out[t] = mk<T>(re, im);
+    }
+}
+
+// BBH = B B^H (P x P).  64x64 output tile per CTA, 16-deep k tiles, 4x4 outputs per thread.
+template <typename T>
+__global__ void __launch_bounds__(256) k_bbh(AdmmP<T> p) {
+    constexpr int TS = 64, KT = 16;
+    __shared__ T are[KT][TS + 4], aim[KT][TS + 4], bre[KT][TS + 4], bim[KT][TS + 4];
+    const int b = blockIdx.z;
+    const cx<T>* B = p.B + (long long)b * p.ld_B;
+    cx<T>* out = p.BBH + (long long)b * p.ld_BBH;
+    const int i0 = blockIdx.x * TS, j0 = blockIdx.y * TS;
+    if (j0 + TS <= i0) return;   // strictly-lower tiles are filled by mirroring
+    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+    T cr[4][4] = {}, ci[4][4] = {};
+    for (int m0 = 0; m0 < p.M; m0 += KT) {
+        for (int idx = threadIdx.x; idx < TS * KT; idx += 256) {
+            int r = idx % TS, k = idx / TS;
+            cx<T> va = mk<T>(T(0), T(0)), vb = va;
+            if (m0 + k < p.M) {
+                if (i0 + r < p.P) va = B[(i0 + r) + (long long)p.P * (m0 + k)];
+                if (j0 + r < p.P) vb = B[(j0 + r) + (long long)p.P * (m0 + k)];
+            }
+            are[k][r] = va.re; aim[k][r] = va.im; bre[k][r] = vb.re; bim[k][r] = vb.im;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            T xr[4], xi[4], yr[4], yi[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { xr[u] = are[k][tx * 4 + u]; xi[u] = aim[k][tx * 4 + u]; yr[u] = bre[k][ty * 4 + u]; yi[u] = bim[k][ty * 4 + u]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) cmac<T>(cr[u][v], ci[u][v], xr[u], xi[u], yr[v], -yi[v]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            int i = i0 + tx * 4 + u, j = j0 + ty * 4 + v;
+            if (i < p.P && j < p.P) {
+                out[i + (long long)p.P * j] = mk<T>(cr[u][v], ci[u][v]);
+                if (j0 >= i0 + TS) out[j + (long long)p.P * i] = mk<T>(cr[u][v], -ci[u][v]);
+            }
+        }
+}
+
+// ---------------------------------------------------------------------------------------
+// eigen-solve of the Gram matrix -> spectral weights W (one CTA per trial)
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) k_svt_weights(AdmmP<T> p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    JacobiSmem sm; sm.carve(smem, p.N);
+    const int b = blockIdx.x, n = p.N, nn = n * n;
+    const double* g = p.gram + (size_t)b * p.nmc * 2 * nn;
+    for (int t = threadIdx.x; t < nn; t += blockDim.x) {
+        double re = 0.0, im = 0.0;
+        for (int c = 0; c < p.nmc; ++c) { re += g[(size_t)c * 2 * nn + 2 * t]; im += g[(size_t)c * 2 * nn + 2 * t + 1]; }
+        sm.Are[t] = re; sm.Aim[t] = im;
+    }
+    __syncthreads();
+    jacobi_hermitian_block(sm, n);
+    const double tau = p.tauY[b] / p.rho[b];
+    cx<T>* W = p.W + (size_t)b * nn;
+    svt_weights_block(sm, n, tau, [&](int i, int j, double re, double im) { W[i + n * j] = mk<T>((T)re, (T)im); });
+}
+
+// largest eigenvalue of up to 3 partial-summed Gram matrices (convergence diagnostics,
+// proposed_algorithm.m:67-69 use the spectral norm).  grid (3, batch).
+template <typename T>
+__global__ void __launch_bounds__(128) k_conv_norms(AdmmP<T> p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    JacobiSmem sm; sm.carve(smem, p.N);
+    const int which = blockIdx.x, b = blockIdx.y, n = p.N, nn = n * n;   // 0: V1, 1: V2, 2: X
+    const int nparts = which == 1 ? p.nxc : p.nmc;
+    const double* g = which == 1 ? p.cgramB + (size_t)b * p.nxc * 2 * nn
+                                 : p.cgramA + ((size_t)b * 2 + (which == 2 ? 1 : 0)) * p.nmc * 2 * nn;
+    for (int t = threadIdx.x; t < nn; t += blockDim.x) {
+        double re = 0.0, im = 0.0;
+        for (int c = 0; c < nparts; ++c) { re += g[(size_t)c * 2 * nn + 2 * t]; im += g[(size_t)c * 2 * nn + 2 * t + 1]; }
+        sm.Are[t] = re; sm.Aim[t] = im;
+    }
+    __syncthreads();
+    jacobi_hermitian_block(sm, n);
+    if (threadIdx.x == 0) {
+        double mx = 0.0;
+        for (int k = 0; k < n; ++k) mx = fmax(mx, sm.Are[k + n * k]);
+        // scratch slot: convd[b][iter][*] is finalised by k_conv_finish
+        p.convd[((size_t)b * p.imax + p.iter) * 3 + which] = mx;   // sigma_max^2
+    }
+}
+
+template <typename T>
+__global__ void k_conv_finish(AdmmP<T> p) {
+    const int b = blockIdx.x;   // one single-thread CTA per trial
+    double* c = p.convd + ((size_t)b * p.imax + p.iter) * 3;
+    double v1 = c[0], v2 = c[1], x = c[2];
+    const double* d = p.dots + (size_t)b * p.npc * 4;
+    double rr = 0.0, rq = 0.0, vv = 0.0;
+    for (int k = 0; k < p.npc; ++k) { rr += d[4 * k]; rq += d[4 * k + 1]; vv += d[4 * k + 2]; }
+    c[0] = v1 / x;    // norm(V1)^2/norm(X)^2   (.m:67)
+    c[1] = v2 / x;    // norm(V2)^2/norm(X)^2   (.m:69)
+    if (p.type == JSTSP_APPROXIMATE) {
+        double alpha = rr / rq;
+        c[2] = (alpha * alpha * rr) / vv;   // norm(prev_v - v)^2 / norm(prev_v)^2 (.m:51)
+    } else c[2] = 0.0;
+}
+
+// ---------------------------------------------------------------------------------------
+// kernel 1: SVT apply + X update + V1 dual update + next Gram + T1 = K B^H   (grid nmc x batch)
+// ---------------------------------------------------------------------------------------
+template <typename T>
+struct XupdSmem {
+    static size_t bytes(int RP, int N, int MC, bool conv) {
+        size_t planes = (size_t)(conv ? 10 : 6) * RP * MC * sizeof(T);   // Z, K, Zn (+X, V1 for conv) planar re/im
+        return planes + sizeof(cx<T>) * (size_t)N * N;
+    }
+};
+
+template <typename T, int KB>
+__global__ void __launch_bounds__(kThreads) k_xupd_t1(AdmmP<T> p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int N = p.N, RP = p.RP, MC = p.MC;
+    const int c0 = chunk * MC;
+    const int ncols = (p.M - c0) < MC ? (p.M - c0) : MC;
+    const bool conv = p.convd != nullptr;
+    T* Zre = reinterpret_cast<T*>(smem);
+    T* Zim = Zre + (size_t)RP * MC;
+    T* Kre = Zim + (size_t)RP * MC;
+    T* Kim = Kre + (size_t)RP * MC;
+    T* Nre = Kim + (size_t)RP * MC;
+    T* Nim = Nre + (size_t)RP * MC;
+    T* Cre = Nim + (size_t)RP * MC;      // conv only: X and V1 planes (4 planes)
+    cx<T>* Ws = reinterpret_cast<cx<T>*>(Nim + (size_t)RP * MC * (conv ? 5 : 1));
+    const T rho = (T)p.rho[b];
+    const T irho = T(1) / rho;
+    const size_t off = (size_t)b * N * p.M + (size_t)c0 * N;
+    cx<T>* X = p.X + off; cx<T>* V1 = p.V1 + off;
+    const cx<T>* V2 = p.V2 + off; const cx<T>* C = p.C + off; const cx<T>* Xs = p.Xs + off;
+    const cx<T>* subY = p.subY + (long long)b * p.ld_subY + (size_t)c0 * N;
+    const T* om = p.omega + (long long)b * p.ld_omega + (size_t)c0 * N;
+    const cx<T>* Wg = p.W + (size_t)b * N * N;
+    // stage W and Z = X - V1/rho (planar); zero the padded rows
+    for (int t = threadIdx.x; t < N * N; t += kThreads) Ws[t] = Wg[t];
+    for (int t = threadIdx.x; t < RP * MC; t += kThreads) {
+        int r = t % RP, c = t / RP;
+        T zr = 0, zi = 0;
+        if (r < N && c < ncols) {
+            cx<T> x = X[(size_t)c * N + r], v = V1[(size_t)c * N + r];
+            zr = x.re - irho * v.re; zi = x.im - irho * v.im;
+        }
+        Zre[t] = zr; Zim[t] = zi; Kre[t] = 0; Kim[t] = 0; Nre[t] = 0; Nim[t] = 0;
+        if (conv) { Cre[t] = 0; Cre[t + (size_t)RP * MC] = 0; Cre[t + 2 * (size_t)RP * MC] = 0; Cre[t + 3 * (size_t)RP * MC] = 0; }
+    }
+    __syncthreads();
+    // element-wise: Y = W Z ; X ; V1 ; K ; Znext          (proposed_algorithm.m:35-43,64)
+    const bool last = (p.iter == p.imax - 1) && p.Yout != nullptr;
+    for (int t = threadIdx.x; t < N * ncols; t += kThreads) {
+        int r = t % N, c = t / N;
+        T yr = 0, yi = 0;
+        for (int k = 0; k < N; ++k) {
+            cx<T> w = Ws[r + N * k];
+            cmac<T>(yr, yi, w.re, w.im, Zre[c * RP + k], Zim[c * RP + k]);
+        }
+        size_t gi = (size_t)c * N + r;
+        cx<T> v1 = V1[gi], v2 = V2[gi], cc = C[gi], xs = Xs[gi], sy = subY[gi];
+        T d = T(1) / (om[gi] + T(2) * rho);                                  // iK1 (.m:20)
+        T xr = (v1.re + rho * yr + sy.re + v2.re + rho * cc.re + rho * xs.re) * d;   // .m:38-40
+        T xi = (v1.im + rho * yi + sy.im + v2.im + rho * cc.im + rho * xs.im) * d;
+        T kr = xr - irho * v2.re - cc.re, ki = xi - irho * v2.im - cc.im;    // .m:43
+        T n1r = v1.re + rho * (yr - xr), n1i = v1.im + rho * (yi - xi);      // .m:64
+        X[gi] = mk<T>(xr, xi);
+        V1[gi] = mk<T>(n1r, n1i);
+        if (last) p.Yout[(long long)b * p.ld_Y + (size_t)(c0 + c) * N + r] = mk<T>(yr, yi);
+        Kre[c * RP + r] = kr; Kim[c * RP + r] = ki;
+        Nre[c * RP + r] = xr - irho * n1r; Nim[c * RP + r] = xi - irho * n1i;   // next SVT input (.m:35)
+        if (conv) {
+            Cre[c * RP + r] = xr; Cre[(size_t)RP * MC + c * RP + r] = xi;
+            Cre[2 * (size_t)RP * MC + c * RP + r] = n1r; Cre[3 * (size_t)RP * MC + c * RP + r] = n1i;
+        }
+    }
+    __syncthreads();
+    // partial Gram of the next SVT input
+    gram_partial<T>(Nre, Nim, RP, N, ncols, p.gram + ((size_t)b * p.nmc + chunk) * 2 * N * N);
+    if (conv) {
+        size_t cg = (size_t)p.nmc * 2 * N * N;
+        double* base = p.cgramA + (size_t)b * 2 * cg + (size_t)chunk * 2 * N * N;
+        gram_partial<T>(Cre + 2 * (size_t)RP * MC, Cre + 3 * (size_t)RP * MC, RP, N, ncols, base);            // V1
+        gram_partial<T>(Cre, Cre + (size_t)RP * MC, RP, N, ncols, base + cg);                                 // X
+    }
+    // T1 partial = K(:,chunk) * B(:,chunk)^H                               (.m:47 / :53)
+    const cx<T>* Bc = p.B + (long long)b * p.ld_B + (long long)c0 * p.P;
+    cx<T>* T1 = p.T1 + ((size_t)b * p.nmc + chunk) * (size_t)N * p.P;
+    contract_cols<T, KB>(Kre, Kim, RP, p.NG, ncols, Bc, (long long)p.P, p.P, N,
+                         [&](int r, int k, T re, T im) { T1[r + (size_t)N * k] = mk<T>(re, im); });
+}
+
+// ---------------------------------------------------------------------------------------
+// kernel 2: Res = A^H T1 - AHA (V BBH)   ['approximate']  /  V = pA (T1 BBHinv)  ['std']
+//           grid (npc, batch); chunk of CC columns of the G x P grid
+// ---------------------------------------------------------------------------------------
+template <typename T, int CB>
+__global__ void __launch_bounds__(kThreads) k_res(AdmmP<T> p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int N = p.N, G = p.G, P = p.P;
+    const bool approx = p.type == JSTSP_APPROXIMATE;
+    // rows of the left operand: G for V (approximate) or N for T1 (std)
+    const int R = approx ? G : N, RP = approx ? p.GP8 : p.RP, NG = approx ? p.GNG : p.NG;
+    const int CC = ExpandSmem<T, CB>::chunk_cols(NG);
+    const int c0 = chunk * CC;
+    const int ncols = (P - c0) < CC ? (P - c0) : CC;
+    const cx<T>* Big = (approx ? p.BBH : p.BBHinv) + (long long)b * p.ld_BBH + (long long)c0 * P;
+    const cx<T>* V = p.V + (size_t)b * G * P;
+    const cx<T>* T1 = p.T1 + (size_t)b * p.nmc * N * P;
+    const int nmc = p.nmc;
+    T ar[kRB][CB], ai[kRB][CB];
+    if (approx) {
+        expand_cols<T, CB>(smem, RP, NG, R, P, [&](int r, int k) { return V[r + (size_t)G * k]; }, Big, (long long)P, ncols, ar, ai);
+    } else {
+        expand_cols<T, CB>(smem, RP, NG, R, P,
+                           [&](int r, int k) {
+                               T re = 0, im = 0;
+                               for (int c = 0; c < nmc; ++c) { cx<T> v = T1[(size_t)c * N * P + r + (size_t)N * k]; re += v.re; im += v.im; }
+                               return mk<T>(re, im);
+                           },
+                           Big, (long long)P, ncols, ar, ai);
+    }
+    __syncthreads();
+    // park the product tile (R x CC) and, for 'approximate', the summed T1 tile (N x CC) in smem
+    cx<T>* prod = reinterpret_cast<cx<T>*>(smem);
+    cx<T>* t1s = prod + (size_t)R * CC;
+    cx<T>* small = t1s + (size_t)N * CC;      // A (N x G) then AHA (G x G)   | 'std': pA (G x N)
+    const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+    const int rg = warp % NG, cg = warp / NG;
+    if (cg < ExpandSmem<T, CB>::ncg(NG)) {
+#pragma unroll
+        for (int j = 0; j < CB; ++j) {
+            int c = cg * kWarp * CB + j * kWarp + lane;
+#pragma unroll
+            for (int r = 0; r < kRB; ++r) {
+                int row = rg * kRB + r;
+                if (row < R) prod[row + (size_t)R * c] = mk<T>(ar[r][j], ai[r][j]);
+            }
+        }
+    }
+    if (approx) {
+        for (int t = threadIdx.x; t < N * ncols; t += kThreads) {
+            int r = t % N, c = t / N;
+            T re = 0, im = 0;
+            for (int k = 0; k < nmc; ++k) { cx<T> v = T1[(size_t)k * N * P + r + (size_t)N * (c0 + c)]; re += v.re; im += v.im; }
+            t1s[r + (size_t)N * c] = mk<T>(re, im);
+        }
+        const cx<T>* A = p.A + (long long)b * p.ld_A;
+        const cx<T>* AHA = p.AHA + (long long)b * p.ld_AHA;
+        for (int t = threadIdx.x; t < N * G; t += kThreads) small[t] = A[t];
+        for (int t = threadIdx.x; t < G * G; t += kThreads) small[N * G + t] = AHA[t];
+    } else {
+        const cx<T>* pA = p.pA + (long long)b * p.ld_pA;
+        for (int t = threadIdx.x; t < G * N; t += kThreads) small[t] = pA[t];
+    }
+    __syncthreads();
+    cx<T>* out = (approx ? p.Res : p.V) + (size_t)b * G * P + (size_t)c0 * G;
+    for (int t = threadIdx.x; t < G * ncols; t += kThreads) {
+        int g = t % G, c = t / G;
+        T re = 0, im = 0;
+        if (approx) {
+            for (int n = 0; n < N; ++n) { cx<T> a = small[n + N * g], v = t1s[n + (size_t)N * c]; cmac<T>(re, im, a.re, -a.im, v.re, v.im); }
+            for (int k = 0; k < G; ++k) { cx<T> a = small[N * G + g + G * k], v = prod[k + (size_t)R * c]; cmac<T>(re, im, -a.re, -a.im, v.re, v.im); }
+        } else {
+            for (int n = 0; n < N; ++n) { cx<T> a = small[g + G * n], v = prod[n + (size_t)R * c]; cmac<T>(re, im, a.re, a.im, v.re, v.im); }
+        }
+        out[g + (size_t)G * c] = mk<T>(re, im);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// kernel 3: Q = AHA (Res BBH); partial <Res,Res>, <Res,Q>, |V|^2   ['approximate' only]
+// ---------------------------------------------------------------------------------------
+template <typename T, int CB>
+__global__ void __launch_bounds__(kThreads) k_q(AdmmP<T> p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ double red[kWarps][3];
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int G = p.G, P = p.P, RP = p.GP8, NG = p.GNG;
+    const int CC = ExpandSmem<T, CB>::chunk_cols(NG);
+    const int c0 = chunk * CC;
+    const int ncols = (P - c0) < CC ? (P - c0) : CC;
+    const cx<T>* Big = p.BBH + (long long)b * p.ld_BBH + (long long)c0 * P;
+    const cx<T>* Res = p.Res + (size_t)b * G * P;
+    T ar[kRB][CB], ai[kRB][CB];
+    expand_cols<T, CB>(smem, RP, NG, G, P, [&](int r, int k) { return Res[r + (size_t)G * k]; }, Big, (long long)P, ncols, ar, ai);
+    __syncthreads();
+    cx<T>* prod = reinterpret_cast<cx<T>*>(smem);
+    cx<T>* small = prod + (size_t)G * CC;
+    const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+    const int rg = warp % NG, cg = warp / NG;
+    if (cg < ExpandSmem<T, CB>::ncg(NG)) {
+#pragma unroll
+        for (int j = 0; j < CB; ++j) {
+            int c = cg * kWarp * CB + j * kWarp + lane;
+#pragma unroll
+            for (int r = 0; r < kRB; ++r) {
+                int row = rg * kRB + r;
+                if (row < G) prod[row + (size_t)G * c] = mk<T>(ar[r][j], ai[r][j]);
+            }
+        }
+    }
+    const cx<T>* AHA = p.AHA + (long long)b * p.ld_AHA;
+    for (int t = threadIdx.x; t < G * G; t += kThreads) small[t] = AHA[t];
+    __syncthreads();
+    const cx<T>* V = p.V + (size_t)b * G * P + (size_t)c0 * G;
+    double rr = 0.0, rq = 0.0, vv = 0.0;
+    for (int t = threadIdx.x; t < G * ncols; t += kThreads) {
+        int g = t % G, c = t / G;
+        T re = 0, im = 0;
+        for (int k = 0; k < G; ++k) { cx<T> a = small[g + G * k], v = prod[k + (size_t)G * c]; cmac<T>(re, im, a.re, a.im, v.re, v.im); }
+        cx<T> r = Res[g + (size_t)G * (c0 + c)];
+        rr += (double)r.re * r.re + (double)r.im * r.im;
+        rq += (double)r.re * re + (double)r.im * im;          // Re(conj(res) * q)
+        if (p.convd) { cx<T> v = V[g + (size_t)G * c]; vv += (double)v.re * v.re + (double)v.im * v.im; }
+    }
+    for (int o = 16; o > 0; o >>= 1) { rr += __shfl_down_sync(0xffffffffu, rr, o); rq += __shfl_down_sync(0xffffffffu, rq, o); vv += __shfl_down_sync(0xffffffffu, vv, o); }
+    if (lane == 0) { red[warp][0] = rr; red[warp][1] = rq; red[warp][2] = vv; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, c = 0, d = 0;
+        for (int w = 0; w < kWarps; ++w) { a += red[w][0]; c += red[w][1]; d += red[w][2]; }
+        double* o = p.dots + ((size_t)b * p.npc + chunk) * 4;
+        o[0] = a; o[1] = c; o[2] = d; o[3] = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// kernel 4: V += alpha Res ; S = soft(V) (masked) ; AS = A S     grid (ceil(P/PV), batch)
+// ---------------------------------------------------------------------------------------
+constexpr int kPV = 32;   // grid columns per CTA in k_vupd
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_vupd(AdmmP<T> p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ double s_alpha;
+    const int b = blockIdx.y, c0 = blockIdx.x * kPV;
+    const int N = p.N, G = p.G, P = p.P;
+    const int ncols = (P - c0) < kPV ? (P - c0) : kPV;
+    cx<T>* Ss = reinterpret_cast<cx<T>*>(smem);      // G x kPV
+    cx<T>* As = Ss + (size_t)G * kPV;                // N x G
+    const cx<T>* A = p.A + (long long)b * p.ld_A;
+    for (int t = threadIdx.x; t < N * G; t += kThreads) As[t] = A[t];
+    const bool approx = p.type == JSTSP_APPROXIMATE;
+    if (approx && threadIdx.x == 0) {
+        const double* d = p.dots + (size_t)b * p.npc * 4;
+        double rr = 0.0, rq = 0.0;
+        for (int k = 0; k < p.npc; ++k) { rr += d[4 * k]; rq += d[4 * k + 1]; }
+        s_alpha = rr / rq;                            // alpha = res'res/(res'R res)  (.m:48); 0/0 -> NaN like MATLAB
+    }
+    __syncthreads();
+    const T thr = (T)(p.tauS[b] / p.rho[b]);
+    cx<T>* V = p.V + (size_t)b * G * P + (size_t)c0 * G;
+    cx<T>* S = p.S + (size_t)b * G * P + (size_t)c0 * G;
+    const cx<T>* Res = p.Res + (size_t)b * G * P + (size_t)c0 * G;
+    const unsigned char* mask = p.angles ? p.smask + (size_t)b * G * P + (size_t)c0 * G : nullptr;
+    for (int t = threadIdx.x; t < G * ncols; t += kThreads) {
+        cx<T> v = V[t];
+        if (approx) {
+            T alpha = (T)s_alpha;
+            cx<T> r = Res[t];
+            v = mk<T>(v.re + alpha * r.re, v.im + alpha * r.im);      // .m:50
+            V[t] = v;
+        }
+        cx<T> s = mk<T>(soft1<T>(v.re, thr), soft1<T>(v.im, thr));    // .m:56
+        if (mask && !mask[t]) s = mk<T>(T(0), T(0));                  // K3*s (_angles.m:68)
+        S[t] = s; Ss[t] = s;
+    }
+    __syncthreads();
+    cx<T>* AS = p.AS + (size_t)b * N * P + (size_t)c0 * N;
+    for (int t = threadIdx.x; t < N * ncols; t += kThreads) {
+        int n = t % N, c = t / N;
+        T re = 0, im = 0;
+        for (int g = 0; g < G; ++g) { cx<T> a = As[n + N * g], s = Ss[g + (size_t)G * c]; cmac<T>(re, im, a.re, a.im, s.re, s.im); }
+        AS[t] = mk<T>(re, im);
+    }
+}
+
+// angles: grow the support mask  Omega_S(indx_S(1:min(10+5i, G*P))) = 1  (_angles.m:36), i = iter+1
+template <typename T>
+__global__ void k_mask_grow(AdmmP<T> p) {
+    const int b = blockIdx.y;
+    const int i1 = p.iter + 1;
+    int hi = 10 + 5 * i1; if (hi > p.G * p.P) hi = p.G * p.P; if (hi > p.n_indx) hi = p.n_indx;
+    int lo = (p.iter == 0) ? 0 : 10 + 5 * p.iter;
+    const int* idx = p.indx + (long long)b * p.ld_indx;
+    unsigned char* m = p.smask + (size_t)b * p.G * p.P;
+    for (int k = lo + blockIdx.x * blockDim.x + threadIdx.x; k < hi; k += gridDim.x * blockDim.x) {
+        int v = idx[k];
+        if (v >= 1 && v <= p.G * p.P) m[v - 1] = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// kernel 5: Xs = AS B ; C ; V2 dual update          grid (nxc, batch)
+// ---------------------------------------------------------------------------------------
+template <typename T, int CB>
+__global__ void __launch_bounds__(kThreads) k_xs(AdmmP<T> p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int N = p.N, P = p.P, RP = p.RP, NG = p.NG;
+    const int CC = ExpandSmem<T, CB>::chunk_cols(NG);
+    const int c0 = chunk * CC;
+    const int ncols = (p.M - c0) < CC ? (p.M - c0) : CC;
+    const cx<T>* Big = p.B + (long long)b * p.ld_B + (long long)c0 * P;
+    const cx<T>* AS = p.AS + (size_t)b * N * P;
+    T ar[kRB][CB], ai[kRB][CB];
+    expand_cols<T, CB>(smem, RP, NG, N, P, [&](int r, int k) { return AS[r + (size_t)N * k]; }, Big, (long long)P, ncols, ar, ai);
+    const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+    const int rg = warp % NG, cg = warp / NG;
+    const bool conv = p.convd != nullptr;
+    T* Vre = reinterpret_cast<T*>(smem);            // conv: V2 tile planar (RP x CC), reuses the GEMM staging area
+    T* Vim = Vre + (size_t)RP * CC;
+    if (conv) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < 2 * RP * CC; t += kThreads) Vre[t] = 0;
+        __syncthreads();
+    }
+    if (cg < ExpandSmem<T, CB>::ncg(NG)) {
+        const T rho = (T)p.rho[b];
+        const T irho = T(1) / rho, kap = rho / (rho + T(1));
+        const size_t off = (size_t)b * N * p.M + (size_t)c0 * N;
+        const cx<T>* X = p.X + off; cx<T>* V2 = p.V2 + off; cx<T>* C = p.C + off; cx<T>* Xs = p.Xs + off;
+#pragma unroll
+        for (int j = 0; j < CB; ++j) {
+            int c = cg * kWarp * CB + j * kWarp + lane;
+            if (c < ncols) {
+#pragma unroll
+                for (int r = 0; r < kRB; ++r) {
+                    int row = rg * kRB + r;
+                    if (row < N) {
+                        size_t gi = (size_t)c * N + row;
+                        cx<T> x = X[gi], v2 = V2[gi];
+                        T sr = ar[r][j], si = ai[r][j];
+                        T cr = kap * (x.re - sr - irho * v2.re), ci = kap * (x.im - si - irho * v2.im);   // .m:61
+                        T nr = v2.re + rho * (cr - x.re + sr), ni = v2.im + rho * (ci - x.im + si);       // .m:65
+                        Xs[gi] = mk<T>(sr, si); C[gi] = mk<T>(cr, ci); V2[gi] = mk<T>(nr, ni);
+                        if (conv) { Vre[c * RP + row] = nr; Vim[c * RP + row] = ni; }
+                    }
+                }
+            }
+        }
+    }
+    if (conv) {
+        __syncthreads();
+        gram_partial<T>(Vre, Vim, RP, N, ncols, p.cgramB + ((size_t)b * p.nxc + chunk) * 2 * N * N);
+    }
+}
+
+// non-finite detector over the S outputs
+template <typename T>
+__global__ void k_count_nonfinite(const cx<T>* S, size_t per_trial, int batch, int* flag) {
+    int b = blockIdx.x;
+    if (b >= batch) return;
+    const cx<T>* s = S + (size_t)b * per_trial;
+    int bad = 0;
+    for (size_t t = threadIdx.x; t < per_trial; t += blockDim.x) { cx<T> v = s[t]; if (!isfinite(v.re) || !isfinite(v.im)) bad = 1; }
+    bad = __syncthreads_or(bad);
+    if (threadIdx.x == 0 && bad) atomicAdd(flag, 1);
+}
+
+// Gauss-Jordan inverse of a Hermitian positive-definite matrix held in global memory
+// (n x n, column-major), in place; one CTA per matrix.  Used once per trial by the 'std'
+// branch for inv(B B^H) and inv(A^H A)  (proposed_algorithm.m:29,53: the LS solution).
+template <typename T>
+__global__ void __launch_bounds__(256) k_hpd_inverse(cx<T>* mats, long long ld, int n) {
+    cx<T>* a = mats + (long long)blockIdx.x * ld;
+    __shared__ double piv_re, piv_im;
+    extern __shared__ __align__(16) unsigned char smem[];
+    cx<T>* colk = reinterpret_cast<cx<T>*>(smem);   // n entries: pivot column snapshot
+    cx<T>* rowk = colk + n;                         // n entries: pivot row snapshot
+    for (int k = 0; k < n; ++k) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) { colk[i] = a[i + (long long)n * k]; rowk[i] = a[k + (long long)n * i]; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            cx<T> pv = colk[k];
+            double d = (double)pv.re * pv.re + (double)pv.im * pv.im;
+            piv_re = pv.re / d; piv_im = -pv.im / d;   // 1/pivot
+        }
+        __syncthreads();
+        const T ir = (T)piv_re, ii = (T)piv_im;
+        for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
+            int i = t % n, j = t / n;
+            cx<T> v;
+            if (i == k && j == k) v = mk<T>(ir, ii);
+            else if (i == k) v = rowk[j] * mk<T>(ir, ii);                       // row k scaled
+            else if (j == k) v = mk<T>(T(0), T(0)) - colk[i] * mk<T>(ir, ii);   // column k
+            else v = a[t] - colk[i] * (rowk[j] * mk<T>(ir, ii));
+            a[t] = v;
+        }
+    }
+}
+
+// pA = inv(AHA) A^H  (G x N), one CTA per trial
+template <typename T>
+__global__ void k_pinv_left(AdmmP<T> p, const cx<T>* AHAinv, long long ld_inv) {
+    const int b = blockIdx.x;
+    const cx<T>* A = p.A + (long long)b * p.ld_A;
+    const cx<T>* Ii = AHAinv + (long long)b * ld_inv;
+    cx<T>* out = p.pA + (long long)b * p.ld_pA;
+    for (int t = threadIdx.x; t < p.G * p.N; t += blockDim.x) {
+        int g = t % p.G, n = t / p.G;
+        T re = 0, im = 0;
+        for (int k = 0; k < p.G; ++k) { cx<T> a = Ii[g + (long long)p.G * k], c = A[n + (long long)p.N * k]; cmac<T>(re, im, a.re, a.im, c.re, -c.im); }
+        out[t] = mk<T>(re, im);
+    }
+}
+
+// convd [b][iter][3] (double) -> caller's conv: imax x 3 column-major in T
+template <typename T>
+__global__ void k_conv_out(const double* convd, T* out, long long ld, int imax) {
+    const int b = blockIdx.x;
+    for (int t = threadIdx.x; t < imax * 3; t += blockDim.x) {
+        int it = t % imax, k = t / imax;
+        out[(long long)b * ld + t] = (T)convd[((size_t)b * imax + it) * 3 + k];
+    }
+}
+
+template <typename Tsrc, typename Tdst>
+__global__ void k_convert(const Tsrc* src, Tdst* dst, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = (Tdst)src[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------------------
+template <typename T>
+static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* subY_, const void* omega_, const int* indx_,
+                    const void* A_, const void* B_, const double* tauY_, const double* tauS_, const double* rho_,
+                    void* S_, void* Y_, void* conv_, bool angles) {
+    constexpr int CB = DT<T>::CB, KB = DT<T>::KB;
+    const int N = d->N, M = d->M, G = d->G, P = d->P, batch = d->batch, imax = d->imax;
+    if (N <= 0 || M <= 0 || G <= 0 || P <= 0 || batch <= 0 || imax < 0) return fail(h, JSTSP_E_ARG, "non-positive dimension");
+    if (!subY_ || !omega_ || !A_ || !B_ || !tauY_ || !tauS_ || !rho_ || !S_) return fail(h, JSTSP_E_ARG, "NULL buffer");
+    if (angles && (!indx_ || d->n_indx <= 0)) return fail(h, JSTSP_E_ARG, "indx_S missing");
+    if (N > 64 || G > 64) return fail(h, JSTSP_E_UNSUPPORTED, "proposed_algorithm kernels cover N <= 64 and G <= 64 rows");
+    const bool approx = d->type == JSTSP_APPROXIMATE;
+    if (!approx && (G > N || P > M)) return fail(h, JSTSP_E_UNSUPPORTED, "'std' branch needs full column rank A (G<=N) and full row rank B (P<=M)");
+    const bool host = mem == JSTSP_HOST;
+    const bool want_conv = conv_ != nullptr;
+    cudaStream_t st = h->stream;
+
+    AdmmP<T> p{};
+    p.N = N; p.M = M; p.G = G; p.P = P; p.RP = round_up8(N); p.NG = p.RP / 8; p.GP8 = round_up8(G); p.GNG = p.GP8 / 8;
+    p.type = d->type; p.angles = angles ? 1 : 0; p.n_indx = d->n_indx; p.imax = imax;
+    // chunk geometry
+    const int XC = ExpandSmem<T, CB>::chunk_cols(p.NG);           // columns per CTA of k_xs
+    const int nxc = ceil_div(M, XC);
+    int MC = 128;
+    while (MC > 16 && XupdSmem<T>::bytes(p.RP, N, MC, want_conv) > 96 * 1024) MC /= 2;
+    p.MC = MC; p.nmc = ceil_div(M, MC); p.nxc = nxc;
+    const int PCr = ExpandSmem<T, CB>::chunk_cols(approx ? p.GNG : p.NG);
+    const int npc = ceil_div(P, ExpandSmem<T, CB>::chunk_cols(p.GNG));
+    p.npc = npc;
+
+    // per-trial workspace
+    size_t NM = (size_t)N * M, GPn = (size_t)G * P;
+    int chunk_trials = batch;
+    if (h->max_chunk > 0 && chunk_trials > h->max_chunk) chunk_trials = h->max_chunk;
+    auto layout = [&](Arena& a, int nb, AdmmP<T>& q) {
+        q.X = a.take<cx<T>>(NM * nb); q.V1 = a.take<cx<T>>(NM * nb); q.V2 = a.take<cx<T>>(NM * nb);
+        q.C = a.take<cx<T>>(NM * nb); q.Xs = a.take<cx<T>>(NM * nb);
+        q.W = a.take<cx<T>>((size_t)N * N * nb);
+        q.gram = a.take<double>((size_t)nb * q.nmc * 2 * N * N);
+        q.T1 = a.take<cx<T>>((size_t)nb * q.nmc * N * P);
+        q.V = a.take<cx<T>>(GPn * nb); q.Res = a.take<cx<T>>(GPn * nb); q.S = a.take<cx<T>>(GPn * nb);
+        q.AS = a.take<cx<T>>((size_t)N * P * nb);
+        q.dots = a.take<double>((size_t)nb * npc * 4);
+        bool sharedA = d->ld_A == 0, sharedB = d->ld_B == 0;
+        q.AHA = a.take<cx<T>>((size_t)G * G * (sharedA ? 1 : nb)); q.ld_AHA = sharedA ? 0 : (long long)G * G;
+        q.BBH = a.take<cx<T>>((size_t)P * P * (sharedB ? 1 : nb)); q.ld_BBH = sharedB ? 0 : (long long)P * P;
+        if (!approx) {
+            q.pA = a.take<cx<T>>((size_t)G * N * (sharedA ? 1 : nb)); q.ld_pA = sharedA ? 0 : (long long)G * N;
+            q.BBHinv = q.BBH;   // inverted in place
+        }
+        if (angles) q.smask = a.take<unsigned char>(GPn * nb);
+        if (want_conv) {
+            q.convd = a.take<double>((size_t)nb * imax * 3);
+            q.cgramA = a.take<double>((size_t)nb * 2 * q.nmc * 2 * N * N);
+            q.cgramB = a.take<double>((size_t)nb * q.nxc * 2 * N * N);
+        }
+        // staging for host inputs / outputs
+        if (host) {
+            q.subY = a.take<cx<T>>(d->ld_subY ? NM * nb : NM);
+            q.omega = a.take<T>(d->ld_omega ? NM * nb : NM);
+            q.A = a.take<cx<T>>((size_t)N * G * (d->ld_A ? nb : 1));
+            q.B = a.take<cx<T>>((size_t)P * M * (d->ld_B ? nb : 1));
+            q.rho = a.take<double>(nb); q.tauY = a.take<double>(nb); q.tauS = a.take<double>(nb);
+            if (angles) q.indx = a.take<int>((size_t)d->n_indx * (d->ld_indx ? nb : 1));
+            if (Y_) q.Yout = a.take<cx<T>>(NM * nb);
+        }
+    };
+    // shrink the pass size until the workspace fits in ~70% of free memory
+    size_t freeb = 0, totalb = 0;
+    JSTSP_CUDA(h, cudaMemGetInfo(&freeb, &totalb));
+    size_t budget = (size_t)((freeb + h->ws_bytes) * 0.7);
+    for (;;) {
+        Arena probe(nullptr, 0); AdmmP<T> q = p; layout(probe, chunk_trials, q);
+        if (probe.off <= budget || chunk_trials == 1) { int rc = ensure_workspace(h, probe.off); if (rc) return rc; break; }
+        chunk_trials = (chunk_trials + 1) / 2;
+    }
+
+    // shared-memory sizes
+    const size_t sm_x = XupdSmem<T>::bytes(p.RP, N, p.MC, want_conv);
+    size_t sm_xs = ExpandSmem<T, CB>::bytes(p.NG, p.RP);
+    if (want_conv) { size_t need = 2 * sizeof(T) * (size_t)p.RP * XC; if (need > sm_xs) sm_xs = need; }
+    const int RPr = approx ? p.GP8 : p.RP, NGr = approx ? p.GNG : p.NG, Rr = approx ? G : N;
+    size_t sm_res = ExpandSmem<T, CB>::bytes(NGr, RPr);
+    { size_t epi = sizeof(cx<T>) * ((size_t)Rr * PCr + (size_t)N * PCr + (size_t)N * G + (size_t)G * G); if (epi > sm_res) sm_res = epi; }
+    size_t sm_q = ExpandSmem<T, CB>::bytes(p.GNG, p.GP8);
+    { size_t epi = sizeof(cx<T>) * ((size_t)G * ExpandSmem<T, CB>::chunk_cols(p.GNG) + (size_t)G * G); if (epi > sm_q) sm_q = epi; }
+    const size_t sm_v = sizeof(cx<T>) * ((size_t)G * kPV + (size_t)N * G);
+    const size_t sm_j = JacobiSmem::bytes(N);
+    int rc;
+    if ((rc = set_smem(h, k_xupd_t1<T, KB>, sm_x))) return rc;
+    if ((rc = set_smem(h, k_xs<T, CB>, sm_xs))) return rc;
+    if ((rc = set_smem(h, k_res<T, CB>, sm_res))) return rc;
+    if ((rc = set_smem(h, k_q<T, CB>, sm_q))) return rc;
+    if ((rc = set_smem(h, k_vupd<T>, sm_v))) return rc;
+    if ((rc = set_smem(h, k_svt_weights<T>, sm_j))) return rc;
+    if ((rc = set_smem(h, k_conv_norms<T>, sm_j))) return rc;
+
+    JSTSP_CUDA(h, cudaMemsetAsync(h->d_flag, 0, sizeof(int), st));
+    const size_t esz = sizeof(cx<T>);
+    for (int b0 = 0; b0 < batch; b0 += chunk_trials) {
+        const int nb = (batch - b0) < chunk_trials ? (batch - b0) : chunk_trials;
+        Arena ar(h->ws, h->ws_bytes);
+        AdmmP<T> q = p;
+        layout(ar, nb, q);
+        q.ld_subY = d->ld_subY; q.ld_omega = d->ld_omega; q.ld_A = d->ld_A; q.ld_B = d->ld_B; q.ld_indx = d->ld_indx; q.ld_Y = d->ld_Y;
+        if (host) {
+            auto up = [&](const void* dst, const void* src, size_t elems_per, long long ld, size_t el) -> cudaError_t {
+                if (ld == 0) return cudaMemcpyAsync(const_cast<void*>(dst), src, elems_per * el, cudaMemcpyHostToDevice, st);
+                if ((size_t)ld == elems_per) return cudaMemcpyAsync(const_cast<void*>(dst), (const char*)src + (size_t)b0 * ld * el, elems_per * el * nb, cudaMemcpyHostToDevice, st);
+                return cudaMemcpy2DAsync(const_cast<void*>(dst), elems_per * el, (const char*)src + (size_t)b0 * ld * el, (size_t)ld * el, elems_per * el, nb, cudaMemcpyHostToDevice, st);
+            };
+            JSTSP_CUDA(h, up(q.subY, subY_, NM, d->ld_subY, esz));
+            JSTSP_CUDA(h, up(q.omega, omega_, NM, d->ld_omega, sizeof(T)));
+            JSTSP_CUDA(h, up(q.A, A_, (size_t)N * G, d->ld_A, esz));
+            JSTSP_CUDA(h, up(q.B, B_, (size_t)P * M, d->ld_B, esz));
+            JSTSP_CUDA(h, cudaMemcpyAsync(const_cast<double*>(q.rho), rho_ + b0, sizeof(double) * nb, cudaMemcpyHostToDevice, st));
+            JSTSP_CUDA(h, cudaMemcpyAsync(const_cast<double*>(q.tauY), tauY_ + b0, sizeof(double) * nb, cudaMemcpyHostToDevice, st));
+            JSTSP_CUDA(h, cudaMemcpyAsync(const_cast<double*>(q.tauS), tauS_ + b0, sizeof(double) * nb, cudaMemcpyHostToDevice, st));
+            if (angles) JSTSP_CUDA(h, up(q.indx, indx_, (size_t)d->n_indx, d->ld_indx, sizeof(int)));
+            if (q.ld_subY) q.ld_subY = NM; if (q.ld_omega) q.ld_omega = NM;
+            if (q.ld_A) q.ld_A = (long long)N * G; if (q.ld_B) q.ld_B = (long long)P * M;
+            if (q.ld_indx) q.ld_indx = d->n_indx;
+            q.ld_Y = NM;
+        } else {
+            q.subY = (const cx<T>*)subY_ + (long long)b0 * d->ld_subY;
+            q.omega = (const T*)omega_ + (long long)b0 * d->ld_omega;
+            q.A = (const cx<T>*)A_ + (long long)b0 * d->ld_A;
+            q.B = (const cx<T>*)B_ + (long long)b0 * d->ld_B;
+            q.rho = rho_ + b0; q.tauY = tauY_ + b0; q.tauS = tauS_ + b0;
+            if (angles) q.indx = indx_ + (long long)b0 * d->ld_indx;
+            q.Yout = Y_ ? (cx<T>*)Y_ + (long long)b0 * d->ld_Y : nullptr;
+        }
+        // state = 0 (proposed_algorithm.m:8-12)
+        JSTSP_CUDA(h, cudaMemsetAsync(q.X, 0, (size_t)((char*)(q.Xs + NM * nb) - (char*)q.X), st));   // X,V1,V2,C,Xs are adjacent
+        JSTSP_CUDA(h, cudaMemsetAsync(q.gram, 0, sizeof(double) * (size_t)nb * q.nmc * 2 * N * N, st));
+        JSTSP_CUDA(h, cudaMemsetAsync(q.V, 0, esz * GPn * nb, st));
+        JSTSP_CUDA(h, cudaMemsetAsync(q.S, 0, esz * GPn * nb, st));
+        if (angles) JSTSP_CUDA(h, cudaMemsetAsync(q.smask, 0, GPn * nb, st));
+        // one-off operators
+        const int nA = d->ld_A ? nb : 1, nB = d->ld_B ? nb : 1;
+        k_aha<T><<<nA, 256, 0, st>>>(q); h->launches++;
+        { dim3 g(ceil_div(P, 64), ceil_div(P, 64), nB); k_bbh<T><<<g, 256, 0, st>>>(q); h->launches++; }
+        if (!approx) {
+            size_t smi = 2 * sizeof(cx<T>) * (size_t)(P > G ? P : G);
+            if ((rc = set_smem(h, k_hpd_inverse<T>, smi))) return rc;
+            k_hpd_inverse<T><<<nB, 256, smi, st>>>(q.BBH, (long long)P * P, P); h->launches++;
+            k_hpd_inverse<T><<<nA, 256, smi, st>>>(q.AHA, (long long)G * G, G); h->launches++;
+            k_pinv_left<T><<<nA, 256, 0, st>>>(q, q.AHA, q.ld_AHA); h->launches++;
+        }
+        for (int it = 0; it < imax; ++it) {
+            q.iter = it;
+            if (angles) { dim3 g(1, nb); k_mask_grow<T><<<g, 64, 0, st>>>(q); h->launches++; }
+            k_svt_weights<T><<<nb, 128, sm_j, st>>>(q); h->launches++;
+            { dim3 g(q.nmc, nb); k_xupd_t1<T, KB><<<g, kThreads, sm_x, st>>>(q); h->launches++; }
+            { dim3 g(approx ? npc : ceil_div(P, PCr), nb); k_res<T, CB><<<g, kThreads, sm_res, st>>>(q); h->launches++; }
+            if (approx) { dim3 g(npc, nb); k_q<T, CB><<<g, kThreads, sm_q, st>>>(q); h->launches++; }
+            { dim3 g(ceil_div(P, kPV), nb); k_vupd<T><<<g, kThreads, sm_v, st>>>(q); h->launches++; }
+            { dim3 g(nxc, nb); k_xs<T, CB><<<g, kThreads, sm_xs, st>>>(q); h->launches++; }
+            if (want_conv) {
+                dim3 g(3, nb); k_conv_norms<T><<<g, 128, sm_j, st>>>(q); h->launches++;
+                k_conv_finish<T><<<nb, 1, 0, st>>>(q); h->launches++;
+            }
+        }
+        JSTSP_CUDA(h, cudaGetLastError());
+        k_count_nonfinite<T><<<nb, 128, 0, st>>>(q.S, GPn, nb, h->d_flag); h->launches++;
+        // outputs
+        if (host) {
+            auto down = [&](void* dst, const void* src, size_t elems_per, long long ld, size_t el) -> cudaError_t {
+                if ((size_t)ld == elems_per || nb == 1) return cudaMemcpyAsync((char*)dst + (size_t)b0 * ld * el, src, elems_per * el * nb, cudaMemcpyDeviceToHost, st);
+                return cudaMemcpy2DAsync((char*)dst + (size_t)b0 * ld * el, (size_t)ld * el, src, elems_per * el, elems_per * el, nb, cudaMemcpyDeviceToHost, st);
+            };
+            JSTSP_CUDA(h, down(S_, q.S, GPn, d->ld_S ? d->ld_S : (long long)GPn, esz));
+            if (Y_) JSTSP_CUDA(h, down(Y_, q.Yout, NM, d->ld_Y ? d->ld_Y : (long long)NM, esz));
+        } else {
+            if ((size_t)d->ld_S == GPn || nb == 1) JSTSP_CUDA(h, cudaMemcpyAsync((cx<T>*)S_ + (long long)b0 * d->ld_S, q.S, esz * GPn * nb, cudaMemcpyDeviceToDevice, st));
+            else JSTSP_CUDA(h, cudaMemcpy2DAsync((cx<T>*)S_ + (long long)b0 * d->ld_S, (size_t)d->ld_S * esz, q.S, GPn * esz, GPn * esz, nb, cudaMemcpyDeviceToDevice, st));
+        }
+        if (want_conv) {
+            // conv is imax x 3 column-major per trial in the caller's real type; convd is [iter][3] double
+            size_t n3 = (size_t)imax * 3;
+            long long ldc0 = d->ld_conv ? d->ld_conv : (long long)n3;
+            if (host) {
+                std::vector<double> tmp(n3 * nb);
+                JSTSP_CUDA(h, cudaMemcpyAsync(tmp.data(), q.convd, sizeof(double) * n3 * nb, cudaMemcpyDeviceToHost, st));
+                JSTSP_CUDA(h, cudaStreamSynchronize(st));
+                long long ldc = d->ld_conv ? d->ld_conv : (long long)n3;
+                for (int bb = 0; bb < nb; ++bb)
+                    for (int it = 0; it < imax; ++it)
+                        for (int k = 0; k < 3; ++k)
+                            ((T*)conv_)[(size_t)(b0 + bb) * ldc + it + (size_t)imax * k] = (T)tmp[((size_t)bb * imax + it) * 3 + k];
+            } else {
+                k_conv_out<T><<<nb, 128, 0, st>>>(q.convd, (T*)conv_ + (long long)b0 * ldc0, ldc0, imax); h->launches++;
+            }
+        }
+        if (host) JSTSP_CUDA(h, cudaStreamSynchronize(st));
+    }
+    int bad = 0;
+    if (host) {
+        JSTSP_CUDA(h, cudaMemcpyAsync(&bad, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        JSTSP_CUDA(h, cudaStreamSynchronize(st));
+    }
+    return bad;
+}
+
+}  // namespace jstsp
+
+using namespace jstsp;
+
+extern "C" int jstsp_proposed_algorithm(jstsp_handle* h, const jstsp_admm_desc* d, int dtype, int mem,
+                                        const void* subY, const void* omega, const void* A, const void* B,
+                                        const double* tau_Y, const double* tau_S, const double* rho,
+                                        void* S, void* Y, void* conv) {
+    if (!h) return JSTSP_E_ARG;
+    if (!d) return fail(h, JSTSP_E_ARG, "NULL descriptor");
+    JSTSP_CUDA(h, cudaSetDevice(h->device));
+    if (dtype == JSTSP_F32) return run_admm<float>(h, d, mem, subY, omega, nullptr, A, B, tau_Y, tau_S, rho, S, Y, conv, false);
+    if (dtype == JSTSP_F64) return run_admm<double>(h, d, mem, subY, omega, nullptr, A, B, tau_Y, tau_S, rho, S, Y, conv, false);
+    return fail(h, JSTSP_E_ARG, "unknown dtype");
+}
+
+extern "C" int jstsp_proposed_algorithm_angles(jstsp_handle* h, const jstsp_admm_desc* d, int dtype, int mem,
+                                               const void* subY, const void* omega, const int* indx_S,
+                                               const void* A, const void* B,
+                                               const double* tau_Y, const double* tau_S, const double* rho,
+                                               void* S, void* Y, void* conv) {
+    if (!h) return JSTSP_E_ARG;
+    if (!d) return fail(h, JSTSP_E_ARG, "NULL descriptor");
+    JSTSP_CUDA(h, cudaSetDevice(h->device));
+    if (dtype == JSTSP_F32) return run_admm<float>(h, d, mem, subY, omega, indx_S, A, B, tau_Y, tau_S, rho, S, Y, conv, true);
+    if (dtype == JSTSP_F64) return run_admm<double>(h, d, mem, subY, omega, indx_S, A, B, tau_Y, tau_S, rho, S, Y, conv, true);
+    return fail(h, JSTSP_E_ARG, "unknown dtype");
+}

@@ -1,0 +1,69 @@
+// api.cu - handle management for libjstsp_b200 (see include/jstsp_b200.h).
+#include "common.cuh"
+
+using namespace jstsp;
+
+extern "C" const char* jstsp_version(void) { return "jstsp19_b200 0.1.0 (sm_100a)"; }
+
+extern "C" int jstsp_create(jstsp_handle** out, int device) {
+    if (!out) return JSTSP_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) { cudaGetLastError(); return JSTSP_E_CUDA; }   // no CPU fallback by design
+    if (device < 0 || device >= ndev) return JSTSP_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return JSTSP_E_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return JSTSP_E_CUDA;
+    if (prop.major < 10) return JSTSP_E_CUDA;   // kernels are compiled for sm_100a only
+    jstsp_handle* h = new jstsp_handle();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return JSTSP_E_CUDA; }
+    h->own_stream = true;
+    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess) { delete h; return JSTSP_E_CUDA; }
+    cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+    if (cudaMalloc(&h->d_flag, sizeof(int)) != cudaSuccess) { delete h; return JSTSP_E_CUDA; }
+    *out = h;
+    return JSTSP_OK;
+}
+
+extern "C" void jstsp_destroy(jstsp_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->ws) cudaFree(h->ws);
+    if (h->d_flag) cudaFree(h->d_flag);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" const char* jstsp_last_error(const jstsp_handle* h) { return h ? h->err.c_str() : "NULL handle"; }
+
+extern "C" int jstsp_set_stream(jstsp_handle* h, void* cuda_stream) {
+    if (!h) return JSTSP_E_ARG;
+    if (h->own_stream && h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    h->stream = static_cast<cudaStream_t>(cuda_stream);
+    h->own_stream = false;
+    return JSTSP_OK;
+}
+
+extern "C" int jstsp_synchronize(jstsp_handle* h) {
+    if (!h) return JSTSP_E_ARG;
+    JSTSP_CUDA(h, cudaSetDevice(h->device));
+    JSTSP_CUDA(h, cudaStreamSynchronize(h->stream));
+    return JSTSP_OK;
+}
+
+extern "C" long long jstsp_launch_count(const jstsp_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int jstsp_set_chunk(jstsp_handle* h, int max_trials_per_pass) {
+    if (!h || max_trials_per_pass < 0) return JSTSP_E_ARG;
+    h->max_chunk = max_trials_per_pass;
+    return JSTSP_OK;
+}

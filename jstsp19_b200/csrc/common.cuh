@@ -1,0 +1,123 @@
+// common.cuh - shared device/host helpers for libjstsp_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/jstsp_b200.h"
+
+namespace jstsp {
+
+// ---------------------------------------------------------------------------
+// complex scalar (interleaved, MATLAB -R2018a layout)
+// ---------------------------------------------------------------------------
+template <typename T>
+struct __align__(2 * sizeof(T)) cx {
+    T re, im;
+};
+template <typename T> __host__ __device__ __forceinline__ cx<T> mk(T re, T im) { cx<T> r; r.re = re; r.im = im; return r; }
+template <typename T> __host__ __device__ __forceinline__ cx<T> operator+(cx<T> a, cx<T> b) { return mk<T>(a.re + b.re, a.im + b.im); }
+template <typename T> __host__ __device__ __forceinline__ cx<T> operator-(cx<T> a, cx<T> b) { return mk<T>(a.re - b.re, a.im - b.im); }
+template <typename T> __host__ __device__ __forceinline__ cx<T> operator*(cx<T> a, cx<T> b) { return mk<T>(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re); }
+template <typename T> __host__ __device__ __forceinline__ cx<T> operator*(T s, cx<T> a) { return mk<T>(s * a.re, s * a.im); }
+template <typename T> __host__ __device__ __forceinline__ cx<T> conj(cx<T> a) { return mk<T>(a.re, -a.im); }
+template <typename T> __host__ __device__ __forceinline__ T abs2(cx<T> a) { return a.re * a.re + a.im * a.im; }
+
+// acc += a * b   /   acc += a * conj(b)
+template <typename T> __device__ __forceinline__ void cmac(T& ar, T& ai, T xr, T xi, T yr, T yi) {
+    ar = fma(xr, yr, ar); ar = fma(-xi, yi, ar);
+    ai = fma(xr, yi, ai); ai = fma(xi, yr, ai);
+}
+
+// soft threshold with MATLAB sign(0) = 0 (proposed_algorithm.m:56)
+template <typename T> __device__ __forceinline__ T soft1(T x, T thr) {
+    T a = fabs(x) - thr;
+    a = a > T(0) ? a : T(0);
+    return x > T(0) ? a : (x < T(0) ? -a : T(0));
+}
+
+constexpr int kWarp = 32;
+
+__host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ __forceinline__ long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------
+// host-side handle
+// ---------------------------------------------------------------------------
+struct Handle {
+    int device = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;      // stream all work is enqueued on
+    cudaStream_t side = nullptr;        // side stream for the eigen-solves (forked/joined by events)
+    bool own_stream = false;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    std::string err;
+    long long launches = 0;
+    int max_chunk = 0;
+    // simple grow-only workspace
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    int* d_flag = nullptr;              // device-side non-finite counter
+};
+
+}  // namespace jstsp
+
+struct jstsp_handle : public jstsp::Handle {};
+
+namespace jstsp {
+
+inline int fail(Handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+#define JSTSP_CUDA(h, expr)                                                                       \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            return ::jstsp::fail((h), JSTSP_E_CUDA,                                               \
+                                 std::string(#expr) + ": " + cudaGetErrorString(_e));             \
+        }                                                                                         \
+    } while (0)
+
+// Bump allocator over the handle's workspace.
+struct Arena {
+    char* base;
+    size_t cap, off;
+    Arena(void* b, size_t c) : base(static_cast<char*>(b)), cap(c), off(0) {}
+    template <typename U> U* take(size_t n) {
+        size_t bytes = (n * sizeof(U) + 255) & ~size_t(255);
+        char* p = base ? base + off : nullptr;
+        off += bytes;
+        return reinterpret_cast<U*>(p);
+    }
+};
+
+inline int ensure_workspace(Handle* h, size_t bytes) {
+    if (bytes <= h->ws_bytes) return JSTSP_OK;
+    if (h->ws) {
+        cudaStreamSynchronize(h->stream);
+        cudaFree(h->ws);
+        h->ws = nullptr; h->ws_bytes = 0;
+    }
+    cudaError_t e = cudaMalloc(&h->ws, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(h, JSTSP_E_NOMEM, "workspace cudaMalloc failed: " + std::to_string(bytes) + " bytes"); }
+    h->ws_bytes = bytes;
+    return JSTSP_OK;
+}
+
+template <typename K>
+inline int set_smem(Handle* h, K kernel, size_t bytes) {
+    if (bytes > h->smem_optin) return fail(h, JSTSP_E_UNSUPPORTED, "kernel needs more shared memory than the device offers");
+    if (bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return fail(h, JSTSP_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    }
+    return JSTSP_OK;
+}
+
+}  // namespace jstsp
