@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py - channel estimates / second of the proposed ADMM estimator on B200.
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on):
+``proposed_algorithm(..., 'approximate')``, Imax=100, Nt=64, Nr=16, NRF(Mr)=4, K(T)=16,
+L=4  ->  subY 16x1024, A 16x16, B 256x1024 (a fresh pilot matrix per trial, like the
+reference's Monte-Carlo loop), S 16x256; trials cycle through the SNR sweep -15:3:15 dB.
+
+One "step" = one batched solve of ``--trials`` independent trials per GPU.
+  value : whole-job estimates/s, inputs already resident in HBM (device C-ABI call).
+  e2e   : same metric through the reference-facing C-ABI call with HOST (pinned)
+          buffers - H2D of subY/Omega/A/B/params and D2H of S inside the timed region.
+  roofline / cpu_baseline : see DESIGN.md sections 5-6.
+``--impl reference`` times the CPU restatement of the reference's MATLAB path (oracle port,
+all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SNR_SWEEP = [-15.0 + 3.0 * i for i in range(11)]          # plot_errorVSsnr.m:24
+IMAX = 100                                                # plot_errorVSsnr.m:25
+METRIC = "channel estimates/sec at Nt=64,Nr=16,K=16"
+UNIT = "estimates/s"
+WORKLOAD = "proposed_algorithm('approximate',Imax=100) Nt=64 Nr=16 NRF=4 K=16 L=4, per-trial pilots, SNR sweep -15:3:15 dB"
+
+
+def flops_per_estimate(N, M, G, P, imax):
+    """Imax * 8 * (2N^2M + 2NMP + 2GP^2 + 2G^2P + 2GNP) + one-off 8 P^2 M (per-trial B B^H)."""
+    per_iter = 8 * (2 * N * N * M + 2 * N * M * P + 2 * G * P * P + 2 * G * G * P + 2 * G * N * P)
+    return imax * per_iter + 8 * P * P * M
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sus=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sus=1400.0, src="fallback")
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(gpu_index)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            busy = [x for x in sm if x > 0.5 * max(mx)] or sm
+            out = dict(sm_mhz=busy[len(busy) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def cpu_port_rate(n_trials, seed0=9000):
+    """Oracle port (structured fp64 NumPy restatement of proposed_algorithm.m) on the host cores."""
+    import numpy as np
+    from oracle import estimators as est
+    from oracle import fixtures as fx
+    trials = [fx.make_trial(fx.METRIC, SNR_SWEEP[k % len(SNR_SWEEP)], seed0 + k) for k in range(n_trials)]
+    t0 = time.perf_counter()
+    for t in trials:
+        est.proposed_algorithm_structured(t["subY"], t["Omega"], t["A"], t["B"], IMAX, t["tau_Y"], t["tau_Z"], t["rho"],
+                                          "approximate", want_conv=False)
+    dt = time.perf_counter() - t0
+    return n_trials / dt, dt
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [i.get("num_threads", 1) for i in threadpool_info() if i.get("user_api") == "blas"]
+        return max(n) if n else (os.cpu_count() or 1)
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np  # noqa: F401
+    per_step = 3
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_port_rate(1)
+    t_total, n_total = 0.0, 0
+    for k in range(args.steps):
+        r, dt = cpu_port_rate(per_step, seed0=9000 + 100 * k)
+        t_total += dt; n_total += per_step
+    val = n_total / t_total
+    cores = host_threads()
+    line = dict(impl="reference", metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * t_total / max(args.steps, 1), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                data="synthetic", config=dict(workload=WORKLOAD, trials_per_step=per_step),
+                cpu_baseline=dict(value=val, unit=UNIT, cores=cores, kind="port",
+                                  sample=f"{n_total} trials of the workload, structured fp64 NumPy restatement of proposed_algorithm.m (no MATLAB/Octave in the image)"),
+                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--trials", type=int, default=592, help="trials per GPU per step (4 x 148 SMs)")
+    ap.add_argument("--e2e-trials", type=int, default=296)
+    ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--cpu-trials", type=int, default=12)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from jstsp19_b200 import _lib, synth
+    from jstsp19_b200.engine import AdmmEngine, MonteCarlo
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warm = max(args.warmup, 3)
+    s = synth.METRIC
+    N, M, G, P = s.Nr, s.M, s.Nr, s.P
+    cd = torch.complex64 if args.precision == "f32" else torch.complex128
+    nb = args.trials
+    first = rank * nb                                  # weak scaling: every rank owns `nb` trials per step
+    snr = torch.tensor([SNR_SWEEP[(first + k) % len(SNR_SWEEP)] for k in range(nb)], dtype=torch.float64)
+    data = synth.make_batch(s, nb, snr, seed=20190913, first_trial=first, device=dev, cdtype=cd)
+    eng = AdmmEngine(local, args.precision)
+    S = torch.empty(nb, P, G, dtype=cd, device=dev)
+
+    def step():
+        eng.proposed_algorithm(data["subY"], data["Omega"], data["A"], data["B"], IMAX, data["tau_Y"], data["tau_Z"], data["rho"],
+                               "approximate", S_out=S)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warm):
+        step()
+    barrier()
+    eng.h.profile(2)
+    l0 = eng.launches
+    clocks = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    clk = clocks.stop()
+    prof = eng.h.profile_read()
+    eng.h.profile(0)
+    launches = eng.launches - l0
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    value = nb * world * args.steps / (ms * 1e-3)
+
+    # parity / sanity: NMSE of this rank's trials, reduced over ranks (the one NCCL exchange of a sweep point)
+    mc = MonteCarlo(dev)
+    mc.add(synth.nmse_spectral(S, data["Zbar"]))
+    stats = mc.reduce()
+
+    # ---- end-to-end through the HOST-buffer C ABI (pinned host memory) ----
+    e2e = None
+    if not args.no_e2e:
+        import ctypes as C
+        ne = min(args.e2e_trials, nb)
+        pin = lambda t: t[:ne].cpu().contiguous().pin_memory()
+        hsubY, hOm, hB = pin(data["subY"]), pin(data["Omega"]), pin(data["B"])
+        hA = data["A"].cpu().contiguous().pin_memory()
+        hty, hts, hrho = (data[k][:ne].cpu().contiguous().pin_memory() for k in ("tau_Y", "tau_Z", "rho"))
+        hS = torch.empty(ne, P, G, dtype=cd).pin_memory()
+        d = _lib.AdmmDesc()
+        d.N, d.M, d.G, d.P, d.imax, d.type, d.batch = N, M, G, P, IMAX, _lib.APPROXIMATE, ne
+        d.ld_subY, d.ld_omega, d.ld_A, d.ld_B, d.ld_S, d.ld_Y = N * M, N * M, 0, P * M, G * P, N * M
+        dt = _lib.F32 if args.precision == "f32" else _lib.F64
+        vp = lambda t: C.c_void_p(t.data_ptr())
+
+        def host_step():
+            rc = _lib.lib.jstsp_proposed_algorithm(eng.h.ptr, C.byref(d), dt, _lib.HOST, vp(hsubY), vp(hOm), vp(hA), vp(hB),
+                                                   vp(hty), vp(hts), vp(hrho), vp(hS), None, None)
+            eng.h.check(rc)
+
+        for _ in range(2):
+            host_step()
+        barrier()
+        t0 = time.perf_counter()
+        ksteps = max(2, args.steps // 2)
+        for _ in range(ksteps):
+            host_step()
+        torch.cuda.synchronize()
+        dt_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt_s, op=dist.ReduceOp.MAX)
+        esz = 8 if args.precision == "f32" else 16
+        h2d = ne * (N * M * esz + N * M * esz // 2 + P * M * esz + 24) + N * G * esz
+        d2h = ne * G * P * esz
+        e2e = dict(value=ne * world * ksteps / float(dt_s.item()), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                   trials_per_step=ne, timing="host wall clock around the synchronous C-ABI call, max over ranks")
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (live CUDA-event timing inside the library) ----
+    pk = peaks()
+    F_est = flops_per_estimate(N, M, G, P, IMAX)
+    kflops = {  # algorithmic real flops per launch of each kernel class (per trial x nb trials)
+        "xupd_t1": 8 * (N * N * M + N * M * P + N * N * M) * nb,      # W Z, K B^H, next Gram
+        "xs": 8 * (N * P * M) * nb,                                  # (A S) B
+        "res": 8 * (G * P * P + G * N * P + G * G * P) * nb,          # V BBH, A^H T1, AHA (.)
+        "q": 8 * (G * P * P + G * G * P) * nb,                        # Res BBH, AHA (.)
+        "vupd": 8 * (N * G * P) * nb,                                # A S
+    }
+    tot_ms = sum(v[0] for v in prof.values()) or 1.0
+    top = max((k for k in prof if k in kflops and prof[k][1] > 0), key=lambda k: prof[k][0], default=None)
+    roof = None
+    if top:
+        avg_ms = prof[top][0] / prof[top][1]
+        achieved = kflops[top] / (avg_ms * 1e-3) / 1e12
+        peak = pk["bf16_sus"] / 2.0 / 3.0          # TF32 dense = bf16/2; a 3xTF32-equivalent fp32 contraction is scored against TF32/3
+        roof = dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=None,
+                    kernel=top, avg_launch_ms=avg_ms, share_of_step=prof[top][0] / tot_ms,
+                    peak_source=f"{pk['src']} bf16_tflops_sustained/2 (TF32) /3 (3xTF32-equivalent fp32 accuracy), SURVEY.md 8(d)",
+                    pipe="fp32 FMA (CUDA cores)", fma_peak_tflops=72.0, frac_of_fma_peak=achieved / 72.0,
+                    kernels={k: dict(ms_total=v[0], launches=v[1]) for k, v in prof.items() if v[1]})
+    cpu = None
+    if not args.no_cpu:
+        r, dt = cpu_port_rate(args.cpu_trials)
+        cpu = dict(value=r, unit=UNIT, cores=host_threads(), kind="port",
+                   sample=f"{args.cpu_trials} trials of the workload ({dt:.1f} s), structured fp64 NumPy restatement of proposed_algorithm.m")
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=warm, ms_per_step=ms / args.steps,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32" if args.precision == "f32" else "f64",
+                data="synthetic",
+                config=dict(workload=WORKLOAD, trials_per_gpu_per_step=nb, imax=IMAX, shape=dict(N=N, M=M, G=G, P=P),
+                            l2="inputs larger than L2 (per-step inputs %.1f GB per GPU)" % (nb * (P * M + 2 * N * M) * (8 if args.precision == "f32" else 16) / 1e9),
+                            parallelism=f"trials sharded over {world} GPU(s), one NCCL all-reduce of NMSE sums"),
+                clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu,
+                algorithmic_gflop_per_estimate=F_est / 1e9, achieved_tflops_whole_step=F_est * value / 1e12,
+                nmse=stats)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

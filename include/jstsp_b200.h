@@ -65,6 +65,13 @@ long long jstsp_launch_count(const jstsp_handle* h);
 /* Upper bound on the trials processed per internal pass (0 = automatic). */
 int jstsp_set_chunk(jstsp_handle* h, int max_trials_per_pass);
 
+/* Per-kernel-class device timing with CUDA events on the handle's stream (for roofline
+ * reports).  enable: 0 = off, 1 = on, 2 = on and reset the accumulators.
+ * jstsp_profile_read returns 0 and fills total_ms / launches / name for `slot`, or 1 when
+ * `slot` is past the last class; it synchronises the stream. */
+int jstsp_profile(jstsp_handle* h, int enable);
+int jstsp_profile_read(jstsp_handle* h, int slot, double* total_ms, long long* launches, const char** name);
+
 /* ---- proposed ADMM matrix completion ------------------------------------------- */
 typedef struct {
     int N, M;          /* subY is N x M  (rows = RF-chain domain, cols = training instants) */

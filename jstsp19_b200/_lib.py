@@ -53,6 +53,8 @@ def _load():
     lib.jstsp_launch_count.argtypes = [vp]
     lib.jstsp_launch_count.restype = ll
     lib.jstsp_set_chunk.argtypes = [vp, i]
+    lib.jstsp_profile.argtypes = [vp, i]
+    lib.jstsp_profile_read.argtypes = [vp, i, dp, C.POINTER(ll), C.POINTER(C.c_char_p)]
     lib.jstsp_proposed_algorithm.argtypes = [vp, C.POINTER(AdmmDesc), i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.jstsp_proposed_algorithm_angles.argtypes = [vp, C.POINTER(AdmmDesc), i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.jstsp_svt.argtypes = [vp, i, i, i, i, i, vp, ll, vp, vp, ll]
@@ -66,7 +68,7 @@ lib = _load()
 #: every symbol include/jstsp_b200.h declares (checked by tests/test_abi.py)
 EXPORTED = [
     "jstsp_create", "jstsp_destroy", "jstsp_last_error", "jstsp_version", "jstsp_set_stream",
-    "jstsp_synchronize", "jstsp_launch_count", "jstsp_set_chunk",
+    "jstsp_synchronize", "jstsp_launch_count", "jstsp_set_chunk", "jstsp_profile", "jstsp_profile_read",
     "jstsp_proposed_algorithm", "jstsp_proposed_algorithm_angles",
     "jstsp_svt", "jstsp_mc_svt", "jstsp_mc_admm",
 ]
@@ -99,6 +101,22 @@ class Handle:
 
     def set_chunk(self, n: int):
         self.check(lib.jstsp_set_chunk(self._h, int(n)))
+
+    def profile(self, enable: int):
+        self.check(lib.jstsp_profile(self._h, int(enable)))
+
+    def profile_read(self):
+        """{kernel class: (total_ms, launches)} accumulated since profiling was (re)started."""
+        out = {}
+        slot = 0
+        while True:
+            ms, n, name = C.c_double(), C.c_longlong(), C.c_char_p()
+            rc = lib.jstsp_profile_read(self._h, slot, C.byref(ms), C.byref(n), C.byref(name))
+            if rc != 0:
+                break
+            out[name.value.decode()] = (ms.value, n.value)
+            slot += 1
+        return out
 
     @property
     def launches(self) -> int:

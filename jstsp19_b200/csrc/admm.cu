@@ -743,31 +743,31 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
         if (angles) JSTSP_CUDA(h, cudaMemsetAsync(q.smask, 0, GPn * nb, st));
         // one-off operators
         const int nA = d->ld_A ? nb : 1, nB = d->ld_B ? nb : 1;
-        k_aha<T><<<nA, 256, 0, st>>>(q); h->launches++;
-        { dim3 g(ceil_div(P, 64), ceil_div(P, 64), nB); k_bbh<T><<<g, 256, 0, st>>>(q); h->launches++; }
+        JSTSP_LAUNCH(h, PK_SETUP, (k_aha<T><<<nA, 256, 0, st>>>(q)));
+        { dim3 g(ceil_div(P, 64), ceil_div(P, 64), nB); JSTSP_LAUNCH(h, PK_SETUP, (k_bbh<T><<<g, 256, 0, st>>>(q))); }
         if (!approx) {
             size_t smi = 2 * sizeof(cx<T>) * (size_t)(P > G ? P : G);
             if ((rc = set_smem(h, k_hpd_inverse<T>, smi))) return rc;
-            k_hpd_inverse<T><<<nB, 256, smi, st>>>(q.BBH, (long long)P * P, P); h->launches++;
-            k_hpd_inverse<T><<<nA, 256, smi, st>>>(q.AHA, (long long)G * G, G); h->launches++;
-            k_pinv_left<T><<<nA, 256, 0, st>>>(q, q.AHA, q.ld_AHA); h->launches++;
+            JSTSP_LAUNCH(h, PK_SETUP, (k_hpd_inverse<T><<<nB, 256, smi, st>>>(q.BBH, (long long)P * P, P)));
+            JSTSP_LAUNCH(h, PK_SETUP, (k_hpd_inverse<T><<<nA, 256, smi, st>>>(q.AHA, (long long)G * G, G)));
+            JSTSP_LAUNCH(h, PK_SETUP, (k_pinv_left<T><<<nA, 256, 0, st>>>(q, q.AHA, q.ld_AHA)));
         }
         for (int it = 0; it < imax; ++it) {
             q.iter = it;
-            if (angles) { dim3 g(1, nb); k_mask_grow<T><<<g, 64, 0, st>>>(q); h->launches++; }
-            k_svt_weights<T><<<nb, 128, sm_j, st>>>(q); h->launches++;
-            { dim3 g(q.nmc, nb); k_xupd_t1<T, KB><<<g, kThreads, sm_x, st>>>(q); h->launches++; }
-            { dim3 g(approx ? npc : ceil_div(P, PCr), nb); k_res<T, CB><<<g, kThreads, sm_res, st>>>(q); h->launches++; }
-            if (approx) { dim3 g(npc, nb); k_q<T, CB><<<g, kThreads, sm_q, st>>>(q); h->launches++; }
-            { dim3 g(ceil_div(P, kPV), nb); k_vupd<T><<<g, kThreads, sm_v, st>>>(q); h->launches++; }
-            { dim3 g(nxc, nb); k_xs<T, CB><<<g, kThreads, sm_xs, st>>>(q); h->launches++; }
+            if (angles) { dim3 g(1, nb); JSTSP_LAUNCH(h, PK_OTHER, (k_mask_grow<T><<<g, 64, 0, st>>>(q))); }
+            JSTSP_LAUNCH(h, PK_EIG, (k_svt_weights<T><<<nb, 128, sm_j, st>>>(q)));
+            { dim3 g(q.nmc, nb); JSTSP_LAUNCH(h, PK_XUPD_T1, (k_xupd_t1<T, KB><<<g, kThreads, sm_x, st>>>(q))); }
+            { dim3 g(approx ? npc : ceil_div(P, PCr), nb); JSTSP_LAUNCH(h, PK_RES, (k_res<T, CB><<<g, kThreads, sm_res, st>>>(q))); }
+            if (approx) { dim3 g(npc, nb); JSTSP_LAUNCH(h, PK_Q, (k_q<T, CB><<<g, kThreads, sm_q, st>>>(q))); }
+            { dim3 g(ceil_div(P, kPV), nb); JSTSP_LAUNCH(h, PK_VUPD, (k_vupd<T><<<g, kThreads, sm_v, st>>>(q))); }
+            { dim3 g(nxc, nb); JSTSP_LAUNCH(h, PK_XS, (k_xs<T, CB><<<g, kThreads, sm_xs, st>>>(q))); }
             if (want_conv) {
-                dim3 g(3, nb); k_conv_norms<T><<<g, 128, sm_j, st>>>(q); h->launches++;
-                k_conv_finish<T><<<nb, 1, 0, st>>>(q); h->launches++;
+                dim3 g(3, nb); JSTSP_LAUNCH(h, PK_OTHER, (k_conv_norms<T><<<g, 128, sm_j, st>>>(q)));
+                JSTSP_LAUNCH(h, PK_OTHER, (k_conv_finish<T><<<nb, 1, 0, st>>>(q)));
             }
         }
         JSTSP_CUDA(h, cudaGetLastError());
-        k_count_nonfinite<T><<<nb, 128, 0, st>>>(q.S, GPn, nb, h->d_flag); h->launches++;
+        JSTSP_LAUNCH(h, PK_OTHER, (k_count_nonfinite<T><<<nb, 128, 0, st>>>(q.S, GPn, nb, h->d_flag)));
         // outputs
         if (host) {
             auto down = [&](void* dst, const void* src, size_t elems_per, long long ld, size_t el) -> cudaError_t {
@@ -794,7 +794,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
                         for (int k = 0; k < 3; ++k)
                             ((T*)conv_)[(size_t)(b0 + bb) * ldc + it + (size_t)imax * k] = (T)tmp[((size_t)bb * imax + it) * 3 + k];
             } else {
-                k_conv_out<T><<<nb, 128, 0, st>>>(q.convd, (T*)conv_ + (long long)b0 * ldc0, ldc0, imax); h->launches++;
+                JSTSP_LAUNCH(h, PK_OTHER, (k_conv_out<T><<<nb, 128, 0, st>>>(q.convd, (T*)conv_ + (long long)b0 * ldc0, ldc0, imax)));
             }
         }
         if (host) JSTSP_CUDA(h, cudaStreamSynchronize(st));

@@ -36,6 +36,7 @@ extern "C" void jstsp_destroy(jstsp_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->ws) cudaFree(h->ws);
     if (h->d_flag) cudaFree(h->d_flag);
+    for (auto e : h->prof.pool) cudaEventDestroy(e);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->side) cudaStreamDestroy(h->side);
@@ -65,5 +66,25 @@ extern "C" long long jstsp_launch_count(const jstsp_handle* h) { return h ? h->l
 extern "C" int jstsp_set_chunk(jstsp_handle* h, int max_trials_per_pass) {
     if (!h || max_trials_per_pass < 0) return JSTSP_E_ARG;
     h->max_chunk = max_trials_per_pass;
+    return JSTSP_OK;
+}
+
+static const char* kProfNames[PK_COUNT] = {"xupd_t1", "res", "q", "vupd", "xs", "eig", "setup", "svt_step", "omp", "other"};
+
+extern "C" int jstsp_profile(jstsp_handle* h, int enable) {
+    if (!h) return JSTSP_E_ARG;
+    prof_collect(h);
+    h->prof.on = enable != 0;
+    if (enable == 2) { for (int i = 0; i < PK_COUNT; ++i) { h->prof.total_ms[i] = 0; h->prof.count[i] = 0; } }
+    return JSTSP_OK;
+}
+
+extern "C" int jstsp_profile_read(jstsp_handle* h, int slot, double* total_ms, long long* launches, const char** name) {
+    if (!h || slot < 0) return JSTSP_E_ARG;
+    if (slot >= PK_COUNT) return 1;   // past the last slot
+    prof_collect(h);
+    if (total_ms) *total_ms = h->prof.total_ms[slot];
+    if (launches) *launches = h->prof.count[slot];
+    if (name) *name = kProfNames[slot];
     return JSTSP_OK;
 }

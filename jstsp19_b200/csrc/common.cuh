@@ -47,7 +47,21 @@ __host__ __device__ __forceinline__ long long ceil_div_ll(long long a, long long
 // ---------------------------------------------------------------------------
 // host-side handle
 // ---------------------------------------------------------------------------
+// Optional per-kernel-class device timing (CUDA events on the launching stream), switched on
+// by jstsp_profile(); bench.py reads it for the live roofline numbers.
+enum { PK_XUPD_T1 = 0, PK_RES, PK_Q, PK_VUPD, PK_XS, PK_EIG, PK_SETUP, PK_SVT_STEP, PK_OMP, PK_OTHER, PK_COUNT };
+struct Prof {
+    bool on = false;
+    struct Rec { int slot; cudaEvent_t a, b; };
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    std::vector<Rec> recs;
+    double total_ms[PK_COUNT] = {};
+    long long count[PK_COUNT] = {};
+};
+
 struct Handle {
+    Prof prof;
     int device = 0;
     int sm_count = 148;
     size_t smem_optin = 0;
@@ -82,6 +96,41 @@ inline int fail(Handle* h, int code, const std::string& msg) {
             return ::jstsp::fail((h), JSTSP_E_CUDA,                                               \
                                  std::string(#expr) + ": " + cudaGetErrorString(_e));             \
         }                                                                                         \
+    } while (0)
+
+inline cudaEvent_t prof_event(Handle* h) {
+    Prof& p = h->prof;
+    if (p.used == p.pool.size()) { cudaEvent_t e; cudaEventCreate(&e); p.pool.push_back(e); }
+    return p.pool[p.used++];
+}
+inline void prof_begin(Handle* h, int slot) {
+    if (!h->prof.on) return;
+    Prof::Rec r{slot, prof_event(h), prof_event(h)};
+    cudaEventRecord(r.a, h->stream);
+    h->prof.recs.push_back(r);
+}
+inline void prof_end(Handle* h) {
+    if (!h->prof.on) return;
+    cudaEventRecord(h->prof.recs.back().b, h->stream);
+}
+inline void prof_collect(Handle* h) {
+    Prof& p = h->prof;
+    if (p.recs.empty()) return;
+    cudaStreamSynchronize(h->stream);
+    for (auto& r : p.recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { p.total_ms[r.slot] += ms; p.count[r.slot]++; }
+    }
+    p.recs.clear();
+    p.used = 0;
+}
+// launch wrapper: counts the launch and (when profiling) brackets it with events
+#define JSTSP_LAUNCH(h, slot, ...)          \
+    do {                                    \
+        ::jstsp::prof_begin((h), (slot));   \
+        __VA_ARGS__;                        \
+        ::jstsp::prof_end((h));             \
+        (h)->launches++;                    \
     } while (0)
 
 // Bump allocator over the handle's workspace.

@@ -240,26 +240,25 @@ static int run_svt_family(Handle* h, int mode, int mem, int N, int M, int batch,
         dim3 grid(q.nmc, nb);
         if (mode == MODE_SVT) {
             q.rho = nullptr;
-            k_gram_of<T><<<grid, kThreads, sm_gram, st>>>(q, q.in, q.ld_in, q.gram, 1, 0); h->launches++;
-            k_weights<T><<<nb, 128, sm_j, st>>>(q); h->launches++;
+            JSTSP_LAUNCH(h, PK_OTHER, (k_gram_of<T><<<grid, kThreads, sm_gram, st>>>(q, q.in, q.ld_in, q.gram, 1, 0)));
+            JSTSP_LAUNCH(h, PK_EIG, (k_weights<T><<<nb, 128, sm_j, st>>>(q)));
             q.iter = 0;
-            k_svt_step<T, MODE_SVT><<<grid, kThreads, sm_step, st>>>(q); h->launches++;
+            JSTSP_LAUNCH(h, PK_SVT_STEP, (k_svt_step<T, MODE_SVT><<<grid, kThreads, sm_step, st>>>(q)));
         } else {
             JSTSP_CUDA(h, cudaMemsetAsync(q.Ys, 0, esz * NM * nb, st));                       // Y = 0 (mc_svt.m:5, mc_admm.m:7)
             if (mode == MODE_MCADMM) JSTSP_CUDA(h, cudaMemsetAsync(q.Zs, 0, esz * NM * nb, st));
             JSTSP_CUDA(h, cudaMemsetAsync(q.gram, 0, sizeof(double) * (size_t)nb * q.nmc * NN2, st));
             if (imax == 0) JSTSP_CUDA(h, cudaMemsetAsync(q.out, 0, esz * NM * nb, st));
             if (want_conv) {
-                k_gram_of<T><<<grid, kThreads, sm_gram, st>>>(q, q.Htrue, q.ld_H, q.cgram, 2, 1); h->launches++;
-                k_mc_conv<T><<<nb, 128, sm_j, st>>>(q, 1); h->launches++;
+                JSTSP_LAUNCH(h, PK_OTHER, (k_gram_of<T><<<grid, kThreads, sm_gram, st>>>(q, q.Htrue, q.ld_H, q.cgram, 2, 1)));
+                JSTSP_LAUNCH(h, PK_OTHER, (k_mc_conv<T><<<nb, 128, sm_j, st>>>(q, 1)));
             }
             for (int it = 0; it < imax; ++it) {
                 q.iter = it;
-                k_weights<T><<<nb, 128, sm_j, st>>>(q); h->launches++;
-                if (mode == MODE_MCSVT) k_svt_step<T, MODE_MCSVT><<<grid, kThreads, sm_step, st>>>(q);
-                else k_svt_step<T, MODE_MCADMM><<<grid, kThreads, sm_step, st>>>(q);
-                h->launches++;
-                if (want_conv) { k_mc_conv<T><<<nb, 128, sm_j, st>>>(q, 0); h->launches++; }
+                JSTSP_LAUNCH(h, PK_EIG, (k_weights<T><<<nb, 128, sm_j, st>>>(q)));
+                if (mode == MODE_MCSVT) JSTSP_LAUNCH(h, PK_SVT_STEP, (k_svt_step<T, MODE_MCSVT><<<grid, kThreads, sm_step, st>>>(q)));
+                else JSTSP_LAUNCH(h, PK_SVT_STEP, (k_svt_step<T, MODE_MCADMM><<<grid, kThreads, sm_step, st>>>(q)));
+                if (want_conv) { JSTSP_LAUNCH(h, PK_OTHER, (k_mc_conv<T><<<nb, 128, sm_j, st>>>(q, 0))); }
             }
         }
         JSTSP_CUDA(h, cudaGetLastError());

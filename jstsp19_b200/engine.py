@@ -1,0 +1,109 @@
+"""Device-resident batched engine: torch tensors in, torch tensors out, all compute in
+``libjstsp_b200.so`` on torch's current CUDA stream (torch is used for device memory,
+streams and ``torch.distributed`` only).
+
+Tensor layout everywhere: ``(batch, cols, rows)`` C-contiguous = per-trial column-major,
+complex64 (``precision="f32"``) or complex128 (``"f64"``).
+
+Multi-GPU: Monte-Carlo trials are independent (the reference uses ``parfor`` over them,
+plot_errorVSdelays.m:51), so ranks take contiguous trial ranges with NO data-path
+collective; ``MonteCarlo.reduce`` is the single NCCL all-reduce of the NMSE partial sums.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import AdmmDesc, Handle
+
+_CD = {"f32": torch.complex64, "f64": torch.complex128}
+_RD = {"f32": torch.float32, "f64": torch.float64}
+_DT = {"f32": _lib.F32, "f64": _lib.F64}
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class AdmmEngine:
+    def __init__(self, device=0, precision="f32", max_trials_per_pass=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("jstsp19_b200.engine needs a CUDA device (no CPU fallback)")
+        self.device = torch.device("cuda", device)
+        self.precision = precision
+        self.h = Handle(device)
+        if max_trials_per_pass:
+            self.h.set_chunk(max_trials_per_pass)
+
+    def _bind_stream(self):
+        self.h.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def proposed_algorithm(self, subY, Omega, A, B, imax, tau_Y, tau_S, rho, type="approximate", indx_S=None,
+                           S_out=None, Y_out=None):
+        """Batched proposed_algorithm / proposed_algorithm_angles on device tensors.
+        subY (b,M,N), Omega (b,M,N) real, A (b|1,G,N), B (b|1,M,P), tau_Y/tau_S/rho (b,) float64.
+        Returns S (b,P,G) [and fills Y_out (b,M,N) when given]; asynchronous on the current stream."""
+        cd, rdt = _CD[self.precision], _RD[self.precision]
+        b, M, N = subY.shape
+        G, P = A.shape[-2], B.shape[-1]
+        for t, dt in ((subY, cd), (A, cd), (B, cd), (Omega, rdt), (tau_Y, torch.float64), (tau_S, torch.float64), (rho, torch.float64)):
+            if t.dtype != dt or not t.is_contiguous() or t.device != self.device:
+                raise ValueError("engine tensors must be contiguous, on the engine's device, and of the engine's precision")
+        if S_out is None:
+            S_out = torch.empty(b, P, G, dtype=cd, device=self.device)
+        d = AdmmDesc()
+        d.N, d.M, d.G, d.P, d.imax, d.batch = N, M, G, P, int(imax), b
+        d.type = _lib.APPROXIMATE if type == "approximate" else _lib.STD
+        d.ld_subY = N * M
+        for t in (Omega, A, B):
+            if t.shape[0] not in (1, b):
+                raise ValueError("leading dimension must be 1 (shared by all trials) or batch")
+        d.ld_omega = N * M if Omega.shape[0] == b else 0
+        d.ld_A = N * G if A.shape[0] == b else 0
+        d.ld_B = P * M if B.shape[0] == b else 0
+        d.ld_S, d.ld_Y, d.ld_conv = G * P, N * M, 0
+        self._bind_stream()
+        if indx_S is None:
+            rc = _lib.lib.jstsp_proposed_algorithm(self.h.ptr, C.byref(d), _DT[self.precision], _lib.DEVICE, _p(subY), _p(Omega), _p(A), _p(B),
+                                                   _p(tau_Y), _p(tau_S), _p(rho), _p(S_out), _p(Y_out), None)
+        else:
+            d.n_indx = indx_S.shape[-1]
+            d.ld_indx = indx_S.shape[-1] if indx_S.dim() == 2 and indx_S.shape[0] == b else 0
+            rc = _lib.lib.jstsp_proposed_algorithm_angles(self.h.ptr, C.byref(d), _DT[self.precision], _lib.DEVICE, _p(subY), _p(Omega),
+                                                          _p(indx_S), _p(A), _p(B), _p(tau_Y), _p(tau_S), _p(rho), _p(S_out), _p(Y_out), None)
+        self.h.check(rc)
+        return S_out
+
+    @property
+    def launches(self):
+        return self.h.launches
+
+
+def shard_range(n_trials, rank, world):
+    """Contiguous trial range [lo, hi) of `rank` (ranks differ by at most one trial)."""
+    base, rem = divmod(n_trials, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class MonteCarlo:
+    """Accumulates per-trial NMSE on a rank and reduces [sum, count, flagged] over ranks -
+    the only cross-rank exchange of a sweep point (mean over trials, plot_errorVSsnr.m:170-178)."""
+
+    def __init__(self, device):
+        self.acc = torch.zeros(3, dtype=torch.float64, device=device)
+
+    def add(self, nmse):
+        bad = ~torch.isfinite(nmse)
+        self.acc[0] += torch.where(bad, torch.zeros_like(nmse), nmse).sum()
+        self.acc[1] += (~bad).sum()
+        self.acc[2] += bad.sum()
+
+    def reduce(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.acc, op=dist.ReduceOp.SUM)
+        s, n, f = (float(x) for x in self.acc.tolist())
+        return dict(mean_nmse=s / n if n else float("nan"), trials=int(n), flagged=int(f))

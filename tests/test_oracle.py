@@ -1,0 +1,155 @@
+"""CPU tests of the oracle itself (the reference has no tests, no seeds
+and no golden vectors, so the oracle is pinned by literal == structured, by algebraic
+properties and by the frozen fixtures under tests/golden/)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import estimators as est
+from oracle import fixtures as fx
+from oracle import matlab_compat as mc
+from oracle import system_model as sm
+from oracle import vamp as ovamp
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def test_toeplitz_hermitian_rule():
+    s = np.array([1 + 2j, 3 - 1j, -2 + 0.5j])
+    T = mc.toeplitz_hermitian(s)
+    assert np.allclose(T[0], s) and np.allclose(T[:, 0], [s[0], np.conj(s[1]), np.conj(s[2])])
+    assert T[1, 1] == s[0] and T[2, 1] == np.conj(s[1])
+    assert np.allclose(mc.toeplitz_hermitian_rows(s, 2), T[:2])
+
+
+def test_matlab_round_and_norm_and_eigs():
+    assert mc.mround(2.5) == 3 and mc.mround(-2.5) == -3 and mc.mround(0.75 * 32) == 24
+    X = np.diag([3.0, 1.0, 2.0]).astype(complex)
+    assert mc.norm2(X) == pytest.approx(3.0) and mc.fro(X) == pytest.approx(np.sqrt(14.0))
+    assert list(mc.eigs6(np.diag(np.arange(1.0, 9.0)))) == [8, 7, 6, 5, 4, 3]
+    assert list(mc.sort_descend_idx([1.0, 3.0, 3.0, 2.0])) == [2, 3, 4, 1]      # stable, 1-based
+
+
+def test_channel_quirks():
+    rng = mc.RefRandom(3)
+    H, Zbar, Ar, At, Dr, Dt = sm.wideband_mmwave_channel(3, 8, 4, 2, 3, 8, 4, rng)
+    # page-1 quirk: every tap is built from tap-1 steering vectors; cluster-1 rays counted twice
+    rng2 = mc.RefRandom(3)
+    H2 = np.zeros_like(H)
+    for l in range(3):
+        for ray in range(6):
+            c = (rng2.randn() + 1j * rng2.randn()) / np.sqrt(2)
+            rng2.rand(); rng2.rand()
+            w = 2.0 if ray < 3 else 1.0
+            H2[:, :, l] += w * c * np.outer(Ar[:, ray, 0], At[:, ray, 0].conj()) / np.sqrt(6)
+    assert _rel(H, H2) < 1e-13
+    Z = np.stack([Dr.conj().T @ H[:, :, l] @ Dt for l in range(3)], axis=2)
+    assert np.allclose(Zbar[:, 4:8], Z[:, :, 1])
+    assert np.allclose(Dr.conj().T @ Dr, np.eye(8))
+
+
+def test_mask_has_exactly_Lr_ones_per_column():
+    t = fx.make_trial(fx.TINY, 5.0, 0)
+    assert set(np.unique(t["Omega"])) <= {0.0, 1.0}
+    assert np.all(t["Omega"].sum(axis=0) == fx.TINY.Mr)
+    rng = mc.RefRandom(1)
+    H = np.zeros((8, 2, 2), complex)
+    Yp, Yc, W, Psi_bar, Omega, Lr = sm.wideband_hybBF_comm_system_training(H, 10, 0.1, 0.75, rng)
+    assert Lr == 6 and np.all(Omega.sum(axis=0) == 6) and np.allclose(Yp, Omega * Yc)
+    assert np.allclose(W.conj().T @ W, np.eye(8))
+
+
+def test_svt_properties():
+    rng = np.random.default_rng(0)
+    Y = rng.standard_normal((6, 15)) + 1j * rng.standard_normal((6, 15))
+    assert not np.any(est.svt_literal(np.zeros((6, 15)), 0.3))                     # NaN guard, svt.m:7-13
+    assert _rel(est.svt_literal(Y, 0.0), Y) < 1e-13
+    assert _rel(est.svt_structured(Y, 1.3), est.svt_literal(Y, 1.3)) < 1e-13
+    s = np.linalg.svd(est.svt_literal(Y, 1.3), compute_uv=False)
+    assert np.allclose(s, np.maximum(np.linalg.svd(Y, compute_uv=False) - 1.3, 0))
+    assert np.all(mc.soft_complex(np.array([0.0 + 0.0j, 2 - 3j, -0.1 + 0.05j]), 0.5) == np.array([0, 1.5 - 2.5j, 0]))
+
+
+@pytest.mark.parametrize("type_", ["approximate", "std"])
+def test_proposed_literal_equals_structured(type_):
+    t = fx.make_trial(fx.TINY, 5.0, 1)
+    a = (t["subY"], t["Omega"], t["A"], t["B"], 25, t["tau_Y"], t["tau_Z"], t["rho"], type_)
+    S1, Y1, c1 = est.proposed_algorithm_literal(*a)
+    S2, Y2, c2 = est.proposed_algorithm_structured(*a)
+    assert _rel(S2, S1) < 1e-11 and _rel(Y2, Y1) < 1e-11
+    assert np.allclose(c1[:, :2], c2[:, :2], rtol=1e-9)
+    if type_ == "approximate":
+        assert np.isinf(c1[0, 2]) and np.allclose(c1[1:, 2], c2[1:, 2], rtol=1e-8)
+
+
+def test_angles_literal_equals_structured_and_support_grows():
+    t = fx.make_trial(fx.TINY, 5.0, 2)
+    a = (t["subY"], t["Omega"], t["A"], t["B"], 8, t["tau_Y"], t["tau_Z"], t["rho"], "approximate")
+    S1, _, _ = est.proposed_algorithm_literal(*a, indx_S=t["indx_S"])
+    S2, _, _ = est.proposed_algorithm_structured(*a, indx_S=t["indx_S"])
+    assert _rel(S2, S1) < 1e-11
+    # after i iterations the support is indx_S(1:min(10+5i, G*P))  (_angles.m:36)
+    S3, _, _ = est.proposed_algorithm_structured(*a[:4], 1, *a[5:], indx_S=t["indx_S"])
+    allowed = np.zeros(S3.size, bool); allowed[t["indx_S"][:15] - 1] = True
+    assert not np.any(mc.vec(S3)[~allowed])
+
+
+def test_mc_admm_and_sparse_admm_literal_equals_structured():
+    t = fx.make_trial(fx.TINY, 5.0, 3)
+    Ht = t["W_e"].conj().T @ t["Ynoiseless"]
+    X1, c1 = est.mc_admm_literal(Ht, t["subY"], t["Omega"], 12, t["tau_Y"], t["rho"])
+    X2, c2 = est.mc_admm_structured(Ht, t["subY"], t["Omega"], 12, t["tau_Y"], t["rho"])
+    assert _rel(X2, X1) < 1e-11 and np.allclose(c1, c2, rtol=1e-9)
+    H0 = t["H"][:, :, 0]
+    OH = H0 + 0.01 * (np.random.default_rng(0).standard_normal(H0.shape))
+    S1, d1 = est.sparse_admm_literal(H0, OH, t["Dr"], t["Dt"], 10)
+    S2, d2 = est.sparse_admm_structured(H0, OH, t["Dr"], t["Dt"], 10)
+    assert _rel(S2, S1) < 1e-10 and np.allclose(d1, d2, rtol=1e-8)
+
+
+def test_omp_support_and_residual():
+    rng = np.random.default_rng(5)
+    A = (rng.standard_normal((40, 90)) + 1j * rng.standard_normal((40, 90))) / np.sqrt(40)
+    x = np.zeros(90, complex); idx = [3, 17, 60, 88]; x[idx] = [2, -1.5j, 1 + 1j, -2]
+    xh, iset, v, T = est.omp_literal(A, A @ x, 4)
+    assert sorted(iset) == [i + 1 for i in idx] and _rel(xh, x) < 1e-12 and T.shape == (40, 4)
+    assert len(set(iset)) == 4                                                     # support monotone while r != 0
+
+
+def test_vamp_runs_and_recovers_sparse_vector():
+    rng = np.random.default_rng(6)
+    m, n, k = 60, 100, 8
+    A = (rng.standard_normal((m, n)) + 1j * rng.standard_normal((m, n))) / np.sqrt(2 * m)
+    x = np.zeros(n, complex); x[rng.choice(n, k, replace=False)] = 3 * (rng.standard_normal(k) + 1j * rng.standard_normal(k))
+    y = A @ x + 0.01 * (rng.standard_normal(m) + 1j * rng.standard_normal(m))
+    xh = ovamp.vamp_literal(y, A, 1e-4, 2 * k)
+    assert np.all(np.isfinite(xh)) and _rel(xh, x) < 0.2
+
+
+def test_nmse_follows_snr():
+    """Order-of-magnitude pin against results/errorVSsnr.fig: the proposed
+    estimator's NMSE falls monotonically with SNR."""
+    e = []
+    for snr in (-15.0, 0.0, 15.0):
+        v = []
+        for sd in range(3):
+            t = fx.make_trial(fx.CONFIG0, snr, 50 + sd)
+            S, _, _ = est.proposed_algorithm_structured(t["subY"], t["Omega"], t["A"], t["B"], 100, t["tau_Y"], t["tau_Z"],
+                                                        t["rho"], "approximate", want_conv=False)
+            v.append(est.nmse(S, t["Zbar"]))
+        e.append(np.mean(v))
+    assert e[0] > e[1] > e[2] and e[0] <= 1.0
+
+
+def test_golden_fixture_frozen():
+    """tests/golden/admm_tiny.npz was produced by tools/make_golden.py from this oracle; the oracle
+    must keep reproducing it bit-for-bit (guards against silent edits of the restatement)."""
+    g = np.load(os.path.join(GOLD, "admm_tiny.npz"))
+    S, Y, c = est.proposed_algorithm_structured(g["subY"], g["Omega"], g["A"], g["B"], int(g["Imax"]), float(g["tau_Y"]),
+                                                float(g["tau_S"]), float(g["rho"]), "approximate")
+    assert _rel(S, g["S"]) < 1e-12 and _rel(Y, g["Y"]) < 1e-12
