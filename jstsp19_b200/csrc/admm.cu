@@ -50,6 +50,10 @@ struct AdmmP {
     double* cgramB; int nxc;            // [b][nxc][2*N*N]    partial Gram of V2           (conv only)
 };
 
+}  // namespace jstsp
+#include "admm_fast.cuh"
+namespace jstsp {
+
 // ---------------------------------------------------------------------------------------
 // setup kernels
 // ---------------------------------------------------------------------------------------
@@ -623,11 +627,24 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
     AdmmP<T> p{};
     p.N = N; p.M = M; p.G = G; p.P = P; p.RP = round_up8(N); p.NG = p.RP / 8; p.GP8 = round_up8(G); p.GNG = p.GP8 / 8;
     p.type = d->type; p.angles = angles ? 1 : 0; p.n_indx = d->n_indx; p.imax = imax;
+    // fast (TMA-pipelined) path: 'approximate', 16-byte aligned segments
+    const size_t esz0 = sizeof(cx<T>);
+    const bool no_fast = getenv("JSTSP_DISABLE_FAST") != nullptr;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    const bool segP = (P * esz0) % 16 == 0, segM = (M * esz0) % 16 == 0;
+    const bool b_ok = host || (al16(B_) && ((size_t)d->ld_B * esz0) % 16 == 0);
+    const bool rows8 = (N % 8 == 0) && (G % 8 == 0);
+    const bool io_ok = host || (al16(subY_) && al16(omega_) && ((size_t)d->ld_subY * esz0) % 16 == 0 && ((size_t)d->ld_omega * sizeof(T)) % 16 == 0);
+    const bool fast_v = approx && !no_fast && rows8 && segP && b_ok && io_ok && P <= cta_width(p.GNG) && P <= cta_width(p.NG) &&
+                        VstepFastSmem<T>::bytes(N, G, p.GNG, P) <= h->smem_optin && XupdFastSmem<T>::bytes(N, p.NG, want_conv) <= h->smem_optin;
+    const bool fast_xupd = fast_v;      // the pair shares the row-major T1 partial layout
+    const bool fast_xs = approx && !no_fast && rows8 && segM && XsFastSmem<T>::bytes(N, p.NG, P, want_conv) <= h->smem_optin;
     // chunk geometry
-    const int XC = ExpandSmem<T, CB>::chunk_cols(p.NG);           // columns per CTA of k_xs
+    const int XC = fast_xs ? cta_width(p.NG) : ExpandSmem<T, CB>::chunk_cols(p.NG);   // columns per CTA of k_xs
     const int nxc = ceil_div(M, XC);
     int MC = 128;
-    while (MC > 16 && XupdSmem<T>::bytes(p.RP, N, MC, want_conv) > 96 * 1024) MC /= 2;
+    if (fast_xupd) MC = FastCfg<T>::MC;
+    else while (MC > 16 && XupdSmem<T>::bytes(p.RP, N, MC, want_conv) > 96 * 1024) MC /= 2;
     p.MC = MC; p.nmc = ceil_div(M, MC); p.nxc = nxc;
     const int PCr = ExpandSmem<T, CB>::chunk_cols(approx ? p.GNG : p.NG);
     const int npc = ceil_div(P, ExpandSmem<T, CB>::chunk_cols(p.GNG));
@@ -637,6 +654,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
     size_t NM = (size_t)N * M, GPn = (size_t)G * P;
     int chunk_trials = batch;
     if (h->max_chunk > 0 && chunk_trials > h->max_chunk) chunk_trials = h->max_chunk;
+    cx<T>* bt_ws = nullptr;
     auto layout = [&](Arena& a, int nb, AdmmP<T>& q) {
         q.X = a.take<cx<T>>(NM * nb); q.V1 = a.take<cx<T>>(NM * nb); q.V2 = a.take<cx<T>>(NM * nb);
         q.C = a.take<cx<T>>(NM * nb); q.Xs = a.take<cx<T>>(NM * nb);
@@ -653,6 +671,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
             q.pA = a.take<cx<T>>((size_t)G * N * (sharedA ? 1 : nb)); q.ld_pA = sharedA ? 0 : (long long)G * N;
             q.BBHinv = q.BBH;   // inverted in place
         }
+        if (fast_xs) bt_ws = a.take<cx<T>>((size_t)P * M * (sharedB ? 1 : nb));
         if (angles) q.smask = a.take<unsigned char>(GPn * nb);
         if (want_conv) {
             q.convd = a.take<double>((size_t)nb * imax * 3);
@@ -699,6 +718,12 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
     if ((rc = set_smem(h, k_vupd<T>, sm_v))) return rc;
     if ((rc = set_smem(h, k_svt_weights<T>, sm_j))) return rc;
     if ((rc = set_smem(h, k_conv_norms<T>, sm_j))) return rc;
+    const size_t sm_fx = fast_xupd ? XupdFastSmem<T>::bytes(N, p.NG, want_conv) : 0;
+    const size_t sm_fv = fast_v ? VstepFastSmem<T>::bytes(N, G, p.GNG, P) : 0;
+    const size_t sm_fs = fast_xs ? XsFastSmem<T>::bytes(N, p.NG, P, want_conv) : 0;
+    if (fast_xupd && (rc = set_smem(h, k_xupd_t1_fast<T>, sm_fx))) return rc;
+    if (fast_v && (rc = set_smem(h, k_vstep_fast<T>, sm_fv))) return rc;
+    if (fast_xs && (rc = set_smem(h, k_xs_fast<T>, sm_fs))) return rc;
 
     JSTSP_CUDA(h, cudaMemsetAsync(h->d_flag, 0, sizeof(int), st));
     const size_t esz = sizeof(cx<T>);
@@ -745,6 +770,11 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
         const int nA = d->ld_A ? nb : 1, nB = d->ld_B ? nb : 1;
         JSTSP_LAUNCH(h, PK_SETUP, (k_aha<T><<<nA, 256, 0, st>>>(q)));
         { dim3 g(ceil_div(P, 64), ceil_div(P, 64), nB); JSTSP_LAUNCH(h, PK_SETUP, (k_bbh<T><<<g, 256, 0, st>>>(q))); }
+        const long long ld_Bt = d->ld_B ? (long long)P * M : 0;
+        if (fast_xs) {
+            dim3 g(ceil_div(P, 32), ceil_div(M, 32), nB);
+            JSTSP_LAUNCH(h, PK_SETUP, (k_transpose_b<T><<<g, 256, 0, st>>>(q.B, q.ld_B, bt_ws, ld_Bt, P, M)));
+        }
         if (!approx) {
             size_t smi = 2 * sizeof(cx<T>) * (size_t)(P > G ? P : G);
             if ((rc = set_smem(h, k_hpd_inverse<T>, smi))) return rc;
@@ -756,11 +786,23 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
             q.iter = it;
             if (angles) { dim3 g(1, nb); JSTSP_LAUNCH(h, PK_OTHER, (k_mask_grow<T><<<g, 64, 0, st>>>(q))); }
             JSTSP_LAUNCH(h, PK_EIG, (k_svt_weights<T><<<nb, 128, sm_j, st>>>(q)));
-            { dim3 g(q.nmc, nb); JSTSP_LAUNCH(h, PK_XUPD_T1, (k_xupd_t1<T, KB><<<g, kThreads, sm_x, st>>>(q))); }
-            { dim3 g(approx ? npc : ceil_div(P, PCr), nb); JSTSP_LAUNCH(h, PK_RES, (k_res<T, CB><<<g, kThreads, sm_res, st>>>(q))); }
-            if (approx) { dim3 g(npc, nb); JSTSP_LAUNCH(h, PK_Q, (k_q<T, CB><<<g, kThreads, sm_q, st>>>(q))); }
-            { dim3 g(ceil_div(P, kPV), nb); JSTSP_LAUNCH(h, PK_VUPD, (k_vupd<T><<<g, kThreads, sm_v, st>>>(q))); }
-            { dim3 g(nxc, nb); JSTSP_LAUNCH(h, PK_XS, (k_xs<T, CB><<<g, kThreads, sm_xs, st>>>(q))); }
+            {
+                dim3 g(q.nmc, nb);
+                if (fast_xupd) JSTSP_LAUNCH(h, PK_XUPD_T1, (k_xupd_t1_fast<T><<<g, kThreads, sm_fx, st>>>(q)));
+                else JSTSP_LAUNCH(h, PK_XUPD_T1, (k_xupd_t1<T, KB><<<g, kThreads, sm_x, st>>>(q)));
+            }
+            if (fast_v) {
+                JSTSP_LAUNCH(h, PK_RES, (k_vstep_fast<T><<<nb, kThreads, sm_fv, st>>>(q)));
+            } else {
+                { dim3 g(approx ? npc : ceil_div(P, PCr), nb); JSTSP_LAUNCH(h, PK_RES, (k_res<T, CB><<<g, kThreads, sm_res, st>>>(q))); }
+                if (approx) { dim3 g(npc, nb); JSTSP_LAUNCH(h, PK_Q, (k_q<T, CB><<<g, kThreads, sm_q, st>>>(q))); }
+                { dim3 g(ceil_div(P, kPV), nb); JSTSP_LAUNCH(h, PK_VUPD, (k_vupd<T><<<g, kThreads, sm_v, st>>>(q))); }
+            }
+            {
+                dim3 g(nxc, nb);
+                if (fast_xs) JSTSP_LAUNCH(h, PK_XS, (k_xs_fast<T><<<g, kThreads, sm_fs, st>>>(q, bt_ws, ld_Bt)));
+                else JSTSP_LAUNCH(h, PK_XS, (k_xs<T, CB><<<g, kThreads, sm_xs, st>>>(q)));
+            }
             if (want_conv) {
                 dim3 g(3, nb); JSTSP_LAUNCH(h, PK_OTHER, (k_conv_norms<T><<<g, 128, sm_j, st>>>(q)));
                 JSTSP_LAUNCH(h, PK_OTHER, (k_conv_finish<T><<<nb, 1, 0, st>>>(q)));

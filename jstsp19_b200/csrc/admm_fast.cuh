@@ -1,0 +1,539 @@
+// admm_fast.cuh - TMA-pipelined fast path of the proposed ADMM iteration ('approximate').
+// Included by admm.cu after AdmmP<T>.  Three kernels per iteration:
+//   k_xupd_t1_fast : SVT apply + X / V1 update + T1 = K B^H + next Gram        (grid nmc x batch)
+//   k_vstep_fast   : Res = A^H T1 - AHA V BBH ; alpha ; V ; S ; A S           (one CTA per trial)
+//   k_xs_fast      : Xs = (A S) B through the transposed copy B^T ; C ; V2    (grid nxc x batch)
+// Every product - streamed (stream_core.cuh: StreamPipe) or shared-memory resident
+// (smem_contract) - uses the same register tile: 8 rows x 2 outputs per thread.
+// Preconditions checked on the host (otherwise the generic kernels in admm.cu run):
+//   N % 8 == 0, G % 8 == 0, N, G <= 64, 16-byte aligned operands / segments (P, M even in
+//   fp32), and for k_vstep_fast P <= outputs of one CTA pass.
+#pragma once
+#include "stream_core.cuh"
+
+namespace jstsp {
+
+template <typename T> struct FastCfg {
+    static constexpr int MC = sizeof(T) == 4 ? 128 : 64;      // X-update column chunk
+};
+constexpr int kXupdStages = 3;   // 3-deep ring keeps two CTAs of k_xupd_t1_fast resident per SM
+
+// 4 consecutive complex values, 16-byte aligned
+template <typename T> __device__ __forceinline__ void ld4c(const cx<T>* __restrict__ p, cx<T> (&v)[4]) {
+    if constexpr (sizeof(T) == 4) {
+        float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 2);
+        v[0] = mk<T>(a.x, a.y); v[1] = mk<T>(a.z, a.w); v[2] = mk<T>(b.x, b.y); v[3] = mk<T>(b.z, b.w);
+    } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = p[u];
+    }
+}
+template <typename T> __device__ __forceinline__ void st4c(cx<T>* __restrict__ p, const cx<T> (&v)[4]) {
+    if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0].re, v[0].im, v[1].re, v[1].im);
+        *reinterpret_cast<float4*>(p + 2) = make_float4(v[2].re, v[2].im, v[3].re, v[3].im);
+    } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) p[u] = v[u];
+    }
+}
+template <typename T> __device__ __forceinline__ void ld4r(const T* __restrict__ p, T (&v)[4]) { load_rows4<T>(p, v); }
+
+// B^T copy: Bt[m + M*p] = B[p + P*m]   (grid ceil(P/32) x ceil(M/32) x nB)
+template <typename T>
+__global__ void __launch_bounds__(256) k_transpose_b(const cx<T>* __restrict__ B, long long ld_B, cx<T>* __restrict__ Bt, long long ld_Bt, int P, int M) {
+    __shared__ cx<T> tile[32][33];
+    const cx<T>* src = B + (long long)blockIdx.z * ld_B;
+    cx<T>* dst = Bt + (long long)blockIdx.z * ld_Bt;
+    const int p0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+    const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+    for (int i = ty; i < 32; i += 8)
+        if (p0 + tx < P && m0 + i < M) tile[i][tx] = src[(p0 + tx) + (long long)P * (m0 + i)];
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8)
+        if (m0 + tx < M && p0 + i < P) dst[(m0 + tx) + (long long)M * (p0 + i)] = tile[tx][i];
+}
+
+// =======================================================================================
+// kernel 1
+// =======================================================================================
+template <typename T>
+struct XupdFastSmem {
+    static constexpr int MC = FastCfg<T>::MC;
+    static size_t bytes(int N, int NG, bool conv) {      // N % 8 == 0 -> RP == N
+        size_t ring = StreamRing<T>::bytes(cta_width(NG), kXupdStages);
+        size_t zt = 2 * sizeof(T) * (size_t)N * (MC + 1);
+        size_t planes = (size_t)(conv ? 8 : 4) * N * MC * sizeof(T);
+        size_t w = 2 * sizeof(T) * (size_t)N * N;
+        return ring + ((zt + 15) & ~size_t(15)) + planes + w;
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_xupd_t1_fast(AdmmP<T> p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bars[kStages];
+    constexpr int MC = FastCfg<T>::MC, ZP = MC + 1;
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int N = p.N, RP = p.RP, NG = p.NG, P = p.P;      // RP == N here
+    const int W = cta_width(NG);
+    const int c0 = chunk * MC;
+    const int ncols = (p.M - c0) < MC ? (p.M - c0) : MC;
+    const bool conv = p.convd != nullptr;
+    const size_t ringb = StreamRing<T>::bytes(W, kXupdStages);
+    cx<T>* ring = reinterpret_cast<cx<T>*>(smem);
+    T* Ztre = reinterpret_cast<T*>(smem + ringb);                       // [N][ZP]  Z transposed, padded pitch
+    T* Ztim = Ztre + (size_t)N * ZP;
+    T* Kre = reinterpret_cast<T*>(smem + ringb + ((2 * sizeof(T) * (size_t)N * ZP + 15) & ~size_t(15)));   // [MC][RP]
+    T* Kim = Kre + (size_t)RP * MC;
+    T* Nre = Kim + (size_t)RP * MC;                                      // next SVT input
+    T* Nim = Nre + (size_t)RP * MC;
+    T* Cx = Nim + (size_t)RP * MC;                                       // conv: X re/im, V1 re/im planes
+    T* Wre = Nim + (size_t)RP * MC * (conv ? 5 : 1);                     // [N][RP]: Wre[k*RP + r] = W[r,k]
+    T* Wim = Wre + (size_t)N * RP;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kXupdStages; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    // start streaming B(:, chunk) right away; the element-wise prologue below hides the first latency
+    const cx<T>* Bc = p.B + (long long)b * p.ld_B + (long long)c0 * P;
+    StreamPipe<T, kXupdStages> pipe;
+    uint32_t it = 0;
+    pipe.start(ring, bars, it, Bc, (long long)P, W, P < W ? P : W, ncols);
+
+    const T rho = (T)p.rho[b];
+    const T irho = T(1) / rho;
+    const size_t off = (size_t)b * N * p.M + (size_t)c0 * N;
+    cx<T>* __restrict__ X = p.X + off; cx<T>* __restrict__ V1 = p.V1 + off;
+    const cx<T>* __restrict__ V2 = p.V2 + off; const cx<T>* __restrict__ C = p.C + off; const cx<T>* __restrict__ Xs = p.Xs + off;
+    const cx<T>* __restrict__ subY = p.subY + (long long)b * p.ld_subY + (size_t)c0 * N;
+    const T* __restrict__ om = p.omega + (long long)b * p.ld_omega + (size_t)c0 * N;
+    const cx<T>* Wg = p.W + (size_t)b * N * N;
+    for (int t = threadIdx.x; t < N * N; t += kThreads) { cx<T> w = Wg[t]; Wre[t] = w.re; Wim[t] = w.im; }   // (r + N*k) == k*RP + r
+    {   // Z = X - V1/rho, transposed into [k][c] (coalesced global reads, padded pitch -> conflict-free)
+        const int nel = N * ncols;
+        for (int t0 = 0; t0 < N * MC; t0 += 4 * kThreads) {
+            cx<T> x[4], v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { int t = t0 + u * kThreads + threadIdx.x; if (t < nel) { x[u] = X[t]; v[u] = V1[t]; } }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int t = t0 + u * kThreads + threadIdx.x;
+                if (t < N * MC) {
+                    int r = t % N, c = t / N;
+                    T zr = 0, zi = 0;
+                    if (t < nel) { zr = x[u].re - irho * v[u].re; zi = x[u].im - irho * v[u].im; }
+                    Ztre[r * ZP + c] = zr; Ztim[r * ZP + c] = zi;
+                }
+            }
+        }
+        if (ncols < MC) {    // padding columns of the streamed operand / Gram planes must be zero
+            for (int t = threadIdx.x + ncols * RP; t < MC * RP; t += kThreads) { Kre[t] = 0; Kim[t] = 0; Nre[t] = 0; Nim[t] = 0; }
+            if (conv) for (int t = threadIdx.x + ncols * RP; t < MC * RP; t += kThreads) { Cx[t] = 0; Cx[t + RP * MC] = 0; Cx[t + 2 * RP * MC] = 0; Cx[t + 3 * RP * MC] = 0; }
+        }
+    }
+    __syncthreads();
+    // Y = W Z (8 rows x 1 column per thread), then the element-wise updates       (proposed_algorithm.m:35-43,64)
+    const bool last = (p.iter == p.imax - 1) && p.Yout != nullptr;
+    for (int item = threadIdx.x; item < NG * MC; item += kThreads) {
+        const int c = item % MC, rg = item / MC;
+        if (c >= ncols) continue;
+        T yr[kRB], yi[kRB];
+#pragma unroll
+        for (int r = 0; r < kRB; ++r) { yr[r] = 0; yi[r] = 0; }
+#pragma unroll 4
+        for (int k = 0; k < N; ++k) {
+            const T zr = Ztre[k * ZP + c], zi = Ztim[k * ZP + c];
+            T wr[kRB], wi[kRB];
+            load_rows8<T>(Wre, RP, k, rg, wr);
+            load_rows8<T>(Wim, RP, k, rg, wi);
+#pragma unroll
+            for (int r = 0; r < kRB; ++r) cmac<T>(yr[r], yi[r], wr[r], wi[r], zr, zi);
+        }
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int r0 = rg * kRB + 4 * hf;
+            const size_t gi = (size_t)c * N + r0;
+            cx<T> v1[4], v2[4], cc[4], xs[4], sy[4], xo[4], n1[4]; T omv[4];
+            ld4c<T>(V1 + gi, v1); ld4c<T>(V2 + gi, v2); ld4c<T>(C + gi, cc); ld4c<T>(Xs + gi, xs); ld4c<T>(subY + gi, sy); ld4r<T>(om + gi, omv);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const T y_r = yr[4 * hf + u], y_i = yi[4 * hf + u];
+                const T d = T(1) / (omv[u] + T(2) * rho);                                                    // iK1 (.m:20)
+                const T xr = (v1[u].re + rho * y_r + sy[u].re + v2[u].re + rho * cc[u].re + rho * xs[u].re) * d;   // .m:38-40
+                const T xi = (v1[u].im + rho * y_i + sy[u].im + v2[u].im + rho * cc[u].im + rho * xs[u].im) * d;
+                const T n1r = v1[u].re + rho * (y_r - xr), n1i = v1[u].im + rho * (y_i - xi);                 // .m:64
+                xo[u] = mk<T>(xr, xi); n1[u] = mk<T>(n1r, n1i);
+                const int si = c * RP + r0 + u;
+                Kre[si] = xr - irho * v2[u].re - cc[u].re; Kim[si] = xi - irho * v2[u].im - cc[u].im;         // .m:43
+                Nre[si] = xr - irho * n1r; Nim[si] = xi - irho * n1i;                                         // next SVT input (.m:35)
+                if (conv) { Cx[si] = xr; Cx[RP * MC + si] = xi; Cx[2 * RP * MC + si] = n1r; Cx[3 * RP * MC + si] = n1i; }
+            }
+            st4c<T>(X + gi, xo); st4c<T>(V1 + gi, n1);
+            if (last) {
+                cx<T> yo[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) yo[u] = mk<T>(yr[4 * hf + u], yi[4 * hf + u]);
+                cx<T>* yp = p.Yout + (long long)b * p.ld_Y + (size_t)(c0 + c) * N + r0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) yp[u] = yo[u];
+            }
+        }
+    }
+    __syncthreads();
+    // T1 partial = K(:,chunk) B(:,chunk)^H, stored row-major [N][P]                (.m:47)
+    cx<T>* T1 = p.T1 + ((size_t)b * p.nmc + chunk) * (size_t)N * P;
+    const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+    const int rg = warp % NG, og = warp / NG;
+    for (int o0 = 0; o0 < P; o0 += W) {
+        if (o0 > 0) pipe.start(ring, bars, it, Bc + o0, (long long)P, W, (P - o0) < W ? (P - o0) : W, ncols);
+        T ar[kRB][2], ai[kRB][2];
+#pragma unroll
+        for (int r = 0; r < kRB; ++r) { ar[r][0] = ar[r][1] = ai[r][0] = ai[r][1] = T(0); }
+        it = pipe.template run<true>(Kre, Kim, RP, NG, ar, ai);
+        if (og < kWarps / NG) {
+            const int ob = o0 + og * kOW;
+            if (ob + out_of<T>(lane, 0) < P) {
+#pragma unroll
+                for (int r = 0; r < kRB; ++r) {
+                    cx<T>* rowp = T1 + (size_t)(rg * kRB + r) * P + ob;
+                    if (ob + out_of<T>(lane, 1) < P) store_pair<T>(rowp, lane, ar[r][0], ai[r][0], ar[r][1], ai[r][1]);
+                    else rowp[out_of<T>(lane, 0)] = mk<T>(ar[r][0], ai[r][0]);
+                }
+            }
+        }
+    }
+    // partial Gram of the next SVT input (the ring is idle now and serves as scratch)
+    T* scratch = reinterpret_cast<T*>(smem);
+    gram_blocked<T>(Nre, Nim, RP, N, ncols, scratch, ringb, p.gram + ((size_t)b * p.nmc + chunk) * 2 * N * N);
+    if (conv) {
+        size_t cg = (size_t)p.nmc * 2 * N * N;
+        double* base = p.cgramA + (size_t)b * 2 * cg + (size_t)chunk * 2 * N * N;
+        gram_blocked<T>(Cx + 2 * (size_t)RP * MC, Cx + 3 * (size_t)RP * MC, RP, N, ncols, scratch, ringb, base);          // V1
+        gram_blocked<T>(Cx, Cx + (size_t)RP * MC, RP, N, ncols, scratch, ringb, base + cg);                              // X
+    }
+}
+
+// =======================================================================================
+// kernel 2 (one CTA per trial)
+// =======================================================================================
+template <typename T>
+struct VstepFastSmem {
+    __host__ __device__ static size_t region0(int N, int G, int GNG, int P) {
+        size_t ring = StreamRing<T>::bytes(cta_width(GNG));
+        size_t exch = sizeof(cx<T>) * (size_t)(N + G) * round_up_to(P, kOW);
+        return ring > exch ? ring : exch;
+    }
+    __host__ __device__ static size_t bytes(int N, int G, int GNG, int P) {
+        size_t lv = 2 * sizeof(T) * (size_t)G * round_up_to(P, stage_cols<T>());
+        size_t small = 2 * sizeof(T) * ((size_t)(N + G) * G + (size_t)G * G + (size_t)G * N);
+        return region0(N, G, GNG, P) + lv + small;
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_vstep_fast(AdmmP<T> p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bars[kStages];
+    __shared__ double red[kWarps][3];
+    __shared__ double s_alpha;
+    const int b = blockIdx.x;
+    const int N = p.N, G = p.G, P = p.P, RG = p.GP8, NGg = p.GNG, RN = p.RP, NGn = p.NG;     // RG == G, RN == N
+    const int W = cta_width(NGg);
+    const int pitch = round_up_to(P, kOW);
+    const int Pc = round_up_to(P, stage_cols<T>());
+    cx<T>* ring = reinterpret_cast<cx<T>*>(smem);
+    cx<T>* E = reinterpret_cast<cx<T>*>(smem);                         // exchange rows [N+G][pitch], aliases the ring
+    T* Lre = reinterpret_cast<T*>(smem + VstepFastSmem<T>::region0(N, G, NGg, P));   // planar [Pc][RG]: V, then Res
+    T* Lim = Lre + (size_t)RG * Pc;
+    T* A1re = Lim + (size_t)RG * Pc;                                   // [A^H | -AHA] : [(N+G)][RG]
+    T* A1im = A1re + (size_t)(N + G) * RG;
+    T* Qre = A1im + (size_t)(N + G) * RG;                              // AHA : [G][RG]
+    T* Qim = Qre + (size_t)G * RG;
+    T* Sre = Qim + (size_t)G * RG;                                     // A : [G][RN]
+    T* Sim = Sre + (size_t)G * RN;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const cx<T>* BBH = p.BBH + (long long)b * p.ld_BBH;
+    StreamPipe<T> pipe;
+    uint32_t it = 0;
+    pipe.start(ring, bars, it, BBH, (long long)P, W, P, P);           // V BBH = sum_p V(:,p) conj(BBH(:,p)).' (BBH Hermitian)
+    cx<T>* __restrict__ V = p.V + (size_t)b * G * P;
+    const cx<T>* A = p.A + (long long)b * p.ld_A;
+    const cx<T>* AHA = p.AHA + (long long)b * p.ld_AHA;
+    for (int t = threadIdx.x; t < N * G; t += kThreads) {
+        const int n = t % N, g = t / N;
+        const cx<T> a = A[t];
+        A1re[n * RG + g] = a.re; A1im[n * RG + g] = -a.im;             // (A^H)[g,n] = conj(A[n,g])
+        Sre[g * RN + n] = a.re; Sim[g * RN + n] = a.im;
+    }
+    for (int t = threadIdx.x; t < G * G; t += kThreads) {
+        const int g = t % G, k = t / G;
+        const cx<T> a = AHA[t];
+        A1re[(N + k) * RG + g] = -a.re; A1im[(N + k) * RG + g] = -a.im;
+        Qre[k * RG + g] = a.re; Qim[k * RG + g] = a.im;
+    }
+    double vv = 0.0;
+    for (int t = threadIdx.x; t < RG * Pc; t += kThreads) {
+        cx<T> v = mk<T>(T(0), T(0));
+        if (t < G * P) v = V[t];                                       // (g + G*o) == o*RG + g
+        Lre[t] = v.re; Lim[t] = v.im;
+        vv += (double)v.re * v.re + (double)v.im * v.im;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+    const int rg = warp % NGg, og = warp / NGg;
+    const bool active = og < kWarps / NGg;
+    const int o_0 = og * kOW + out_of<T>(lane, 0), o_1 = og * kOW + out_of<T>(lane, 1);
+    T ar[kRB][2], ai[kRB][2];
+#pragma unroll
+    for (int r = 0; r < kRB; ++r) { ar[r][0] = ar[r][1] = ai[r][0] = ai[r][1] = T(0); }
+    it = pipe.template run<true>(Lre, Lim, RG, NGg, ar, ai);
+    // exchange rows: [0,N) = summed T1 (row-major partials), [N,N+G) = V BBH
+    if (active && og * kOW < pitch) {
+#pragma unroll
+        for (int r = 0; r < kRB; ++r) store_pair<T>(E + (size_t)(N + rg * kRB + r) * pitch + og * kOW, lane, ar[r][0], ai[r][0], ar[r][1], ai[r][1]);
+    }
+    const cx<T>* T1 = p.T1 + (size_t)b * p.nmc * N * P;
+    for (int t = threadIdx.x; t < N * P; t += kThreads) {
+        T re = 0, im = 0;
+        for (int k = 0; k < p.nmc; ++k) { cx<T> v = T1[(size_t)k * N * P + t]; re += v.re; im += v.im; }
+        E[(size_t)(t / P) * pitch + (t % P)] = mk<T>(re, im);
+    }
+    __syncthreads();
+    // Res = A^H T1 - AHA (V BBH)        (.m:47)
+    T rr_[kRB][2], ri_[kRB][2];
+#pragma unroll
+    for (int r = 0; r < kRB; ++r) { rr_[r][0] = rr_[r][1] = ri_[r][0] = ri_[r][1] = T(0); }
+    if (active && og * kOW < pitch) smem_contract<T>(A1re, A1im, RG, rg, E, pitch, og, N + G, rr_, ri_);
+    double rr = 0.0;
+    if (active) {
+#pragma unroll
+        for (int r = 0; r < kRB; ++r) {
+            if (o_0 < P) rr += (double)rr_[r][0] * rr_[r][0] + (double)ri_[r][0] * ri_[r][0];
+            if (o_1 < P) rr += (double)rr_[r][1] * rr_[r][1] + (double)ri_[r][1] * ri_[r][1];
+        }
+    }
+    __syncthreads();                                                   // V planes and E fully consumed
+    if (active) {
+#pragma unroll
+        for (int r = 0; r < kRB; ++r) {
+            if (o_0 < P) { Lre[o_0 * RG + rg * kRB + r] = rr_[r][0]; Lim[o_0 * RG + rg * kRB + r] = ri_[r][0]; }
+            if (o_1 < P) { Lre[o_1 * RG + rg * kRB + r] = rr_[r][1]; Lim[o_1 * RG + rg * kRB + r] = ri_[r][1]; }
+        }
+    }
+    __syncthreads();
+    pipe.start(ring, bars, it, BBH, (long long)P, W, P, P);
+#pragma unroll
+    for (int r = 0; r < kRB; ++r) { ar[r][0] = ar[r][1] = ai[r][0] = ai[r][1] = T(0); }
+    it = pipe.template run<true>(Lre, Lim, RG, NGg, ar, ai);
+    if (active && og * kOW < pitch) {
+#pragma unroll
+        for (int r = 0; r < kRB; ++r) store_pair<T>(E + (size_t)(rg * kRB + r) * pitch + og * kOW, lane, ar[r][0], ai[r][0], ar[r][1], ai[r][1]);
+    }
+    __syncthreads();
+    // <Res, Q>, Q = AHA (Res BBH)        (.m:48)
+#pragma unroll
+    for (int r = 0; r < kRB; ++r) { ar[r][0] = ar[r][1] = ai[r][0] = ai[r][1] = T(0); }
+    if (active && og * kOW < pitch) smem_contract<T>(Qre, Qim, RG, rg, E, pitch, og, G, ar, ai);
+    double rq = 0.0;
+    if (active) {
+#pragma unroll
+        for (int r = 0; r < kRB; ++r) {
+            if (o_0 < P) rq += (double)rr_[r][0] * ar[r][0] + (double)ri_[r][0] * ai[r][0];
+            if (o_1 < P) rq += (double)rr_[r][1] * ar[r][1] + (double)ri_[r][1] * ai[r][1];
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) { rr += __shfl_down_sync(0xffffffffu, rr, o); rq += __shfl_down_sync(0xffffffffu, rq, o); vv += __shfl_down_sync(0xffffffffu, vv, o); }
+    if (lane == 0) { red[warp][0] = rr; red[warp][1] = rq; red[warp][2] = vv; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, c = 0, d = 0;
+        for (int w = 0; w < kWarps; ++w) { a += red[w][0]; c += red[w][1]; d += red[w][2]; }
+        s_alpha = a / c;                                               // alpha = res'res / (res' R res)  (.m:48)
+        double* o = p.dots + (size_t)b * p.npc * 4;
+        o[0] = a; o[1] = c; o[2] = d; o[3] = 0.0;
+        for (int k = 1; k < p.npc; ++k) { o[4 * k] = 0.0; o[4 * k + 1] = 0.0; o[4 * k + 2] = 0.0; o[4 * k + 3] = 0.0; }
+    }
+    __syncthreads();
+    // V += alpha Res ; S = soft(V) (masked)          (.m:50,56 ; _angles.m:68)
+    const T alpha = (T)s_alpha;
+    const T thr = (T)(p.tauS[b] / p.rho[b]);
+    cx<T>* __restrict__ S = p.S + (size_t)b * G * P;
+    const unsigned char* mask = p.angles ? p.smask + (size_t)b * G * P : nullptr;
+    if (active) {
+        T s_re[kRB][2], s_im[kRB][2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int o = j == 0 ? o_0 : o_1;
+#pragma unroll
+            for (int r = 0; r < kRB; ++r) { s_re[r][j] = 0; s_im[r][j] = 0; }
+            if (o < P) {
+                const size_t gi = (size_t)o * G + rg * kRB;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    cx<T> v[4], s[4];
+                    ld4c<T>(V + gi + 4 * hf, v);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = 4 * hf + u;
+                        v[u] = mk<T>(v[u].re + alpha * rr_[r][j], v[u].im + alpha * ri_[r][j]);
+                        s[u] = mk<T>(soft1<T>(v[u].re, thr), soft1<T>(v[u].im, thr));
+                        if (mask && !mask[gi + r]) s[u] = mk<T>(T(0), T(0));
+                        s_re[r][j] = s[u].re; s_im[r][j] = s[u].im;
+                    }
+                    st4c<T>(V + gi + 4 * hf, v); st4c<T>(S + gi + 4 * hf, s);
+                }
+            }
+        }
+        if (og * kOW < pitch) {
+#pragma unroll
+            for (int r = 0; r < kRB; ++r) store_pair<T>(E + (size_t)(rg * kRB + r) * pitch + og * kOW, lane, s_re[r][0], s_im[r][0], s_re[r][1], s_im[r][1]);
+        }
+    }
+    __syncthreads();
+    // A S      (.m:58, left factor)
+    {
+        const int rgn = warp % NGn, ogn = warp / NGn;
+        if (ogn < kWarps / NGn && ogn * kOW < pitch) {
+#pragma unroll
+            for (int r = 0; r < kRB; ++r) { ar[r][0] = ar[r][1] = ai[r][0] = ai[r][1] = T(0); }
+            smem_contract<T>(Sre, Sim, RN, rgn, E, pitch, ogn, G, ar, ai);
+            cx<T>* __restrict__ AS = p.AS + (size_t)b * N * P;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int o = ogn * kOW + out_of<T>(lane, j);
+                if (o < P) {
+                    const size_t gi = (size_t)o * N + rgn * kRB;
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        cx<T> v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) v[u] = mk<T>(ar[4 * hf + u][j], ai[4 * hf + u][j]);
+                        st4c<T>(AS + gi + 4 * hf, v);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// =======================================================================================
+// kernel 3
+// =======================================================================================
+constexpr int kPCH = 256;   // reduction columns of A S held in shared memory at a time
+template <typename T>
+struct XsFastSmem {
+    __host__ __device__ static size_t region0(int N, int NG, bool conv) {
+        size_t ring = StreamRing<T>::bytes(cta_width(NG));
+        size_t cv = conv ? 2 * sizeof(T) * (size_t)N * cta_width(NG) : 0;     // V2 planes alias the ring
+        return ring > cv ? ring : cv;
+    }
+    static size_t bytes(int N, int NG, int P, bool conv) {
+        int pch = round_up_to(P < kPCH ? P : kPCH, stage_cols<T>());
+        size_t l = 2 * sizeof(T) * (size_t)N * pch;
+        size_t scratch = conv ? (size_t)N * N * 2 * sizeof(T) : 0;            // at least one Gram slice
+        return region0(N, NG, conv) + (l > scratch ? l : scratch);
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_xs_fast(AdmmP<T> p, const cx<T>* __restrict__ Bt, long long ld_Bt) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bars[kStages];
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int N = p.N, P = p.P, M = p.M, RP = p.RP, NG = p.NG;      // RP == N
+    const int W = cta_width(NG);
+    const int m0 = chunk * W;
+    const int nvalid = (M - m0) < W ? (M - m0) : W;
+    const bool conv = p.convd != nullptr;
+    cx<T>* ring = reinterpret_cast<cx<T>*>(smem);
+    const size_t r0b = XsFastSmem<T>::region0(N, NG, conv);
+    T* Lre = reinterpret_cast<T*>(smem + r0b);
+    const int pchmax = P < kPCH ? P : kPCH;
+    const int pchp = round_up_to(pchmax, stage_cols<T>());
+    T* Lim = Lre + (size_t)RP * pchp;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const cx<T>* Btc = Bt + (long long)b * ld_Bt + m0;
+    const cx<T>* __restrict__ AS = p.AS + (size_t)b * N * P;
+    StreamPipe<T> pipe;
+    uint32_t it = 0;
+    T ar[kRB][2], ai[kRB][2];
+#pragma unroll
+    for (int r = 0; r < kRB; ++r) { ar[r][0] = ar[r][1] = ai[r][0] = ai[r][1] = T(0); }
+    for (int p0 = 0; p0 < P; p0 += pchmax) {
+        const int np = (P - p0) < pchmax ? (P - p0) : pchmax;
+        pipe.start(ring, bars, it, Btc + (long long)p0 * M, (long long)M, W, nvalid, np);
+        // stage (A S)(:, p0:p0+np) planar; zero the padding columns
+        for (int t0 = 0; t0 < RP * pchp; t0 += 4 * kThreads) {
+            cx<T> v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { int t = t0 + u * kThreads + threadIdx.x; v[u] = mk<T>(T(0), T(0)); if (t < N * np) v[u] = AS[(size_t)N * p0 + t]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { int t = t0 + u * kThreads + threadIdx.x; if (t < RP * pchp) { Lre[t] = v[u].re; Lim[t] = v[u].im; } }
+        }
+        __syncthreads();
+        it = pipe.template run<false>(Lre, Lim, RP, NG, ar, ai);
+    }
+    const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+    const int rg = warp % NG, og = warp / NG;
+    T* Vre = reinterpret_cast<T*>(smem);
+    T* Vim = Vre + (size_t)RP * W;
+    if (conv) {
+        for (int t = threadIdx.x; t < 2 * RP * W; t += kThreads) Vre[t] = 0;
+        __syncthreads();
+    }
+    if (og < kWarps / NG) {
+        const T rho = (T)p.rho[b];
+        const T irho = T(1) / rho, kap = rho / (rho + T(1));
+        const size_t off = (size_t)b * N * M + (size_t)m0 * N;
+        const cx<T>* __restrict__ X = p.X + off; cx<T>* __restrict__ V2 = p.V2 + off; cx<T>* __restrict__ C = p.C + off; cx<T>* __restrict__ Xs = p.Xs + off;
+        cx<T> x[2][2][4], v2[2][2][4];
+        int cs[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            cs[j] = og * kOW + out_of<T>(lane, j);
+            if (cs[j] < nvalid) {
+                const size_t gi = (size_t)cs[j] * N + rg * kRB;
+                ld4c<T>(X + gi, x[j][0]); ld4c<T>(X + gi + 4, x[j][1]); ld4c<T>(V2 + gi, v2[j][0]); ld4c<T>(V2 + gi + 4, v2[j][1]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (cs[j] < nvalid) {
+                const size_t gi = (size_t)cs[j] * N + rg * kRB;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    cx<T> so[4], co[4], vo[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = 4 * hf + u;
+                        const T sr = ar[r][j], si = ai[r][j];
+                        const cx<T> xx = x[j][hf][u], vv2 = v2[j][hf][u];
+                        const T cr = kap * (xx.re - sr - irho * vv2.re), ci = kap * (xx.im - si - irho * vv2.im);     // .m:61
+                        const T nr = vv2.re + rho * (cr - xx.re + sr), ni = vv2.im + rho * (ci - xx.im + si);         // .m:65
+                        so[u] = mk<T>(sr, si); co[u] = mk<T>(cr, ci); vo[u] = mk<T>(nr, ni);
+                        if (conv) { Vre[cs[j] * RP + rg * kRB + r] = nr; Vim[cs[j] * RP + rg * kRB + r] = ni; }
+                    }
+                    st4c<T>(Xs + gi + 4 * hf, so); st4c<T>(C + gi + 4 * hf, co); st4c<T>(V2 + gi + 4 * hf, vo);
+                }
+            }
+        }
+    }
+    if (conv) {
+        __syncthreads();
+        const size_t lbytes = 2 * sizeof(T) * (size_t)RP * pchp;
+        const size_t sb = lbytes > (size_t)N * N * 2 * sizeof(T) ? lbytes : (size_t)N * N * 2 * sizeof(T);
+        gram_blocked<T>(Vre, Vim, RP, N, nvalid, Lre, sb, p.cgramB + ((size_t)b * p.nxc + chunk) * 2 * N * N);
+    }
+}
+
+}  // namespace jstsp
