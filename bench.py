@@ -152,6 +152,7 @@ def main():
     ap.add_argument("--cpu-trials", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--shared-b", action="store_true", help="diagnostic: one pilot matrix B for all trials (L2-resident dictionary)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -177,6 +178,8 @@ def main():
     first = rank * nb                                  # weak scaling: every rank owns `nb` trials per step
     snr = torch.tensor([SNR_SWEEP[(first + k) % len(SNR_SWEEP)] for k in range(nb)], dtype=torch.float64)
     data = synth.make_batch(s, nb, snr, seed=20190913, first_trial=first, device=dev, cdtype=cd)
+    if args.shared_b:
+        data["B"] = data["B"][:1].contiguous()
     eng = AdmmEngine(local, args.precision)
     S = torch.empty(nb, P, G, dtype=cd, device=dev)
 

@@ -72,6 +72,10 @@ int jstsp_set_chunk(jstsp_handle* h, int max_trials_per_pass);
 int jstsp_profile(jstsp_handle* h, int enable);
 int jstsp_profile_read(jstsp_handle* h, int slot, double* total_ms, long long* launches, const char** name);
 
+/* Developer hook: device buffer (8 x int64 per CTA of the largest grid) that receives in-kernel
+ * clock64() phase timestamps of the ADMM fast-path kernels; NULL (default) disables. */
+int jstsp_debug_buffer(jstsp_handle* h, void* device_buffer);
+
 /* ---- proposed ADMM matrix completion ------------------------------------------- */
 typedef struct {
     int N, M;          /* subY is N x M  (rows = RF-chain domain, cols = training instants) */

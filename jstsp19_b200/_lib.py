@@ -53,6 +53,7 @@ def _load():
     lib.jstsp_launch_count.argtypes = [vp]
     lib.jstsp_launch_count.restype = ll
     lib.jstsp_set_chunk.argtypes = [vp, i]
+    lib.jstsp_debug_buffer.argtypes = [vp, vp]
     lib.jstsp_profile.argtypes = [vp, i]
     lib.jstsp_profile_read.argtypes = [vp, i, dp, C.POINTER(ll), C.POINTER(C.c_char_p)]
     lib.jstsp_proposed_algorithm.argtypes = [vp, C.POINTER(AdmmDesc), i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -68,7 +69,7 @@ lib = _load()
 #: every symbol include/jstsp_b200.h declares (checked by tests/test_abi.py)
 EXPORTED = [
     "jstsp_create", "jstsp_destroy", "jstsp_last_error", "jstsp_version", "jstsp_set_stream",
-    "jstsp_synchronize", "jstsp_launch_count", "jstsp_set_chunk", "jstsp_profile", "jstsp_profile_read",
+    "jstsp_synchronize", "jstsp_launch_count", "jstsp_set_chunk", "jstsp_profile", "jstsp_profile_read", "jstsp_debug_buffer",
     "jstsp_proposed_algorithm", "jstsp_proposed_algorithm_angles",
     "jstsp_svt", "jstsp_mc_svt", "jstsp_mc_admm",
 ]

@@ -48,6 +48,7 @@ struct AdmmP {
     double* convd;                      // [b][imax][3] diagnostics in double (or null)
     double* cgramA;                     // [b][2][nmc][2*N*N] partial Grams of V1 and X   (conv only)
     double* cgramB; int nxc;            // [b][nxc][2*N*N]    partial Gram of V2           (conv only)
+    long long* dbg; int dbg_kernel;     // phase timestamps of kernel #dbg_kernel (0 xupd, 1 vstep, 2 xs), or null
 };
 
 }  // namespace jstsp
@@ -627,9 +628,11 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
     AdmmP<T> p{};
     p.N = N; p.M = M; p.G = G; p.P = P; p.RP = round_up8(N); p.NG = p.RP / 8; p.GP8 = round_up8(G); p.GNG = p.GP8 / 8;
     p.type = d->type; p.angles = angles ? 1 : 0; p.n_indx = d->n_indx; p.imax = imax;
+    p.dbg = h->dbg; p.dbg_kernel = getenv("JSTSP_DBG_KERNEL") ? atoi(getenv("JSTSP_DBG_KERNEL")) : 0;
     // fast (TMA-pipelined) path: 'approximate', 16-byte aligned segments
     const size_t esz0 = sizeof(cx<T>);
     const bool no_fast = getenv("JSTSP_DISABLE_FAST") != nullptr;
+    const bool overlap_eig = getenv("JSTSP_NO_OVERLAP") == nullptr;
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     const bool segP = (P * esz0) % 16 == 0, segM = (M * esz0) % 16 == 0;
     const bool b_ok = host || (al16(B_) && ((size_t)d->ld_B * esz0) % 16 == 0);
@@ -655,10 +658,12 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
     int chunk_trials = batch;
     if (h->max_chunk > 0 && chunk_trials > h->max_chunk) chunk_trials = h->max_chunk;
     cx<T>* bt_ws = nullptr;
+    const int Wn = cta_width(p.NG);
+    const long long Mpad = (long long)ceil_div(M, Wn) * Wn;      // B^T is stored in Wn-wide column tiles
     auto layout = [&](Arena& a, int nb, AdmmP<T>& q) {
         q.X = a.take<cx<T>>(NM * nb); q.V1 = a.take<cx<T>>(NM * nb); q.V2 = a.take<cx<T>>(NM * nb);
         q.C = a.take<cx<T>>(NM * nb); q.Xs = a.take<cx<T>>(NM * nb);
-        q.W = a.take<cx<T>>((size_t)N * N * nb);
+        q.W = a.take<cx<T>>((size_t)N * N * nb * 2);           // double-buffered: the eigen-solve of iteration i+1 overlaps iteration i
         q.gram = a.take<double>((size_t)nb * q.nmc * 2 * N * N);
         q.T1 = a.take<cx<T>>((size_t)nb * q.nmc * N * P);
         q.V = a.take<cx<T>>(GPn * nb); q.Res = a.take<cx<T>>(GPn * nb); q.S = a.take<cx<T>>(GPn * nb);
@@ -671,7 +676,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
             q.pA = a.take<cx<T>>((size_t)G * N * (sharedA ? 1 : nb)); q.ld_pA = sharedA ? 0 : (long long)G * N;
             q.BBHinv = q.BBH;   // inverted in place
         }
-        if (fast_xs) bt_ws = a.take<cx<T>>((size_t)P * M * (sharedB ? 1 : nb));
+        if (fast_xs) bt_ws = a.take<cx<T>>((size_t)P * Mpad * (sharedB ? 1 : nb));
         if (angles) q.smask = a.take<unsigned char>(GPn * nb);
         if (want_conv) {
             q.convd = a.take<double>((size_t)nb * imax * 3);
@@ -770,10 +775,10 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
         const int nA = d->ld_A ? nb : 1, nB = d->ld_B ? nb : 1;
         JSTSP_LAUNCH(h, PK_SETUP, (k_aha<T><<<nA, 256, 0, st>>>(q)));
         { dim3 g(ceil_div(P, 64), ceil_div(P, 64), nB); JSTSP_LAUNCH(h, PK_SETUP, (k_bbh<T><<<g, 256, 0, st>>>(q))); }
-        const long long ld_Bt = d->ld_B ? (long long)P * M : 0;
+        const long long ld_Bt = d->ld_B ? (long long)P * Mpad : 0;
         if (fast_xs) {
-            dim3 g(ceil_div(P, 32), ceil_div(M, 32), nB);
-            JSTSP_LAUNCH(h, PK_SETUP, (k_transpose_b<T><<<g, 256, 0, st>>>(q.B, q.ld_B, bt_ws, ld_Bt, P, M)));
+            dim3 g(ceil_div(P, 32), (unsigned)(Mpad / 32), nB);
+            JSTSP_LAUNCH(h, PK_SETUP, (k_transpose_b<T><<<g, 256, 0, st>>>(q.B, q.ld_B, bt_ws, ld_Bt, P, M, Wn)));
         }
         if (!approx) {
             size_t smi = 2 * sizeof(cx<T>) * (size_t)(P > G ? P : G);
@@ -782,14 +787,31 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
             JSTSP_LAUNCH(h, PK_SETUP, (k_hpd_inverse<T><<<nA, 256, smi, st>>>(q.AHA, (long long)G * G, G)));
             JSTSP_LAUNCH(h, PK_SETUP, (k_pinv_left<T><<<nA, 256, 0, st>>>(q, q.AHA, q.ld_AHA)));
         }
+        cx<T>* const Wslots = q.W;
+        const size_t wslot = (size_t)N * N * nb;
+        if (imax > 0) JSTSP_LAUNCH(h, PK_EIG, (k_svt_weights<T><<<nb, 128, sm_j, st>>>(q)));      // W(0) from the zero Gram
         for (int it = 0; it < imax; ++it) {
             q.iter = it;
+            q.W = Wslots + (size_t)(it & 1) * wslot;
             if (angles) { dim3 g(1, nb); JSTSP_LAUNCH(h, PK_OTHER, (k_mask_grow<T><<<g, 64, 0, st>>>(q))); }
-            JSTSP_LAUNCH(h, PK_EIG, (k_svt_weights<T><<<nb, 128, sm_j, st>>>(q)));
             {
                 dim3 g(q.nmc, nb);
                 if (fast_xupd) JSTSP_LAUNCH(h, PK_XUPD_T1, (k_xupd_t1_fast<T><<<g, kThreads, sm_fx, st>>>(q)));
                 else JSTSP_LAUNCH(h, PK_XUPD_T1, (k_xupd_t1<T, KB><<<g, kThreads, sm_x, st>>>(q)));
+            }
+            if (it + 1 < imax) {
+                // the Gram matrix of the NEXT SVT input is complete: solve it on the side stream while the
+                // V / S / Xs updates of this iteration run on the main stream
+                AdmmP<T> qe = q;
+                qe.W = Wslots + (size_t)((it + 1) & 1) * wslot;
+                if (overlap_eig) {
+                    JSTSP_CUDA(h, cudaEventRecord(h->ev_fork, st));
+                    JSTSP_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+                    k_svt_weights<T><<<nb, 128, sm_j, h->side>>>(qe); h->launches++;
+                    JSTSP_CUDA(h, cudaEventRecord(h->ev_join, h->side));
+                } else {
+                    JSTSP_LAUNCH(h, PK_EIG, (k_svt_weights<T><<<nb, 128, sm_j, st>>>(qe)));
+                }
             }
             if (fast_v) {
                 JSTSP_LAUNCH(h, PK_RES, (k_vstep_fast<T><<<nb, kThreads, sm_fv, st>>>(q)));
@@ -803,6 +825,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
                 if (fast_xs) JSTSP_LAUNCH(h, PK_XS, (k_xs_fast<T><<<g, kThreads, sm_fs, st>>>(q, bt_ws, ld_Bt)));
                 else JSTSP_LAUNCH(h, PK_XS, (k_xs<T, CB><<<g, kThreads, sm_xs, st>>>(q)));
             }
+            if (it + 1 < imax && overlap_eig) JSTSP_CUDA(h, cudaStreamWaitEvent(st, h->ev_join, 0));
             if (want_conv) {
                 dim3 g(3, nb); JSTSP_LAUNCH(h, PK_OTHER, (k_conv_norms<T><<<g, 128, sm_j, st>>>(q)));
                 JSTSP_LAUNCH(h, PK_OTHER, (k_conv_finish<T><<<nb, 1, 0, st>>>(q)));

@@ -13,6 +13,12 @@
 
 namespace jstsp {
 
+// phase timestamp (developer hook, see jstsp_debug_buffer)
+#define JSTSP_STAMP(p, kid, cta, slot)                                                              \
+    do {                                                                                            \
+        if ((p).dbg && (p).dbg_kernel == (kid) && threadIdx.x == 0) (p).dbg[(size_t)(cta) * 8 + (slot)] = clock64(); \
+    } while (0)
+
 template <typename T> struct FastCfg {
     static constexpr int MC = sizeof(T) == 4 ? 128 : 64;      // X-update column chunk
 };
@@ -38,20 +44,39 @@ template <typename T> __device__ __forceinline__ void st4c(cx<T>* __restrict__ p
     }
 }
 template <typename T> __device__ __forceinline__ void ld4r(const T* __restrict__ p, T (&v)[4]) { load_rows4<T>(p, v); }
+// 2 consecutive complex values (16-byte aligned in fp32, two 16-byte accesses in fp64)
+template <typename T> __device__ __forceinline__ void ld2c(const cx<T>* __restrict__ p, cx<T> (&v)[2]) {
+    if constexpr (sizeof(T) == 4) { float4 a = *reinterpret_cast<const float4*>(p); v[0] = mk<T>(a.x, a.y); v[1] = mk<T>(a.z, a.w); }
+    else { v[0] = p[0]; v[1] = p[1]; }
+}
+template <typename T> __device__ __forceinline__ void st2c(cx<T>* __restrict__ p, const cx<T> (&v)[2]) {
+    if constexpr (sizeof(T) == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0].re, v[0].im, v[1].re, v[1].im);
+    else { p[0] = v[0]; p[1] = v[1]; }
+}
+template <typename T> __device__ __forceinline__ void ld2r(const T* __restrict__ p, T (&v)[2]) {
+    if constexpr (sizeof(T) == 4) { float2 a = *reinterpret_cast<const float2*>(p); v[0] = a.x; v[1] = a.y; }
+    else { double2 a = *reinterpret_cast<const double2*>(p); v[0] = a.x; v[1] = a.y; }
+}
 
-// B^T copy: Bt[m + M*p] = B[p + P*m]   (grid ceil(P/32) x ceil(M/32) x nB)
+// Tiled B^T copy: Bt[(chunk*P + p)*W + (m - chunk*W)] = B[p + P*m], chunk = m / W; columns beyond M are zero.
+// (grid ceil(P/32) x ceil(Mpad/32) x nB, Mpad = ceil(M/W)*W)
 template <typename T>
-__global__ void __launch_bounds__(256) k_transpose_b(const cx<T>* __restrict__ B, long long ld_B, cx<T>* __restrict__ Bt, long long ld_Bt, int P, int M) {
+__global__ void __launch_bounds__(256) k_transpose_b(const cx<T>* __restrict__ B, long long ld_B, cx<T>* __restrict__ Bt, long long ld_Bt, int P, int M, int W) {
     __shared__ cx<T> tile[32][33];
     const cx<T>* src = B + (long long)blockIdx.z * ld_B;
     cx<T>* dst = Bt + (long long)blockIdx.z * ld_Bt;
     const int p0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
     const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
-    for (int i = ty; i < 32; i += 8)
-        if (p0 + tx < P && m0 + i < M) tile[i][tx] = src[(p0 + tx) + (long long)P * (m0 + i)];
+    for (int i = ty; i < 32; i += 8) {
+        cx<T> v = mk<T>(T(0), T(0));
+        if (p0 + tx < P && m0 + i < M) v = src[(p0 + tx) + (long long)P * (m0 + i)];
+        tile[i][tx] = v;
+    }
     __syncthreads();
-    for (int i = ty; i < 32; i += 8)
-        if (m0 + tx < M && p0 + i < P) dst[(m0 + tx) + (long long)M * (p0 + i)] = tile[tx][i];
+    for (int i = ty; i < 32; i += 8) {
+        const int m = m0 + tx, pp = p0 + i;
+        if (pp < P) dst[((long long)(m / W) * P + pp) * W + (m % W)] = tile[tx][i];
+    }
 }
 
 // =======================================================================================
@@ -72,7 +97,8 @@ struct XupdFastSmem {
 template <typename T>
 __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_xupd_t1_fast(AdmmP<T> p) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bars[kStages];
+    __shared__ PipeBars<kXupdStages> pb;
+    uint64_t* bars = pb.full;
     constexpr int MC = FastCfg<T>::MC, ZP = MC + 1;
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int N = p.N, RP = p.RP, NG = p.NG, P = p.P;      // RP == N here
@@ -91,11 +117,10 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_xupd_t1_fa
     T* Cx = Nim + (size_t)RP * MC;                                       // conv: X re/im, V1 re/im planes
     T* Wre = Nim + (size_t)RP * MC * (conv ? 5 : 1);                     // [N][RP]: Wre[k*RP + r] = W[r,k]
     T* Wim = Wre + (size_t)N * RP;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kXupdStages; ++s) mbar_init(&bars[s], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
+    const int cta_id = blockIdx.y * gridDim.x + blockIdx.x;
+    JSTSP_STAMP(p, 0, cta_id, 0);
+    pipe_bars_init(pb, smem, ringb);
+    JSTSP_STAMP(p, 0, cta_id, 1);
     // start streaming B(:, chunk) right away; the element-wise prologue below hides the first latency
     const cx<T>* Bc = p.B + (long long)b * p.ld_B + (long long)c0 * P;
     StreamPipe<T, kXupdStages> pipe;
@@ -111,20 +136,23 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_xupd_t1_fa
     const T* __restrict__ om = p.omega + (long long)b * p.ld_omega + (size_t)c0 * N;
     const cx<T>* Wg = p.W + (size_t)b * N * N;
     for (int t = threadIdx.x; t < N * N; t += kThreads) { cx<T> w = Wg[t]; Wre[t] = w.re; Wim[t] = w.im; }   // (r + N*k) == k*RP + r
-    {   // Z = X - V1/rho, transposed into [k][c] (coalesced global reads, padded pitch -> conflict-free)
-        const int nel = N * ncols;
-        for (int t0 = 0; t0 < N * MC; t0 += 4 * kThreads) {
-            cx<T> x[4], v[4];
+    const int nel = N * ncols;                 // elements of this chunk; global index e = c*N + r (N == RP)
+    {   // Z = X - V1/rho, transposed into [k][c]: coalesced 16-byte global reads, padded pitch -> conflict-free
+        for (int e0 = 0; e0 < N * MC; e0 += 2 * kThreads * 4) {
+            cx<T> x[4][2], v[4][2];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { int t = t0 + u * kThreads + threadIdx.x; if (t < nel) { x[u] = X[t]; v[u] = V1[t]; } }
+            for (int u = 0; u < 4; ++u) { const int e = e0 + 2 * (u * kThreads + threadIdx.x); if (e < nel) { ld2c<T>(X + e, x[u]); ld2c<T>(V1 + e, v[u]); } }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                int t = t0 + u * kThreads + threadIdx.x;
-                if (t < N * MC) {
-                    int r = t % N, c = t / N;
-                    T zr = 0, zi = 0;
-                    if (t < nel) { zr = x[u].re - irho * v[u].re; zi = x[u].im - irho * v[u].im; }
-                    Ztre[r * ZP + c] = zr; Ztim[r * ZP + c] = zi;
+                const int e = e0 + 2 * (u * kThreads + threadIdx.x);
+                if (e < N * MC) {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int r = (e + q) % N, c = (e + q) / N;
+                        T zr = 0, zi = 0;
+                        if (e < nel) { zr = x[u][q].re - irho * v[u][q].re; zi = x[u][q].im - irho * v[u][q].im; }
+                        Ztre[r * ZP + c] = zr; Ztim[r * ZP + c] = zi;
+                    }
                 }
             }
         }
@@ -134,8 +162,8 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_xupd_t1_fa
         }
     }
     __syncthreads();
-    // Y = W Z (8 rows x 1 column per thread), then the element-wise updates       (proposed_algorithm.m:35-43,64)
-    const bool last = (p.iter == p.imax - 1) && p.Yout != nullptr;
+    JSTSP_STAMP(p, 0, cta_id, 2);
+    // Y = W Z, register-blocked (8 rows x 1 column per thread); parked in the N planes        (svt.m via SURVEY A.2)
     for (int item = threadIdx.x; item < NG * MC; item += kThreads) {
         const int c = item % MC, rg = item / MC;
         if (c >= ncols) continue;
@@ -152,36 +180,42 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_xupd_t1_fa
             for (int r = 0; r < kRB; ++r) cmac<T>(yr[r], yi[r], wr[r], wi[r], zr, zi);
         }
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-            const int r0 = rg * kRB + 4 * hf;
-            const size_t gi = (size_t)c * N + r0;
-            cx<T> v1[4], v2[4], cc[4], xs[4], sy[4], xo[4], n1[4]; T omv[4];
-            ld4c<T>(V1 + gi, v1); ld4c<T>(V2 + gi, v2); ld4c<T>(C + gi, cc); ld4c<T>(Xs + gi, xs); ld4c<T>(subY + gi, sy); ld4r<T>(om + gi, omv);
+        for (int r = 0; r < kRB; ++r) { Nre[c * RP + rg * kRB + r] = yr[r]; Nim[c * RP + rg * kRB + r] = yi[r]; }
+    }
+    __syncthreads();
+    // element-wise updates with fully coalesced 16-byte global accesses          (proposed_algorithm.m:38-43,64)
+    const bool last = (p.iter == p.imax - 1) && p.Yout != nullptr;
+    for (int e0 = 0; e0 < nel; e0 += 2 * kThreads * 2) {
+        cx<T> v1[2][2], v2[2][2], cc[2][2], xs[2][2], sy[2][2]; T omv[2][2];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const T y_r = yr[4 * hf + u], y_i = yi[4 * hf + u];
-                const T d = T(1) / (omv[u] + T(2) * rho);                                                    // iK1 (.m:20)
-                const T xr = (v1[u].re + rho * y_r + sy[u].re + v2[u].re + rho * cc[u].re + rho * xs[u].re) * d;   // .m:38-40
-                const T xi = (v1[u].im + rho * y_i + sy[u].im + v2[u].im + rho * cc[u].im + rho * xs[u].im) * d;
-                const T n1r = v1[u].re + rho * (y_r - xr), n1i = v1[u].im + rho * (y_i - xi);                 // .m:64
-                xo[u] = mk<T>(xr, xi); n1[u] = mk<T>(n1r, n1i);
-                const int si = c * RP + r0 + u;
-                Kre[si] = xr - irho * v2[u].re - cc[u].re; Kim[si] = xi - irho * v2[u].im - cc[u].im;         // .m:43
-                Nre[si] = xr - irho * n1r; Nim[si] = xi - irho * n1i;                                         // next SVT input (.m:35)
+        for (int u = 0; u < 2; ++u) {
+            const int e = e0 + 2 * (u * kThreads + threadIdx.x);
+            if (e < nel) { ld2c<T>(V1 + e, v1[u]); ld2c<T>(V2 + e, v2[u]); ld2c<T>(C + e, cc[u]); ld2c<T>(Xs + e, xs[u]); ld2c<T>(subY + e, sy[u]); ld2r<T>(om + e, omv[u]); }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int e = e0 + 2 * (u * kThreads + threadIdx.x);
+            if (e >= nel) continue;
+            cx<T> xo[2], n1[2], yo[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int si = e + q;                                  // == c*RP + r
+                const T y_r = Nre[si], y_i = Nim[si];
+                const T d = T(1) / (omv[u][q] + T(2) * rho);                                                             // iK1 (.m:20)
+                const T xr = (v1[u][q].re + rho * y_r + sy[u][q].re + v2[u][q].re + rho * cc[u][q].re + rho * xs[u][q].re) * d;   // .m:38-40
+                const T xi = (v1[u][q].im + rho * y_i + sy[u][q].im + v2[u][q].im + rho * cc[u][q].im + rho * xs[u][q].im) * d;
+                const T n1r = v1[u][q].re + rho * (y_r - xr), n1i = v1[u][q].im + rho * (y_i - xi);                      // .m:64
+                xo[q] = mk<T>(xr, xi); n1[q] = mk<T>(n1r, n1i); yo[q] = mk<T>(y_r, y_i);
+                Kre[si] = xr - irho * v2[u][q].re - cc[u][q].re; Kim[si] = xi - irho * v2[u][q].im - cc[u][q].im;        // .m:43
+                Nre[si] = xr - irho * n1r; Nim[si] = xi - irho * n1i;                                                    // next SVT input (.m:35)
                 if (conv) { Cx[si] = xr; Cx[RP * MC + si] = xi; Cx[2 * RP * MC + si] = n1r; Cx[3 * RP * MC + si] = n1i; }
             }
-            st4c<T>(X + gi, xo); st4c<T>(V1 + gi, n1);
-            if (last) {
-                cx<T> yo[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) yo[u] = mk<T>(yr[4 * hf + u], yi[4 * hf + u]);
-                cx<T>* yp = p.Yout + (long long)b * p.ld_Y + (size_t)(c0 + c) * N + r0;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) yp[u] = yo[u];
-            }
+            st2c<T>(X + e, xo); st2c<T>(V1 + e, n1);
+            if (last) { cx<T>* yp = p.Yout + (long long)b * p.ld_Y + (size_t)c0 * N + e; yp[0] = yo[0]; yp[1] = yo[1]; }
         }
     }
     __syncthreads();
+    JSTSP_STAMP(p, 0, cta_id, 3);
     // T1 partial = K(:,chunk) B(:,chunk)^H, stored row-major [N][P]                (.m:47)
     cx<T>* T1 = p.T1 + ((size_t)b * p.nmc + chunk) * (size_t)N * P;
     const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
@@ -204,9 +238,12 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_xupd_t1_fa
             }
         }
     }
+    JSTSP_STAMP(p, 0, cta_id, 4);
     // partial Gram of the next SVT input (the ring is idle now and serves as scratch)
     T* scratch = reinterpret_cast<T*>(smem);
     gram_blocked<T>(Nre, Nim, RP, N, ncols, scratch, ringb, p.gram + ((size_t)b * p.nmc + chunk) * 2 * N * N);
+    JSTSP_STAMP(p, 0, cta_id, 5);
+    if (p.dbg && p.dbg_kernel == 0 && threadIdx.x == 0) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); p.dbg[(size_t)cta_id * 8 + 7] = sm; }
     if (conv) {
         size_t cg = (size_t)p.nmc * 2 * N * N;
         double* base = p.cgramA + (size_t)b * 2 * cg + (size_t)chunk * 2 * N * N;
@@ -235,7 +272,8 @@ struct VstepFastSmem {
 template <typename T>
 __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_vstep_fast(AdmmP<T> p) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bars[kStages];
+    __shared__ PipeBars<kStages> pb;
+    uint64_t* bars = pb.full;
     __shared__ double red[kWarps][3];
     __shared__ double s_alpha;
     const int b = blockIdx.x;
@@ -253,11 +291,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_vstep_fast
     T* Qim = Qre + (size_t)G * RG;
     T* Sre = Qim + (size_t)G * RG;                                     // A : [G][RN]
     T* Sim = Sre + (size_t)G * RN;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
+    pipe_bars_init(pb, smem, StreamRing<T>::bytes(W));
     const cx<T>* BBH = p.BBH + (long long)b * p.ld_BBH;
     StreamPipe<T> pipe;
     uint32_t it = 0;
@@ -326,6 +360,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_vstep_fast
             if (o_1 < P) { Lre[o_1 * RG + rg * kRB + r] = rr_[r][1]; Lim[o_1 * RG + rg * kRB + r] = ri_[r][1]; }
         }
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // exchange rows (generic proxy) -> ring refill (async proxy)
     __syncthreads();
     pipe.start(ring, bars, it, BBH, (long long)P, W, P, P);
 #pragma unroll
@@ -430,21 +465,24 @@ template <typename T>
 struct XsFastSmem {
     __host__ __device__ static size_t region0(int N, int NG, bool conv) {
         size_t ring = StreamRing<T>::bytes(cta_width(NG));
-        size_t cv = conv ? 2 * sizeof(T) * (size_t)N * cta_width(NG) : 0;     // V2 planes alias the ring
-        return ring > cv ? ring : cv;
+        size_t xt = sizeof(cx<T>) * (size_t)cta_width(NG) * (N + 2);           // product tile parked for the coalesced epilogue
+        size_t sc = conv ? (size_t)N * N * 2 * sizeof(T) : 0;                  // at least one Gram slice
+        size_t m = ring > xt ? ring : xt;
+        return m > sc ? m : sc;
     }
     static size_t bytes(int N, int NG, int P, bool conv) {
         int pch = round_up_to(P < kPCH ? P : kPCH, stage_cols<T>());
         size_t l = 2 * sizeof(T) * (size_t)N * pch;
-        size_t scratch = conv ? (size_t)N * N * 2 * sizeof(T) : 0;            // at least one Gram slice
-        return region0(N, NG, conv) + (l > scratch ? l : scratch);
+        size_t cv = conv ? 2 * sizeof(T) * (size_t)N * cta_width(NG) : 0;      // V2 planes reuse the (A S) planes
+        return region0(N, NG, conv) + (l > cv ? l : cv);
     }
 };
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_xs_fast(AdmmP<T> p, const cx<T>* __restrict__ Bt, long long ld_Bt) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ __align__(8) uint64_t bars[kStages];
+    __shared__ PipeBars<kStages> pb;
+    uint64_t* bars = pb.full;
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int N = p.N, P = p.P, M = p.M, RP = p.RP, NG = p.NG;      // RP == N
     const int W = cta_width(NG);
@@ -457,12 +495,12 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_xs_fast(Ad
     const int pchmax = P < kPCH ? P : kPCH;
     const int pchp = round_up_to(pchmax, stage_cols<T>());
     T* Lim = Lre + (size_t)RP * pchp;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    const cx<T>* Btc = Bt + (long long)b * ld_Bt + m0;
+    const int cta_id = blockIdx.y * gridDim.x + blockIdx.x;
+    JSTSP_STAMP(p, 2, cta_id, 0);
+    pipe_bars_init(pb, smem, StreamRing<T>::bytes(W));
+    JSTSP_STAMP(p, 2, cta_id, 1);
+    // B^T is stored tiled: [m-chunk][p][W] so that the reduction columns of a stage are contiguous
+    const cx<T>* Btc = Bt + (long long)b * ld_Bt + (long long)chunk * P * W;
     const cx<T>* __restrict__ AS = p.AS + (size_t)b * N * P;
     StreamPipe<T> pipe;
     uint32_t it = 0;
@@ -471,7 +509,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_xs_fast(Ad
     for (int r = 0; r < kRB; ++r) { ar[r][0] = ar[r][1] = ai[r][0] = ai[r][1] = T(0); }
     for (int p0 = 0; p0 < P; p0 += pchmax) {
         const int np = (P - p0) < pchmax ? (P - p0) : pchmax;
-        pipe.start(ring, bars, it, Btc + (long long)p0 * M, (long long)M, W, nvalid, np);
+        pipe.start(ring, bars, it, Btc + (long long)p0 * W, (long long)W, W, W, np);
         // stage (A S)(:, p0:p0+np) planar; zero the padding columns
         for (int t0 = 0; t0 < RP * pchp; t0 += 4 * kThreads) {
             cx<T> v[4];
@@ -481,58 +519,67 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_xs_fast(Ad
             for (int u = 0; u < 4; ++u) { int t = t0 + u * kThreads + threadIdx.x; if (t < RP * pchp) { Lre[t] = v[u].re; Lim[t] = v[u].im; } }
         }
         __syncthreads();
+        JSTSP_STAMP(p, 2, cta_id, 2);
         it = pipe.template run<false>(Lre, Lim, RP, NG, ar, ai);
+        JSTSP_STAMP(p, 2, cta_id, 3);
     }
     const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
     const int rg = warp % NG, og = warp / NG;
-    T* Vre = reinterpret_cast<T*>(smem);
-    T* Vim = Vre + (size_t)RP * W;
-    if (conv) {
-        for (int t = threadIdx.x; t < 2 * RP * W; t += kThreads) Vre[t] = 0;
-        __syncthreads();
-    }
+    // park the product tile in shared memory ([column][N+2] complex, the ring is idle now) so that the
+    // element-wise C / V2 update below runs with fully coalesced 16-byte global accesses
+    const int NPp = N + 2;
+    cx<T>* Xt = reinterpret_cast<cx<T>*>(smem);
+    T* Vre = Lre;                                   // conv: V2 planes reuse the (A S) planes
+    T* Vim = Lre + (size_t)RP * W;
     if (og < kWarps / NG) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int c = og * kOW + out_of<T>(lane, j);
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                cx<T> v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = mk<T>(ar[4 * hf + u][j], ai[4 * hf + u][j]);
+                st4c<T>(Xt + (size_t)c * NPp + rg * kRB + 4 * hf, v);
+            }
+        }
+    }
+    if (conv) for (int t = threadIdx.x + nvalid * RP; t < 2 * RP * W; t += kThreads) if (t < RP * W || t >= RP * W + nvalid * RP) Vre[t] = 0;
+    __syncthreads();
+    {
         const T rho = (T)p.rho[b];
         const T irho = T(1) / rho, kap = rho / (rho + T(1));
         const size_t off = (size_t)b * N * M + (size_t)m0 * N;
         const cx<T>* __restrict__ X = p.X + off; cx<T>* __restrict__ V2 = p.V2 + off; cx<T>* __restrict__ C = p.C + off; cx<T>* __restrict__ Xs = p.Xs + off;
-        cx<T> x[2][2][4], v2[2][2][4];
-        int cs[2];
+        const int nel = N * nvalid;
+        for (int e0 = 0; e0 < nel; e0 += 2 * kThreads * 4) {
+            cx<T> x[4][2], v2[4][2];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            cs[j] = og * kOW + out_of<T>(lane, j);
-            if (cs[j] < nvalid) {
-                const size_t gi = (size_t)cs[j] * N + rg * kRB;
-                ld4c<T>(X + gi, x[j][0]); ld4c<T>(X + gi + 4, x[j][1]); ld4c<T>(V2 + gi, v2[j][0]); ld4c<T>(V2 + gi + 4, v2[j][1]);
-            }
-        }
+            for (int u = 0; u < 4; ++u) { const int e = e0 + 2 * (u * kThreads + threadIdx.x); if (e < nel) { ld2c<T>(X + e, x[u]); ld2c<T>(V2 + e, v2[u]); } }
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            if (cs[j] < nvalid) {
-                const size_t gi = (size_t)cs[j] * N + rg * kRB;
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + 2 * (u * kThreads + threadIdx.x);
+                if (e >= nel) continue;
+                const int c = e / N, r = e % N;
+                cx<T> sv[2], so[2], co[2], vo[2];
+                ld2c<T>(Xt + (size_t)c * NPp + r, sv);
 #pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    cx<T> so[4], co[4], vo[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int r = 4 * hf + u;
-                        const T sr = ar[r][j], si = ai[r][j];
-                        const cx<T> xx = x[j][hf][u], vv2 = v2[j][hf][u];
-                        const T cr = kap * (xx.re - sr - irho * vv2.re), ci = kap * (xx.im - si - irho * vv2.im);     // .m:61
-                        const T nr = vv2.re + rho * (cr - xx.re + sr), ni = vv2.im + rho * (ci - xx.im + si);         // .m:65
-                        so[u] = mk<T>(sr, si); co[u] = mk<T>(cr, ci); vo[u] = mk<T>(nr, ni);
-                        if (conv) { Vre[cs[j] * RP + rg * kRB + r] = nr; Vim[cs[j] * RP + rg * kRB + r] = ni; }
-                    }
-                    st4c<T>(Xs + gi + 4 * hf, so); st4c<T>(C + gi + 4 * hf, co); st4c<T>(V2 + gi + 4 * hf, vo);
+                for (int q = 0; q < 2; ++q) {
+                    const T sr = sv[q].re, si = sv[q].im;
+                    const T cr = kap * (x[u][q].re - sr - irho * v2[u][q].re), ci = kap * (x[u][q].im - si - irho * v2[u][q].im);   // .m:61
+                    const T nr = v2[u][q].re + rho * (cr - x[u][q].re + sr), ni = v2[u][q].im + rho * (ci - x[u][q].im + si);       // .m:65
+                    so[q] = mk<T>(sr, si); co[q] = mk<T>(cr, ci); vo[q] = mk<T>(nr, ni);
+                    if (conv) { Vre[e + q] = nr; Vim[e + q] = ni; }
                 }
+                st2c<T>(Xs + e, so); st2c<T>(C + e, co); st2c<T>(V2 + e, vo);
             }
         }
     }
+    JSTSP_STAMP(p, 2, cta_id, 4);
+    if (p.dbg && p.dbg_kernel == 2 && threadIdx.x == 0) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); p.dbg[(size_t)cta_id * 8 + 7] = sm; }
     if (conv) {
         __syncthreads();
-        const size_t lbytes = 2 * sizeof(T) * (size_t)RP * pchp;
-        const size_t sb = lbytes > (size_t)N * N * 2 * sizeof(T) ? lbytes : (size_t)N * N * 2 * sizeof(T);
-        gram_blocked<T>(Vre, Vim, RP, N, nvalid, Lre, sb, p.cgramB + ((size_t)b * p.nxc + chunk) * 2 * N * N);
+        gram_blocked<T>(Vre, Vim, RP, N, nvalid, reinterpret_cast<T*>(smem), r0b, p.cgramB + ((size_t)b * p.nxc + chunk) * 2 * N * N);
     }
 }
 

@@ -88,3 +88,11 @@ extern "C" int jstsp_profile_read(jstsp_handle* h, int slot, double* total_ms, l
     if (name) *name = kProfNames[slot];
     return JSTSP_OK;
 }
+
+// Developer hook (not part of the drop-in surface): device buffer that receives in-kernel
+// clock64() phase timestamps, 8 slots per CTA, for tools/phase_probe.py.  NULL disables.
+extern "C" int jstsp_debug_buffer(jstsp_handle* h, void* device_buffer) {
+    if (!h) return JSTSP_E_ARG;
+    h->dbg = static_cast<long long*>(device_buffer);
+    return JSTSP_OK;
+}

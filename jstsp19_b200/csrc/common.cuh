@@ -76,6 +76,7 @@ struct Handle {
     void* ws = nullptr;
     size_t ws_bytes = 0;
     int* d_flag = nullptr;              // device-side non-finite counter
+    long long* dbg = nullptr;           // optional device buffer for in-kernel phase timestamps (tools/phase_probe.py)
 };
 
 }  // namespace jstsp

@@ -51,6 +51,68 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
                  : "memory");
 }
 
+// ---- packed fp32x2 FMA (Blackwell FFMA2): two IEEE fp32 FMAs per issue slot ----------------------
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void ffma2(uint64_t& d, uint64_t a, uint64_t b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b)); }
+
+// Register tile of one thread: 8 rows x 2 outputs, complex.  fp32 keeps ROW PAIRS packed in 64-bit
+// registers so that one complex MAC of two rows is 4 FFMA2 (the 8x2 tile update of one reduction
+// column is 32 FFMA2 instead of 64 FFMA); fp64 uses plain DFMA.  Both round exactly like scalar FMAs.
+template <typename T> struct AccTile;
+template <> struct AccTile<float> {
+    uint64_t R[4][2], I[4][2];
+    __device__ __forceinline__ void load(const float (&ar)[kRB][2], const float (&ai)[kRB][2]) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) { R[q][j] = pack2(ar[2 * q][j], ar[2 * q + 1][j]); I[q][j] = pack2(ai[2 * q][j], ai[2 * q + 1][j]); }
+    }
+    __device__ __forceinline__ void store(float (&ar)[kRB][2], float (&ai)[kRB][2]) const {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) { unpack2(R[q][j], ar[2 * q][j], ar[2 * q + 1][j]); unpack2(I[q][j], ai[2 * q][j], ai[2 * q + 1][j]); }
+    }
+    // tile += L(:, col) * [b0 b1]   ;  lre/lim point at this thread's 8 rows of the column
+    __device__ __forceinline__ void mac(const float* __restrict__ lre, const float* __restrict__ lim, cx<float> b0, cx<float> b1) {
+        const float4 r0 = *reinterpret_cast<const float4*>(lre), r1 = *reinterpret_cast<const float4*>(lre + 4);
+        const float4 i0 = *reinterpret_cast<const float4*>(lim), i1 = *reinterpret_cast<const float4*>(lim + 4);
+        const uint64_t LR[4] = {pack2(r0.x, r0.y), pack2(r0.z, r0.w), pack2(r1.x, r1.y), pack2(r1.z, r1.w)};
+        const uint64_t LI[4] = {pack2(i0.x, i0.y), pack2(i0.z, i0.w), pack2(i1.x, i1.y), pack2(i1.z, i1.w)};
+        const uint64_t B0R = pack2(b0.re, b0.re), B0I = pack2(b0.im, b0.im), B0N = pack2(-b0.im, -b0.im);
+        const uint64_t B1R = pack2(b1.re, b1.re), B1I = pack2(b1.im, b1.im), B1N = pack2(-b1.im, -b1.im);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            ffma2(R[q][0], LR[q], B0R); ffma2(I[q][0], LR[q], B0I);
+            ffma2(R[q][1], LR[q], B1R); ffma2(I[q][1], LR[q], B1I);
+            ffma2(R[q][0], LI[q], B0N); ffma2(I[q][0], LI[q], B0R);
+            ffma2(R[q][1], LI[q], B1N); ffma2(I[q][1], LI[q], B1R);
+        }
+    }
+};
+template <> struct AccTile<double> {
+    double r[kRB][2], i[kRB][2];
+    __device__ __forceinline__ void load(const double (&ar)[kRB][2], const double (&ai)[kRB][2]) {
+#pragma unroll
+        for (int q = 0; q < kRB; ++q) { r[q][0] = ar[q][0]; r[q][1] = ar[q][1]; i[q][0] = ai[q][0]; i[q][1] = ai[q][1]; }
+    }
+    __device__ __forceinline__ void store(double (&ar)[kRB][2], double (&ai)[kRB][2]) const {
+#pragma unroll
+        for (int q = 0; q < kRB; ++q) { ar[q][0] = r[q][0]; ar[q][1] = r[q][1]; ai[q][0] = i[q][0]; ai[q][1] = i[q][1]; }
+    }
+    __device__ __forceinline__ void mac(const double* __restrict__ lre, const double* __restrict__ lim, cx<double> b0, cx<double> b1) {
+        double lr[kRB], li[kRB];
+        load_rows8<double>(lre, 0, 0, 0, lr);
+        load_rows8<double>(lim, 0, 0, 0, li);
+#pragma unroll
+        for (int q = 0; q < kRB; ++q) {
+            cmac<double>(r[q][0], i[q][0], lr[q], li[q], b0.re, b0.im);
+            cmac<double>(r[q][1], i[q][1], lr[q], li[q], b1.re, b1.im);
+        }
+    }
+};
+
 template <typename T>
 struct StreamRing {
     __host__ __device__ static size_t bytes(int width, int stages = kStages) { return sizeof(cx<T>) * (size_t)stages * stage_cols<T>() * width; }
@@ -81,31 +143,62 @@ template <typename T> __device__ __forceinline__ void store_pair(cx<T>* __restri
 
 // One streaming contraction.  All threads of the CTA must call start() and run().
 //   ring   : shared memory, StreamRing<T>::bytes(width, STAGES), 16-byte aligned
-//   bars   : STAGES mbarriers (initialised once per kernel with mbar_init(.,1) + fence + sync)
+//   bars   : STAGES mbarriers followed by STAGES int arrival counters - use PipeBars<STAGES> and
+//            pipe_bars_init() once per kernel
 //   it0    : running stage counter of this CTA (carried across calls so barrier phases stay consistent)
 //   Big    : global pointer at (first output of this CTA's tile, column 0); ld in elements
 //   width  : outputs covered by this CTA = (warps / NG) * 64 ; nvalid <= width actually present
 //   L planes must hold round_up(ncols, stage_cols) columns, the padding columns zero.
+template <int STAGES>
+struct __align__(8) PipeBars {
+    uint64_t full[STAGES];
+    int cnt[STAGES];
+};
+// Initialise the barriers and zero the ring (so that never-written ring bytes are finite), then make
+// the generic-proxy writes visible to the async proxy before the first bulk copy lands.
+template <int STAGES>
+__device__ __forceinline__ void pipe_bars_init(PipeBars<STAGES>& pb, void* ring, size_t ring_bytes) {
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&pb.full[s], 1); pb.cnt[s] = 0; }
+        mbar_fence_init();
+    }
+    float4* r4 = reinterpret_cast<float4*>(ring);
+    for (size_t i = threadIdx.x; i < ring_bytes / 16; i += blockDim.x) r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+}
+
 template <typename T, int STAGES = kStages>
 struct StreamPipe {
     static constexpr int kSC = stage_cols<T>();
-    cx<T>* ring; uint64_t* bars; const cx<T>* big; long long ld; int width, nvalid, ncols, nst; uint32_t it0;
+    cx<T>* ring; uint64_t* bars; int* cnt; const cx<T>* big; long long ld; int width, nvalid, ncols, nst; uint32_t it0;
+    bool contig;    // the reduction columns are back to back in global memory (ld == nvalid): one bulk copy per stage
 
     __device__ __forceinline__ void issue(int t) {   // called by ONE thread
         const uint32_t slot = (it0 + t) % STAGES;
         const int c0 = t * kSC;
         const uint32_t seg = (uint32_t)(nvalid * sizeof(cx<T>));
-        mbar_expect_tx(&bars[slot], seg * kSC);
         cx<T>* dst = ring + (size_t)slot * kSC * width;
+        if (contig) {
+            // width == nvalid == ld: the whole stage is one contiguous block; a short tail stage leaves
+            // stale (finite: the ring is zero-initialised) values against zero L columns
+            const int nc = (ncols - c0) < kSC ? (ncols - c0) : kSC;
+            mbar_expect_tx(&bars[slot], seg * nc);
+            tma_bulk_g2s(dst, big + (long long)c0 * ld, seg * nc, &bars[slot]);
+        } else {
+            mbar_expect_tx(&bars[slot], seg * kSC);
 #pragma unroll
-        for (int c = 0; c < kSC; ++c) {
-            const int col = (c0 + c) < ncols ? (c0 + c) : (ncols - 1);    // tail: any valid column (its L column is zero)
-            tma_bulk_g2s(dst + (size_t)c * width, big + (long long)col * ld, seg, &bars[slot]);
+            for (int c = 0; c < kSC; ++c) {
+                const int col = (c0 + c) < ncols ? (c0 + c) : (ncols - 1);    // tail: any valid column (its L column is zero)
+                tma_bulk_g2s(dst + (size_t)c * width, big + (long long)col * ld, seg, &bars[slot]);
+            }
         }
     }
     __device__ __forceinline__ void start(cx<T>* ring_, uint64_t* bars_, uint32_t it0_, const cx<T>* big_, long long ld_, int width_, int nvalid_,
                                           int ncols_) {
-        ring = ring_; bars = bars_; it0 = it0_; big = big_; ld = ld_; width = width_; nvalid = nvalid_; ncols = ncols_;
+        ring = ring_; bars = bars_; cnt = reinterpret_cast<int*>(bars_ + STAGES); it0 = it0_; big = big_; ld = ld_; nvalid = nvalid_; ncols = ncols_;
+        contig = (ld_ == (long long)nvalid_);
+        width = contig ? nvalid_ : width_;          // ring row pitch
         nst = (ncols + kSC - 1) / kSC;
         if (threadIdx.x == 0) {
             const int pre = nst < STAGES ? nst : STAGES;
@@ -118,6 +211,8 @@ struct StreamPipe {
         const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
         const int rg = warp % NG, og = warp / NG;
         const bool active = og < kWarps / NG;
+        AccTile<T> acc;
+        acc.load(ar, ai);
         for (int t = 0; t < nst; ++t) {
             const uint32_t g = it0 + t, slot = g % STAGES;
             mbar_wait(&bars[slot], (g / STAGES) & 1u);
@@ -129,20 +224,23 @@ struct StreamPipe {
                 for (int c = 0; c < kSC; ++c) {
                     cx<T> b0, b1;
                     load_pair<T>(st + (size_t)c * width, lane, b0, b1);
-                    T lr[kRB], li[kRB];
-                    load_rows8<T>(lre, RP, c, 0, lr);
-                    load_rows8<T>(lim, RP, c, 0, li);
-                    const T b0i = CONJ ? -b0.im : b0.im, b1i = CONJ ? -b1.im : b1.im;
-#pragma unroll
-                    for (int r = 0; r < kRB; ++r) {
-                        cmac<T>(ar[r][0], ai[r][0], lr[r], li[r], b0.re, b0i);
-                        cmac<T>(ar[r][1], ai[r][1], lr[r], li[r], b1.re, b1i);
-                    }
+                    if (CONJ) { b0.im = -b0.im; b1.im = -b1.im; }
+                    acc.mac(lre + (size_t)c * RP, lim + (size_t)c * RP, b0, b1);
                 }
             }
-            __syncthreads();                       // every warp is done with this ring slot
-            if (threadIdx.x == 0 && t + STAGES < nst) issue(t + STAGES);
+            // release the slot: the LAST warp to finish it refills it (no CTA-wide barrier per stage,
+            // warps may run up to STAGES-1 stages apart)
+            __syncwarp();
+            if (lane == 0) {
+                const int old = atomicAdd(&cnt[slot], 1);
+                if (old == kWarps - 1) {
+                    cnt[slot] = 0;
+                    if (t + STAGES < nst) issue(t + STAGES);
+                }
+            }
         }
+        acc.store(ar, ai);
+        __syncthreads();                           // ring and L planes may be reused by the caller
         return it0 + nst;
     }
 };
@@ -154,19 +252,15 @@ __device__ __forceinline__ void smem_contract(const T* __restrict__ Lre, const T
                                               int pitch, int og, int nk, T (&ar)[kRB][2], T (&ai)[kRB][2]) {
     const int lane = threadIdx.x % kWarp;
     const cx<T>* rp = R2 + og * kOW;
+    AccTile<T> acc;
+    acc.load(ar, ai);
 #pragma unroll 4
     for (int k = 0; k < nk; ++k) {
         cx<T> b0, b1;
         load_pair<T>(rp + (size_t)k * pitch, lane, b0, b1);
-        T lr[kRB], li[kRB];
-        load_rows8<T>(Lre, RP, k, rg, lr);
-        load_rows8<T>(Lim, RP, k, rg, li);
-#pragma unroll
-        for (int r = 0; r < kRB; ++r) {
-            cmac<T>(ar[r][0], ai[r][0], lr[r], li[r], b0.re, b0.im);
-            cmac<T>(ar[r][1], ai[r][1], lr[r], li[r], b1.re, b1.im);
-        }
+        acc.mac(Lre + (size_t)k * RP + rg * kRB, Lim + (size_t)k * RP + rg * kRB, b0, b1);
     }
+    acc.store(ar, ai);
 }
 
 template <typename T> __device__ __forceinline__ void load_rows4(const T* __restrict__ p, T (&v)[4]) {

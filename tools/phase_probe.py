@@ -1,0 +1,43 @@
+"""In-kernel phase timing of the ADMM fast-path kernels (developer tool, needs a B200).
+usage: JSTSP_DBG_KERNEL={0|2} python tools/phase_probe.py   (0 = k_xupd_t1_fast, 2 = k_xs_fast)"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from jstsp19_b200 import _lib, synth  # noqa: E402
+from jstsp19_b200.engine import AdmmEngine  # noqa: E402
+
+nb = 592
+s = synth.METRIC
+dev = torch.device("cuda", 0)
+data = synth.make_batch(s, nb, torch.zeros(nb, dtype=torch.float64), seed=1, device=dev)
+eng = AdmmEngine(0, "f32")
+kid = int(os.environ.get("JSTSP_DBG_KERNEL", "0"))
+ncta = nb * 8
+buf = torch.zeros(ncta * 8, dtype=torch.int64, device=dev)
+for it in range(2):
+    eng.proposed_algorithm(data["subY"], data["Omega"], data["A"], data["B"], 3, data["tau_Y"], data["tau_Z"], data["rho"])
+torch.cuda.synchronize()
+_lib.lib.jstsp_debug_buffer(eng.h.ptr, C.c_void_p(buf.data_ptr()))
+eng.proposed_algorithm(data["subY"], data["Omega"], data["A"], data["B"], 3, data["tau_Y"], data["tau_Z"], data["rho"])
+torch.cuda.synchronize()
+_lib.lib.jstsp_debug_buffer(eng.h.ptr, None)
+t = buf.cpu().numpy().reshape(ncta, 8)
+t = t[t[:, 0] > 0]
+names = {0: ["init+ring zero", "Z staging", "W Z + element-wise", "T1 main loop", "gram"], 2: ["init+ring zero", "AS staging", "main loop", "epilogue"]}[kid]
+d = np.diff(t[:, : len(names) + 1], axis=1).astype(np.float64)
+print(f"kernel {kid}: {len(t)} CTAs, clock cycles per phase (median / mean / p90)")
+for i, n in enumerate(names):
+    print(f"  {n:22s} {np.median(d[:, i]):10.0f} {d[:, i].mean():10.0f} {np.percentile(d[:, i], 90):10.0f}")
+tot = (t[:, len(names)] - t[:, 0]).astype(np.float64)
+print(f"  {'total':22s} {np.median(tot):10.0f} {tot.mean():10.0f} {np.percentile(tot, 90):10.0f}")
+sm = t[:, 7]
+for sid in (0, 1):
+    sel = t[sm == sid]
+    order = np.argsort(sel[:, 0])
+    base = sel[order[0], 0]
+    print(f"SM {sid}: CTA (start, end) cycles:", [(int(r[0] - base), int(r[len(names)] - base)) for r in sel[order][:8]])
