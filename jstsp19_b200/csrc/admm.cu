@@ -48,6 +48,7 @@ struct AdmmP {
     double* convd;                      // [b][imax][3] diagnostics in double (or null)
     double* cgramA;                     // [b][2][nmc][2*N*N] partial Grams of V1 and X   (conv only)
     double* cgramB; int nxc;            // [b][nxc][2*N*N]    partial Gram of V2           (conv only)
+    double* Uprev;                      // [b][2*N*N] eigenvectors of the previous Gram matrix (Jacobi warm start)
     long long* dbg; int dbg_kernel;     // phase timestamps of kernel #dbg_kernel (0 xupd, 1 vstep, 2 xs), or null
 };
 
@@ -137,10 +138,24 @@ __global__ void __launch_bounds__(128) k_svt_weights(AdmmP<T> p) {
         sm.Are[t] = re; sm.Aim[t] = im;
     }
     __syncthreads();
-    jacobi_hermitian_block(sm, n);
+    long long t0 = 0;
+    if (p.dbg && p.dbg_kernel == 5 && threadIdx.x == 0) { t0 = clock64(); p.dbg[(size_t)b * 8 + 0] = t0; }
+    // Warm start from the previous iteration's eigenvectors (the ADMM iterates move slowly, so Q^H G Q is
+    // nearly diagonal and one or two sweeps suffice); every 16th iteration restarts cold to shed drift.
+    double* Up = p.Uprev + (size_t)b * 2 * nn;
+    const bool warm = p.iter > 0 && (p.iter % 16) != 0;
+    if (warm) {
+        for (int t = threadIdx.x; t < nn; t += blockDim.x) { sm.Ure[t] = Up[t]; sm.Uim[t] = Up[nn + t]; }
+        __syncthreads();
+        jacobi_similarity_block(sm, n, reinterpret_cast<double*>(smem + JacobiSmem::bytes(n)));
+    }
+    const int sweeps = jacobi_hermitian_block(sm, n, 24, warm);
+    for (int t = threadIdx.x; t < nn; t += blockDim.x) { Up[t] = sm.Ure[t]; Up[nn + t] = sm.Uim[t]; }
+    if (p.dbg && p.dbg_kernel == 5 && threadIdx.x == 0) { p.dbg[(size_t)b * 8 + 1] = clock64(); p.dbg[(size_t)b * 8 + 2] = sweeps; }
     const double tau = p.tauY[b] / p.rho[b];
     cx<T>* W = p.W + (size_t)b * nn;
     svt_weights_block(sm, n, tau, [&](int i, int j, double re, double im) { W[i + n * j] = mk<T>((T)re, (T)im); });
+    if (p.dbg && p.dbg_kernel == 5 && threadIdx.x == 0) p.dbg[(size_t)b * 8 + 3] = clock64();
 }
 
 // largest eigenvalue of up to 3 partial-summed Gram matrices (convergence diagnostics,
@@ -663,6 +678,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
     auto layout = [&](Arena& a, int nb, AdmmP<T>& q) {
         q.X = a.take<cx<T>>(NM * nb); q.V1 = a.take<cx<T>>(NM * nb); q.V2 = a.take<cx<T>>(NM * nb);
         q.C = a.take<cx<T>>(NM * nb); q.Xs = a.take<cx<T>>(NM * nb);
+        q.Uprev = a.take<double>((size_t)2 * N * N * nb);
         q.W = a.take<cx<T>>((size_t)N * N * nb * 2);           // double-buffered: the eigen-solve of iteration i+1 overlaps iteration i
         q.gram = a.take<double>((size_t)nb * q.nmc * 2 * N * N);
         q.T1 = a.take<cx<T>>((size_t)nb * q.nmc * N * P);
@@ -714,7 +730,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
     size_t sm_q = ExpandSmem<T, CB>::bytes(p.GNG, p.GP8);
     { size_t epi = sizeof(cx<T>) * ((size_t)G * ExpandSmem<T, CB>::chunk_cols(p.GNG) + (size_t)G * G); if (epi > sm_q) sm_q = epi; }
     const size_t sm_v = sizeof(cx<T>) * ((size_t)G * kPV + (size_t)N * G);
-    const size_t sm_j = JacobiSmem::bytes(N);
+    const size_t sm_j = JacobiSmem::bytes(N) + 2 * sizeof(double) * (size_t)N * N + 16;
     int rc;
     if ((rc = set_smem(h, k_xupd_t1<T, KB>, sm_x))) return rc;
     if ((rc = set_smem(h, k_xs<T, CB>, sm_xs))) return rc;
@@ -789,6 +805,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
         }
         cx<T>* const Wslots = q.W;
         const size_t wslot = (size_t)N * N * nb;
+        q.iter = 0;
         if (imax > 0) JSTSP_LAUNCH(h, PK_EIG, (k_svt_weights<T><<<nb, 128, sm_j, st>>>(q)));      // W(0) from the zero Gram
         for (int it = 0; it < imax; ++it) {
             q.iter = it;
@@ -803,6 +820,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
                 // the Gram matrix of the NEXT SVT input is complete: solve it on the side stream while the
                 // V / S / Xs updates of this iteration run on the main stream
                 AdmmP<T> qe = q;
+                qe.iter = it + 1;
                 qe.W = Wslots + (size_t)((it + 1) & 1) * wslot;
                 if (overlap_eig) {
                     JSTSP_CUDA(h, cudaEventRecord(h->ev_fork, st));

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_xupd_t1_fa
     T* Wim = Wre + (size_t)N * RP;
     const int cta_id = blockIdx.y * gridDim.x + blockIdx.x;
     JSTSP_STAMP(p, 0, cta_id, 0);
-    pipe_bars_init(pb, smem, ringb);
+    pipe_bars_init(pb, smem, ringb, (ncols % stage_cols<T>()) != 0);
     JSTSP_STAMP(p, 0, cta_id, 1);
     // start streaming B(:, chunk) right away; the element-wise prologue below hides the first latency
     const cx<T>* Bc = p.B + (long long)b * p.ld_B + (long long)c0 * P;
@@ -135,6 +135,14 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_xupd_t1_fa
     const cx<T>* __restrict__ subY = p.subY + (long long)b * p.ld_subY + (size_t)c0 * N;
     const T* __restrict__ om = p.omega + (long long)b * p.ld_omega + (size_t)c0 * N;
     const cx<T>* Wg = p.W + (size_t)b * N * N;
+    {   // warm L2 with the tiles the element-wise phase reads ~20k cycles from now
+        const size_t tile_bytes = sizeof(cx<T>) * (size_t)N * ncols;
+        for (size_t o = (size_t)threadIdx.x * 128; o < tile_bytes; o += (size_t)kThreads * 128) {
+            prefetch_l2(reinterpret_cast<const char*>(V2) + o); prefetch_l2(reinterpret_cast<const char*>(C) + o);
+            prefetch_l2(reinterpret_cast<const char*>(Xs) + o); prefetch_l2(reinterpret_cast<const char*>(subY) + o);
+            if (o < tile_bytes / 2) prefetch_l2(reinterpret_cast<const char*>(om) + o);
+        }
+    }
     for (int t = threadIdx.x; t < N * N; t += kThreads) { cx<T> w = Wg[t]; Wre[t] = w.re; Wim[t] = w.im; }   // (r + N*k) == k*RP + r
     const int nel = N * ncols;                 // elements of this chunk; global index e = c*N + r (N == RP)
     {   // Z = X - V1/rho, transposed into [k][c]: coalesced 16-byte global reads, padded pitch -> conflict-free
@@ -291,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_vstep_fast
     T* Qim = Qre + (size_t)G * RG;
     T* Sre = Qim + (size_t)G * RG;                                     // A : [G][RN]
     T* Sim = Sre + (size_t)G * RN;
-    pipe_bars_init(pb, smem, StreamRing<T>::bytes(W));
+    pipe_bars_init(pb, smem, StreamRing<T>::bytes(W), (P % stage_cols<T>()) != 0);
     const cx<T>* BBH = p.BBH + (long long)b * p.ld_BBH;
     StreamPipe<T> pipe;
     uint32_t it = 0;
@@ -497,7 +505,15 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_xs_fast(Ad
     T* Lim = Lre + (size_t)RP * pchp;
     const int cta_id = blockIdx.y * gridDim.x + blockIdx.x;
     JSTSP_STAMP(p, 2, cta_id, 0);
-    pipe_bars_init(pb, smem, StreamRing<T>::bytes(W));
+    pipe_bars_init(pb, smem, StreamRing<T>::bytes(W), (P % stage_cols<T>()) != 0 || (pchmax % stage_cols<T>()) != 0);
+    {   // warm L2 with the X / V2 tiles the epilogue will read (written by earlier kernels of this iteration)
+        const size_t off = (size_t)b * N * M + (size_t)m0 * N;
+        const size_t tile_bytes = sizeof(cx<T>) * (size_t)N * nvalid;
+        for (size_t o = (size_t)threadIdx.x * 128; o < tile_bytes; o += (size_t)kThreads * 128) {
+            prefetch_l2(reinterpret_cast<const char*>(p.X + off) + o);
+            prefetch_l2(reinterpret_cast<const char*>(p.V2 + off) + o);
+        }
+    }
     JSTSP_STAMP(p, 2, cta_id, 1);
     // B^T is stored tiled: [m-chunk][p][W] so that the reduction columns of a stage are contiguous
     const cx<T>* Btc = Bt + (long long)b * ld_Bt + (long long)chunk * P * W;
@@ -511,12 +527,19 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_xs_fast(Ad
         const int np = (P - p0) < pchmax ? (P - p0) : pchmax;
         pipe.start(ring, bars, it, Btc + (long long)p0 * W, (long long)W, W, W, np);
         // stage (A S)(:, p0:p0+np) planar; zero the padding columns
-        for (int t0 = 0; t0 < RP * pchp; t0 += 4 * kThreads) {
-            cx<T> v[4];
+        for (int t0 = 0; t0 < RP * pchp; t0 += 2 * 8 * kThreads) {
+            cx<T> v[8][2];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { int t = t0 + u * kThreads + threadIdx.x; v[u] = mk<T>(T(0), T(0)); if (t < N * np) v[u] = AS[(size_t)N * p0 + t]; }
+            for (int u = 0; u < 8; ++u) {
+                const int t = t0 + 2 * (u * kThreads + threadIdx.x);
+                v[u][0] = mk<T>(T(0), T(0)); v[u][1] = v[u][0];
+                if (t < N * np) ld2c<T>(AS + (size_t)N * p0 + t, v[u]);
+            }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { int t = t0 + u * kThreads + threadIdx.x; if (t < RP * pchp) { Lre[t] = v[u].re; Lim[t] = v[u].im; } }
+            for (int u = 0; u < 8; ++u) {
+                const int t = t0 + 2 * (u * kThreads + threadIdx.x);
+                if (t < RP * pchp) { Lre[t] = v[u][0].re; Lim[t] = v[u][0].im; Lre[t + 1] = v[u][1].re; Lim[t + 1] = v[u][1].im; }
+            }
         }
         __syncthreads();
         JSTSP_STAMP(p, 2, cta_id, 2);
@@ -552,12 +575,13 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_xs_fast(Ad
         const size_t off = (size_t)b * N * M + (size_t)m0 * N;
         const cx<T>* __restrict__ X = p.X + off; cx<T>* __restrict__ V2 = p.V2 + off; cx<T>* __restrict__ C = p.C + off; cx<T>* __restrict__ Xs = p.Xs + off;
         const int nel = N * nvalid;
-        for (int e0 = 0; e0 < nel; e0 += 2 * kThreads * 4) {
-            cx<T> x[4][2], v2[4][2];
+        constexpr int EB = sizeof(T) == 4 ? 8 : 4;      // element pairs in flight per thread
+        for (int e0 = 0; e0 < nel; e0 += 2 * kThreads * EB) {
+            cx<T> x[EB][2], v2[EB][2];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { const int e = e0 + 2 * (u * kThreads + threadIdx.x); if (e < nel) { ld2c<T>(X + e, x[u]); ld2c<T>(V2 + e, v2[u]); } }
+            for (int u = 0; u < EB; ++u) { const int e = e0 + 2 * (u * kThreads + threadIdx.x); if (e < nel) { ld2c<T>(X + e, x[u]); ld2c<T>(V2 + e, v2[u]); } }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < EB; ++u) {
                 const int e = e0 + 2 * (u * kThreads + threadIdx.x);
                 if (e >= nel) continue;
                 const int c = e / N, r = e % N;

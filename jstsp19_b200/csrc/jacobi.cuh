@@ -27,6 +27,27 @@ struct JacobiSmem {
     }
 };
 
+// Fast fp64 reciprocal square root / reciprocal: fp32 hardware seed + Newton steps in fp64 (full
+// double accuracy after two/three steps).  The argument is range-reduced through its exponent so
+// the fp32 seed never over/underflows.  x > 0 and finite.
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    const int ex = ((__double2hiint(x) >> 20) & 0x7ff) - 1023;
+    const int hshift = ex >> 1;
+    const double xs = scalbn(x, -2 * hshift);                 // in [1, 4)
+    double r = (double)rsqrtf((float)xs);
+    r = r * (1.5 - 0.5 * xs * r * r);
+    r = r * (1.5 - 0.5 * xs * r * r);
+    r = r * (1.5 - 0.5 * xs * r * r);
+    return scalbn(r, -hshift);
+}
+__device__ __forceinline__ double fast_rcp_ge1(double d) {     // d >= 1 ; huge d (> fp32 range) returns 0
+    double r = (double)__frcp_rn((float)d);
+    r = r * (2.0 - d * r);
+    r = r * (2.0 - d * r);
+    r = r * (2.0 - d * r);
+    return r;
+}
+
 // Round-robin ("circle method") pairing: npad players, step s in [0, npad-1).
 __device__ __forceinline__ void rr_pair(int npad, int s, int k, int& p, int& q) {
     int a, b;
@@ -37,18 +58,27 @@ __device__ __forceinline__ void rr_pair(int npad, int s, int k, int& p, int& q) 
 
 // In: Hermitian A (sm.Are/Aim).  Out: eigenvalues on the diagonal of A, eigenvectors in U.
 // All threads of the block must call; uses __syncthreads().
-__device__ inline void jacobi_hermitian_block(JacobiSmem& sm, int n, int max_sweeps = 24) {
+// keep_U: U already holds a unitary matrix Q and A holds Q^H G Q (warm start); the rotations are
+// accumulated onto Q so that U ends as the eigenvector matrix of G.
+__device__ inline int jacobi_hermitian_block(JacobiSmem& sm, int n, int max_sweeps = 24, bool keep_U = false) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int npad = n + (n & 1), h = npad / 2;
-    for (int i = tid; i < n * n; i += nt) { sm.Ure[i] = (i % n == i / n) ? 1.0 : 0.0; sm.Uim[i] = 0.0; }
-    if (tid == 0) {
+    if (!keep_U) for (int i = tid; i < n * n; i += nt) { sm.Ure[i] = (i % n == i / n) ? 1.0 : 0.0; sm.Uim[i] = 0.0; }
+    {   // Frobenius norm^2 (block reduction; deterministic order)
         double f = 0.0;
-        for (int i = 0; i < n * n; ++i) f += sm.Are[i] * sm.Are[i] + sm.Aim[i] * sm.Aim[i];
-        sm.red[0] = f; sm.red[2] = 0.0;
+        for (int i = tid; i < n * n; i += nt) f += sm.Are[i] * sm.Are[i] + sm.Aim[i] * sm.Aim[i];
+        for (int o = 16; o > 0; o >>= 1) f += __shfl_down_sync(0xffffffffu, f, o);
+        if (tid == 0) { sm.red[0] = 0.0; sm.red[2] = 0.0; }
+        __syncthreads();
+        // warps add their partials one after the other (fixed order)
+        for (int w = 0; w < (nt + 31) / 32; ++w) {
+            if (tid == w * 32) sm.red[0] += f;
+            __syncthreads();
+        }
     }
-    __syncthreads();
-    if (n < 2 || sm.red[0] == 0.0) return;
-    for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    if (n < 2 || sm.red[0] == 0.0) return 0;
+    int sweep = 0;
+    for (; sweep < max_sweeps; ++sweep) {
         if (tid < h) sm.offacc[tid] = 0.0;
         for (int step = 0; step < npad - 1; ++step) {
             // phase 0: rotation parameters, one thread per pair
@@ -60,13 +90,15 @@ __device__ inline void jacobi_hermitian_block(JacobiSmem& sm, int n, int max_swe
                     double ar = sm.Are[p + n * q], ai = sm.Aim[p + n * q];
                     double app = sm.Are[p + n * p], aqq = sm.Are[q + n * q];
                     double m2 = ar * ar + ai * ai;
-                    if (m2 > 0.0 && m2 > 1e-36 * fabs(app * aqq)) {
+                    if (m2 > 1e-290 && m2 > 1e-36 * fabs(app * aqq)) {
                         sm.offacc[tid] += m2;
-                        double mag = sqrt(m2);
-                        er = ar / mag; ei = ai / mag;
-                        double tau = (aqq - app) / (2.0 * mag);
-                        double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                        c = 1.0 / sqrt(1.0 + t * t);
+                        const double rm = fast_rsqrt(m2);              // 1/|a_pq|
+                        er = ar * rm; ei = ai * rm;
+                        const double tau = (aqq - app) * 0.5 * rm;
+                        const double s1 = 1.0 + tau * tau;
+                        const double w = s1 < 1e300 ? s1 * fast_rsqrt(s1) : fabs(tau);     // sqrt(1 + tau^2)
+                        const double t = (tau >= 0.0 ? 1.0 : -1.0) * fast_rcp_ge1(fabs(tau) + w);
+                        c = fast_rsqrt(1.0 + t * t);
                         s = t * c;
                     }
                 }
@@ -131,11 +163,48 @@ __device__ inline void jacobi_hermitian_block(JacobiSmem& sm, int n, int max_swe
         if (tid == 0) {
             double off = 0.0;
             for (int k = 0; k < h; ++k) off += sm.offacc[k];
-            sm.red[2] = (off <= 1e-31 * sm.red[0]) ? 1.0 : 0.0;
+            // `off` is the off-diagonal mass seen BEFORE this sweep's rotations; Jacobi converges
+            // quadratically, so a sweep that started below 1e-10 (relative) ends at rounding level.
+            sm.red[2] = (off <= 1e-20 * sm.red[0]) ? 1.0 : 0.0;
         }
         __syncthreads();
-        if (sm.red[2] != 0.0) break;
+        if (sm.red[2] != 0.0) { ++sweep; break; }
     }
+    return sweep;
+}
+
+// Warm start: A <- Q^H A Q with Q = U (n x n, in sm.U), using `tmp` (2*n*n doubles of shared memory).
+__device__ inline void jacobi_similarity_block(JacobiSmem& sm, int n, double* tmp) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double* Tre = tmp; double* Tim = tmp + n * n;
+    for (int t = tid; t < n * n; t += nt) {          // T = A Q
+        const int i = t % n, j = t / n;
+        double re = 0.0, im = 0.0;
+        for (int k = 0; k < n; ++k) {
+            const double ar = sm.Are[i + n * k], ai = sm.Aim[i + n * k], qr = sm.Ure[k + n * j], qi = sm.Uim[k + n * j];
+            re += ar * qr - ai * qi; im += ar * qi + ai * qr;
+        }
+        Tre[t] = re; Tim[t] = im;
+    }
+    __syncthreads();
+    for (int t = tid; t < n * n; t += nt) {          // A = Q^H T
+        const int i = t % n, j = t / n;
+        double re = 0.0, im = 0.0;
+        for (int k = 0; k < n; ++k) {
+            const double qr = sm.Ure[k + n * i], qi = -sm.Uim[k + n * i], tr = Tre[k + n * j], ti = Tim[k + n * j];
+            re += qr * tr - qi * ti; im += qr * ti + qi * tr;
+        }
+        sm.Are[t] = re; sm.Aim[t] = im;
+    }
+    __syncthreads();
+    for (int t = tid; t < n * n; t += nt) {          // enforce exact Hermitian symmetry
+        const int i = t % n, j = t / n;
+        if (i < j) {
+            const double re = 0.5 * (sm.Are[i + n * j] + sm.Are[j + n * i]), im = 0.5 * (sm.Aim[i + n * j] - sm.Aim[j + n * i]);
+            sm.Are[i + n * j] = re; sm.Aim[i + n * j] = im; sm.Are[j + n * i] = re; sm.Aim[j + n * i] = -im;
+        } else if (i == j) sm.Aim[t] = 0.0;
+    }
+    __syncthreads();
 }
 
 // Spectral weights of svt.m:7 applied on the left: W = U diag(f) U^H with

@@ -156,17 +156,21 @@ struct __align__(8) PipeBars {
 };
 // Initialise the barriers and zero the ring (so that never-written ring bytes are finite), then make
 // the generic-proxy writes visible to the async proxy before the first bulk copy lands.
+// (the zero fill is only needed when some reduction range is not a multiple of stage_cols)
 template <int STAGES>
-__device__ __forceinline__ void pipe_bars_init(PipeBars<STAGES>& pb, void* ring, size_t ring_bytes) {
+__device__ __forceinline__ void pipe_bars_init(PipeBars<STAGES>& pb, void* ring, size_t ring_bytes, bool zero_ring) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&pb.full[s], 1); pb.cnt[s] = 0; }
         mbar_fence_init();
     }
-    float4* r4 = reinterpret_cast<float4*>(ring);
-    for (size_t i = threadIdx.x; i < ring_bytes / 16; i += blockDim.x) r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (zero_ring) {
+        float4* r4 = reinterpret_cast<float4*>(ring);
+        for (size_t i = threadIdx.x; i < ring_bytes / 16; i += blockDim.x) r4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     __syncthreads();
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <typename T, int STAGES = kStages>
 struct StreamPipe {
