@@ -132,6 +132,82 @@ int jstsp_mc_admm(jstsp_handle* h, int dtype, int mem, int Mr, int Mt, int batch
                   const void* omega, long long ld_omega, const double* tau, const double* rho,
                   void* X, long long ld_X, void* conv, long long ld_conv);
 
+/* ---- orthogonal matching pursuit ------------------------------------------------------ */
+/* [x_hat, indexSet, v, targetMatrix] = OMP(A, v, m, snr)   replaces benchmark_algorithms/OMP.m:1-32
+ *   (snr is unused by the reference and absent here; v is echoed by the gateway).
+ *   A measures x size_d complex; v measures x 1; x_hat size_d x 1 (out); index_set m int32 per
+ *   trial, 1-based, first-maximum tie rule of OMP.m:17 (out); target_matrix measures x m (out, may
+ *   be NULL); ambiguous (may be NULL): per trial, the number of iterations whose best/runner-up
+ *   correlation magnitudes differ by less than margin_tol (relative) - 0 means the support is
+ *   robust against evaluation-order rounding. */
+int jstsp_omp(jstsp_handle* h, int dtype, int mem, int measures, int size_d, int m, int batch,
+              const void* A, long long ld_A, const void* v, long long ld_v,
+              void* x_hat, long long ld_x, int* index_set, void* target_matrix, int* ambiguous, double margin_tol);
+
+/* [S, convergence_error] = sparse_admm(Htrue, OH, Dr, Dt, Imax)
+ *   replaces benchmark_algorithms/sparse_admm.m:1-36 (rho = 0.01, tau_s = 1e-4 hard-coded, :12-13).
+ *   Like the reference this needs Gr == Mr and Gt == Mt (Dr Mr x Mr, Dt Mt x Mt); Mr, Mt <= 64.
+ *   Htrue and conv (imax x 1 real) may both be NULL. */
+int jstsp_sparse_admm(jstsp_handle* h, int dtype, int mem, int Mr, int Mt, int batch, int imax,
+                      const void* Htrue, long long ld_H, const void* OH, long long ld_OH,
+                      const void* Dr, long long ld_Dr, const void* Dt, long long ld_Dt,
+                      void* S, long long ld_S, void* conv, long long ld_conv);
+
+/* ---- VAMP ------------------------------------------------------------------------------- */
+/* x = vamp(y, A, sigma, L)   replaces benchmark_algorithms/vamp.m:1-55 + VampGlmEst.m:350-521 for
+ *   nit iterations (vamp.m: 100) with damping `damp` (vamp.m: 0.85).  y m x 1, A m x n complex;
+ *   sigma (noise variance) and L (expected non-zeros) one double per trial.  The spectral basis is an
+ *   input, computed by the caller exactly where vamp.m:32 calls svd: for m <= n `basis` is the m x m
+ *   complex eigenvector matrix U of A A^H and d its m eigenvalues (= squared singular values of A,
+ *   each of which appears twice in the reference's real-embedded d).  m > n is not implemented. */
+int jstsp_vamp(jstsp_handle* h, int dtype, int mem, int m, int n, int batch, int nit, double damp,
+               const void* y, long long ld_y, const void* A, long long ld_A, const double* sigma, const double* L,
+               const void* basis, long long ld_basis, const void* d, long long ld_d, void* x, long long ld_x);
+
+/* ---- measurement model ------------------------------------------------------------------ */
+/* [H,Zbar,Ar,At,Dr,Dt] = wideband_mmwave_channel(L,Mr,Mt,Ncl,Nray,Gr,Gt)
+ *   replaces basic_system_functions/wideband_mmwave_channel.m:1-62, quirks included (page-1
+ *   steering vectors :24-25, cumulative cluster sum :29).  The draws are inputs, per trial and in
+ *   the reference's order: normals[2*(l*Np+ray)+{0,1}] = the two randn of :19,
+ *   uniforms[2*(l*Np+ray)+{0,1}] = the rand of :20 and of :22.  Any output may be NULL.
+ *   H Mr x Mt x L, Zbar Gr x (L*Gt), Ar Mr x Np x L, At Mt x Np x L, Dr Mr x Gr, Dt Mt x Gt. */
+int jstsp_wideband_mmwave_channel(jstsp_handle* h, int dtype, int mem, int L, int Mr, int Mt, int ncl, int nray, int Gr, int Gt, int batch,
+                                  const double* normals, const double* uniforms,
+                                  void* H, void* Zbar, void* Ar, void* At, void* Dr, void* Dt);
+
+typedef struct {
+    int Nr, Nt, L, T;      /* H is Nr x Nt x L, T training columns                                 */
+    int Wc;                /* W_e = W(:, 1:Wc)  (Lr_e of proposed_hbf.m:11, Lr of hbf.m:23)          */
+    int Lr;                /* ones per mask column (proposed_hbf.m:39); ignored when perm == NULL   */
+    int psi_mode;          /* 0: Psi is Psi_i (Tp x Tp x Nt, only rows 1..L are read);              */
+    int Tp;                /* 1: Psi is the pilot matrix (Nt x T, row k = s_k), Toeplitz rows built on the fly */
+    int batch;
+    long long ld_H, ld_N, ld_Psi, ld_W;   /* trial strides (0 = shared)                            */
+} jstsp_meas_desc;
+
+/* Measurement synthesis shared by
+ *   [Y_proposed_hbf,W_e,Psi_bar,Omega,Y] = proposed_hbf(H,N,Psi_i,T,Lr_e,Lr,W)   (proposed_hbf.m:1-44)
+ *   [Y_conventional_hbf,W_c,Psi_bar,Y]   = hbf(H,N,Psi_i,T,Lr,W)                 (hbf.m:1-26)
+ *   and the synthesis part of wideband_hybBF_comm_system_training.m:24-56:
+ *     Y = sum_l H(:,:,l) Psi_bar(:,:,l), Psi_bar(k,:,l) = Psi_i(l,:,k);  Y_out = [Omega .*] (W_e' (Y + N)).
+ *   perm: the randperm draws of proposed_hbf.m:38, T x Wc int32 per trial (1-based), or NULL for
+ *   the unmasked (hbf) output.  Outputs (any may be NULL): Y_out Wc x T, W_e Nr x Wc,
+ *   Psi_bar Nt x T x L, Omega Wc x T real, Y_noiseless Nr x T. */
+int jstsp_measure(jstsp_handle* h, const jstsp_meas_desc* d, int dtype, int mem,
+                  const void* H, const void* N, const void* Psi, const void* W, const int* perm,
+                  void* Y_out, void* W_e, void* Psi_bar, void* Omega, void* Y_noiseless);
+
+/* ---- driver-side metric and parameters ("next" rows) ---------------------- */
+/* nmse[b] = min(1, norm(S-Zbar)^2/norm(Zbar)^2) with matrix 2-norms (plot_errorVSsnr.m:138-141). */
+int jstsp_nmse(jstsp_handle* h, int dtype, int mem, int G, int P, int batch,
+               const void* S, long long ld_S, const void* Zbar, long long ld_Z, double* nmse);
+/* tau_Y = 1/norm(Y,'fro')^2, tau_Z = 1/norm(Zbar,'fro')^2/2, rho = sqrt(lambda_k(Y'Y)/norm(Y,'fro')^2)
+ * with k = kth_eig: 6 for min(eigs(.)) (plot_errorVSsnr.m:127-130), 1 for max(eigs(.))
+ * (plot_errorVSdelays.m:127-128).  Zbar / tau_Z may be NULL. */
+int jstsp_admm_parameters(jstsp_handle* h, int dtype, int mem, int N, int M, int G, int P, int batch, int kth_eig,
+                          const void* Y, long long ld_Y, const void* Zbar, long long ld_Z,
+                          double* tau_Y, double* tau_Z, double* rho);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,12 @@ class AdmmDesc(C.Structure):
     ]
 
 
+class MeasDesc(C.Structure):
+    _fields_ = [("Nr", C.c_int), ("Nt", C.c_int), ("L", C.c_int), ("T", C.c_int), ("Wc", C.c_int), ("Lr", C.c_int),
+                ("psi_mode", C.c_int), ("Tp", C.c_int), ("batch", C.c_int),
+                ("ld_H", C.c_longlong), ("ld_N", C.c_longlong), ("ld_Psi", C.c_longlong), ("ld_W", C.c_longlong)]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(
@@ -60,6 +66,13 @@ def _load():
     lib.jstsp_proposed_algorithm_angles.argtypes = [vp, C.POINTER(AdmmDesc), i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.jstsp_svt.argtypes = [vp, i, i, i, i, i, vp, ll, vp, vp, ll]
     lib.jstsp_mc_svt.argtypes = [vp, i, i, i, i, i, i, vp, ll, vp, ll, vp, vp, vp, ll]
+    lib.jstsp_omp.argtypes = [vp, i, i, i, i, i, i, vp, ll, vp, ll, vp, ll, vp, vp, vp, C.c_double]
+    lib.jstsp_sparse_admm.argtypes = [vp, i, i, i, i, i, i, vp, ll, vp, ll, vp, ll, vp, ll, vp, ll, vp, ll]
+    lib.jstsp_vamp.argtypes = [vp, i, i, i, i, i, i, C.c_double, vp, ll, vp, ll, vp, vp, vp, ll, vp, ll, vp, ll]
+    lib.jstsp_wideband_mmwave_channel.argtypes = [vp, i, i, i, i, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.jstsp_measure.argtypes = [vp, C.POINTER(MeasDesc), i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.jstsp_nmse.argtypes = [vp, i, i, i, i, i, vp, ll, vp, ll, vp]
+    lib.jstsp_admm_parameters.argtypes = [vp, i, i, i, i, i, i, i, i, vp, ll, vp, ll, vp, vp, vp]
     lib.jstsp_mc_admm.argtypes = [vp, i, i, i, i, i, i, vp, ll, vp, ll, vp, ll, vp, vp, vp, ll, vp, ll]
     return lib
 
@@ -71,7 +84,8 @@ EXPORTED = [
     "jstsp_create", "jstsp_destroy", "jstsp_last_error", "jstsp_version", "jstsp_set_stream",
     "jstsp_synchronize", "jstsp_launch_count", "jstsp_set_chunk", "jstsp_profile", "jstsp_profile_read", "jstsp_debug_buffer",
     "jstsp_proposed_algorithm", "jstsp_proposed_algorithm_angles",
-    "jstsp_svt", "jstsp_mc_svt", "jstsp_mc_admm",
+    "jstsp_svt", "jstsp_mc_svt", "jstsp_mc_admm", "jstsp_omp", "jstsp_sparse_admm", "jstsp_vamp",
+    "jstsp_wideband_mmwave_channel", "jstsp_measure", "jstsp_nmse", "jstsp_admm_parameters",
 ]
 
 

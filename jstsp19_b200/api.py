@@ -173,3 +173,183 @@ def mc_admm(Htrue, OH, Omega, Imax, tau, rho, *, precision="f64", handle=None, n
         X = X[0]
         conv = conv[0] if conv is not None else None
     return (X, conv) if nargout >= 2 else X
+
+
+def OMP(A, v, m, snr=None, *, precision="f64", handle=None, return_ambiguous=False):
+    """[x_hat, indexSet, v, targetMatrix] = OMP(A, v, m, snr)  (benchmark_algorithms/OMP.m:1).
+    ``indexSet`` is a list of 1-based indices (the reference returns a 1 x m cell of scalars);
+    ``snr`` is accepted and ignored exactly like the reference does.  A leading batch axis on
+    ``v`` (and optionally ``A``) solves independent problems in one call."""
+    h = handle or default_handle()
+    cd = _CD[precision]
+    v_in = v
+    va = np.asarray(v)
+    single = va.ndim == 1 or (va.ndim == 2 and 1 in va.shape and np.asarray(A).ndim == 2)
+    vb = np.ascontiguousarray(va.reshape(1, -1) if single else va.reshape(va.shape[0], -1), dtype=cd)
+    batch, measures = vb.shape
+    Am = _cm(A, cd)
+    size_d = Am.shape[-2]
+    if Am.shape[-1] != measures:
+        raise ValueError("A must be measures x size_d")
+    m = int(m)
+    x = np.empty((batch, size_d), dtype=cd)
+    idx = np.empty((batch, m), dtype=np.int32)
+    tgt = np.empty((batch, m, measures), dtype=cd)
+    amb = np.zeros(batch, dtype=np.int32)
+    tol = 1e-10 if precision == "f64" else 1e-4
+    h.check(_lib.lib.jstsp_omp(h.ptr, _DT[precision], _lib.HOST, measures, size_d, m, batch, _ptr(Am),
+                               measures * size_d if Am.ndim == 3 else 0, _ptr(vb), measures, _ptr(x), size_d,
+                               _ptr(idx), _ptr(tgt), _ptr(amb), tol))
+    T = np.swapaxes(tgt, -1, -2)
+    if single:
+        out = (x[0], [int(k) for k in idx[0]], v_in, T[0])
+        return out + (int(amb[0]),) if return_ambiguous else out
+    out = (x, idx, v_in, T)
+    return out + (amb,) if return_ambiguous else out
+
+
+def sparse_admm(Htrue, OH, Dr, Dt, Imax, *, precision="f64", handle=None, nargout=2):
+    """[S, convergence_error] = sparse_admm(Htrue, OH, Dr, Dt, Imax)  (benchmark_algorithms/sparse_admm.m:1)."""
+    h = handle or default_handle()
+    cd, rd = _CD[precision], _RD[precision]
+    bs = _batch_of(OH, 2)
+    batch = 1 if bs is None else bs
+    Om = _cm(OH, cd)
+    Mr, Mt = Om.shape[-1], Om.shape[-2]
+    Drm, Dtm = _cm(Dr, cd), _cm(Dt, cd)
+    if Drm.shape[-2:] != (Mr, Mr) or Dtm.shape[-2:] != (Mt, Mt):
+        raise ValueError("sparse_admm needs square dictionaries (Gr == Mr, Gt == Mt), like the reference")
+    Ht = _cm(Htrue, cd) if (Htrue is not None and nargout >= 2) else None
+    S = np.empty((batch, Mt, Mr), dtype=cd)
+    conv = np.empty((batch, int(Imax)), dtype=rd) if Ht is not None else None
+    h.check(_lib.lib.jstsp_sparse_admm(h.ptr, _DT[precision], _lib.HOST, Mr, Mt, batch, int(Imax),
+                                       _ptr(Ht), Mr * Mt, _ptr(Om), Mr * Mt, _ptr(Drm), Mr * Mr if Drm.ndim == 3 else 0,
+                                       _ptr(Dtm), Mt * Mt if Dtm.ndim == 3 else 0, _ptr(S), Mr * Mt, _ptr(conv), int(Imax)))
+    S = np.swapaxes(S, -1, -2)
+    if bs is None:
+        S = S[0]
+        conv = conv[0] if conv is not None else None
+    return (S, conv) if nargout >= 2 else S
+
+
+def vamp(y, A, sigma, L, *, precision="f64", handle=None, nit=100, damp=0.85):
+    """x = vamp(y, A, sigma, L)  (benchmark_algorithms/vamp.m:1).  The spectral decomposition that
+    vamp.m:32 obtains from MATLAB's ``svd`` is taken from the host's LAPACK here (NumPy); the 100
+    VampGlmEst iterations run on the GPU."""
+    h = handle or default_handle()
+    cd, rd = _CD[precision], _RD[precision]
+    A = np.asarray(A, dtype=np.complex128)
+    m, n = A.shape
+    if m > n:
+        raise NotImplementedError("vamp: m > n (VampGlmEst.m:407-411) is not implemented on the GPU path yet")
+    U, s, _ = np.linalg.svd(A, full_matrices=True)                # complex svd of A; embedding doubles each singular value
+    d = np.concatenate([s ** 2, np.zeros(m - s.size)])
+    yv = np.ascontiguousarray(np.asarray(y).reshape(1, -1), dtype=cd)
+    Am, Um = _cm(A, cd), _cm(U, cd)
+    dv = np.ascontiguousarray(d, dtype=rd)
+    x = np.empty((1, n), dtype=cd)
+    sg, Ln = _per_trial(sigma, 1), _per_trial(L, 1)
+    h.check(_lib.lib.jstsp_vamp(h.ptr, _DT[precision], _lib.HOST, m, n, 1, int(nit), float(damp), _ptr(yv), m, _ptr(Am), 0,
+                                _ptr(sg), _ptr(Ln), _ptr(Um), 0, _ptr(dv), 0, _ptr(x), n))
+    return x[0]
+
+
+def wideband_mmwave_channel(L, Mr, Mt, total_num_of_clusters, total_num_of_rays, Gr, Gt, *, normals, uniforms,
+                            precision="f64", handle=None):
+    """[H, Zbar, Ar, At, Dr, Dt] = wideband_mmwave_channel(L, Mr, Mt, Ncl, Nray, Gr, Gt)
+    (basic_system_functions/wideband_mmwave_channel.m:1).  ``normals`` / ``uniforms``: the randn / rand
+    draws in the reference's order, shape (L*Ncl*Nray, 2) each (a MEX gateway takes them from MATLAB's RNG)."""
+    h = handle or default_handle()
+    cd = _CD[precision]
+    Np = total_num_of_clusters * total_num_of_rays
+    nr = np.ascontiguousarray(np.asarray(normals, dtype=np.float64).reshape(L * Np * 2))
+    un = np.ascontiguousarray(np.asarray(uniforms, dtype=np.float64).reshape(L * Np * 2))
+    H = np.empty((L, Mt, Mr), dtype=cd); Zbar = np.empty((L * Gt, Gr), dtype=cd)
+    Ar = np.empty((L, Np, Mr), dtype=cd); At = np.empty((L, Np, Mt), dtype=cd)
+    Dr = np.empty((Gr, Mr), dtype=cd); Dt = np.empty((Gt, Mt), dtype=cd)
+    h.check(_lib.lib.jstsp_wideband_mmwave_channel(h.ptr, _DT[precision], _lib.HOST, L, Mr, Mt, total_num_of_clusters, total_num_of_rays,
+                                                   Gr, Gt, 1, _ptr(nr), _ptr(un), _ptr(H), _ptr(Zbar), _ptr(Ar), _ptr(At), _ptr(Dr), _ptr(Dt)))
+    t3 = lambda a: np.transpose(a, (2, 1, 0))                     # (L, cols, rows) storage -> rows x cols x L
+    return t3(H), Zbar.T, t3(Ar), t3(At), Dr.T, Dt.T
+
+
+def _measure(H, N, Psi_i, T, Wc, Lr, W, perm, precision, handle, pilots=None):
+    h = handle or default_handle()
+    cd, rd = _CD[precision], _RD[precision]
+    H = np.asarray(H)
+    Nr, Nt, L = H.shape
+    d = _lib.MeasDesc()
+    d.Nr, d.Nt, d.L, d.T, d.Wc, d.Lr, d.batch = Nr, Nt, L, int(T), int(Wc), int(Lr), 1
+    Hm = np.ascontiguousarray(np.transpose(H, (2, 1, 0)), dtype=cd)
+    Nm = _cm(N, cd) if N is not None else None
+    if pilots is not None:
+        d.psi_mode, d.Tp = 1, 0
+        Pm = _cm(pilots, cd)
+    else:
+        Psi_i = np.asarray(Psi_i)
+        d.psi_mode, d.Tp = 0, Psi_i.shape[0]
+        Pm = np.ascontiguousarray(np.transpose(Psi_i, (2, 1, 0)), dtype=cd)
+    Wm = _cm(W, cd)
+    pm = np.ascontiguousarray(perm, dtype=np.int32) if perm is not None else None
+    Y = np.empty((T, Wc), dtype=cd); We = np.empty((Wc, Nr), dtype=cd); Pb = np.empty((L, T, Nt), dtype=cd)
+    Om = np.empty((T, Wc), dtype=rd) if perm is not None else None
+    Yn = np.empty((T, Nr), dtype=cd)
+    h.check(_lib.lib.jstsp_measure(h.ptr, C.byref(d), _DT[precision], _lib.HOST, _ptr(Hm), _ptr(Nm), _ptr(Pm), _ptr(Wm), _ptr(pm),
+                                   _ptr(Y), _ptr(We), _ptr(Pb), _ptr(Om), _ptr(Yn)))
+    return Y.T, We.T, np.transpose(Pb, (2, 1, 0)), (Om.T if Om is not None else None), Yn.T
+
+
+def proposed_hbf(H, N, Psi_i, T, Lr_e, Lr, W, *, perm, precision="f64", handle=None, pilots=None):
+    """[Y_proposed_hbf, W_e, Psi_bar, Omega, Y] = proposed_hbf(H, N, Psi_i, T, Lr_e, Lr, W)
+    (basic_system_functions/proposed_hbf.m:1).  ``perm``: the T randperm(Lr_e) draws of :38, shape (T, Lr_e),
+    1-based.  ``pilots`` (Nt x T) may replace the dense ``Psi_i`` (T x T x Nt) - same values, no T^2 array."""
+    return _measure(H, N, Psi_i, T, Lr_e, Lr, W, perm, precision, handle, pilots)
+
+
+def hbf(H, N, Psi_i, T, Lr, W, *, precision="f64", handle=None, pilots=None):
+    """[Y_conventional_hbf, W_c, Psi_bar, Y] = hbf(H, N, Psi_i, T, Lr, W)  (basic_system_functions/hbf.m:1)."""
+    Y, Wc, Pb, _, Yn = _measure(H, N, Psi_i, T, Lr, 0, W, None, precision, handle, pilots)
+    return Y, Wc, Pb, Yn
+
+
+def wideband_hybBF_comm_system_training(H, T, snr, subSamplingRatio, *, noise_normals, pilot_normals, perm, precision="f64", handle=None):
+    """[Y_proposed_hbf, Y_conventional_hbf, W_tilde, Psi_bar, Omega, Lr] = wideband_hybBF_comm_system_training(H, T, snr, ratio)
+    (basic_system_functions/wideband_hybBF_comm_system_training.m:1).  Draws in the reference's order:
+    ``noise_normals`` (2, Nr, T) = the two randn(Nr,T) of :16; ``pilot_normals`` (Nt, 2, T) = the randn(1,T) pairs of :20;
+    ``perm`` (T, Nr) = the randperm(Nr) of :49."""
+    import math
+    H = np.asarray(H)
+    Nr, Nt, L = H.shape
+    Lr = int(math.floor(abs(subSamplingRatio * Nr) + 0.5))        # MATLAB round (:5)
+    nn, pn = np.asarray(noise_normals, dtype=np.float64), np.asarray(pilot_normals, dtype=np.float64)
+    N = math.sqrt(snr / 2.0) * (nn[0] + 1j * nn[1])                # :16
+    pilots = (pn[:, 0, :] + 1j * pn[:, 1, :]) / math.sqrt(2.0)     # :20
+    W = np.fft.fft(np.eye(Nr), axis=0) / math.sqrt(Nr)             # :10
+    Yp, _, Pb, Om, _ = _measure(H, N, None, T, Nr, Lr, W, perm, precision, handle, pilots)
+    Yc, _, _, _, _ = _measure(H, N, None, T, Nr, 0, W, None, precision, handle, pilots)
+    return Yp, Yc, W, Pb, Om, Lr
+
+
+def nmse(S, Zbar, *, precision="f64", handle=None):
+    """min(1, norm(S-Zbar)^2/norm(Zbar)^2), matrix 2-norms (plot_errorVSsnr.m:138-141)."""
+    h = handle or default_handle()
+    cd = _CD[precision]
+    bs = _batch_of(S, 2)
+    batch = 1 if bs is None else bs
+    Sm, Zm = _cm(S, cd), _cm(Zbar, cd)
+    G, P = Sm.shape[-1], Sm.shape[-2]
+    out = np.empty(batch, dtype=np.float64)
+    h.check(_lib.lib.jstsp_nmse(h.ptr, _DT[precision], _lib.HOST, G, P, batch, _ptr(Sm), G * P, _ptr(Zm), G * P, _ptr(out)))
+    return float(out[0]) if bs is None else out
+
+
+def admm_parameters(Y, Zbar, rho_rule="sigma6", *, precision="f64", handle=None):
+    """(tau_Y, tau_Z, rho) of plot_errorVSsnr.m:127-130 (rho_rule 'sigma6') or plot_errorVSdelays.m:127-128 ('sigma1')."""
+    h = handle or default_handle()
+    cd = _CD[precision]
+    Ym, Zm = _cm(Y, cd), _cm(Zbar, cd)
+    N, M, G, P = Ym.shape[-1], Ym.shape[-2], Zm.shape[-1], Zm.shape[-2]
+    tY, tZ, rho = (np.empty(1, dtype=np.float64) for _ in range(3))
+    h.check(_lib.lib.jstsp_admm_parameters(h.ptr, _DT[precision], _lib.HOST, N, M, G, P, 1, 6 if rho_rule == "sigma6" else 1,
+                                           _ptr(Ym), N * M, _ptr(Zm), G * P, _ptr(tY), _ptr(tZ), _ptr(rho)))
+    return float(tY[0]), float(tZ[0]), float(rho[0])
