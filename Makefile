@@ -21,3 +21,16 @@ clean:
 	rm -rf build/obj $(LIB)
 
 .PHONY: all clean
+
+# ---- MEX gateways against the in-repo mex.h shim (unit-test build; a MATLAB user runs `mex -R2018a`) ----
+MEXDIR  := jstsp19_b200/mex
+MEXSRC  := $(filter-out $(MEXDIR)/shim/%,$(wildcard $(MEXDIR)/*.c))
+MEXOUT  := $(patsubst $(MEXDIR)/%.c,$(MEXDIR)/build/%.so,$(MEXSRC))
+
+mex-shim: $(LIB) $(MEXOUT)
+
+$(MEXDIR)/build/%.so: $(MEXDIR)/%.c $(MEXDIR)/gateway_common.h $(MEXDIR)/shim/mex.h $(MEXDIR)/shim/mex_shim.c include/jstsp_b200.h
+	@mkdir -p $(MEXDIR)/build
+	gcc -O2 -Wall -Wno-misleading-indentation -Wno-unused-function -shared -fPIC -I$(MEXDIR)/shim -o $@ $< $(MEXDIR)/shim/mex_shim.c -Ljstsp19_b200 -ljstsp_b200 -Wl,-rpath,'$$ORIGIN/../..' -lm
+
+.PHONY: mex-shim

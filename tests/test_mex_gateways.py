@@ -1,0 +1,208 @@
+"""MEX gateways (jstsp19_b200/mex/*.c) driven through the mex.h shim (tests/mexharness.py).
+
+CPU part: every gateway compiles, exports mexFunction, validates nargin / sizes with MATLAB-style error ids, and
+fails loudly (jstsp:nogpu) when no CUDA device exists.  GPU part: each gateway reproduces the oracle on the
+same seeded inputs, with the reference's RNG calls served through mexCallMATLAB in the reference's order."""
+import numpy as np
+import pytest
+
+from oracle import estimators as est
+from oracle import fixtures as fx
+from oracle import matlab_compat as mc
+from oracle import system_model as sm
+from oracle import vamp as ovamp
+
+import mexharness as mh
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300))
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    mh.build()
+
+
+@pytest.mark.parametrize("name", mh.GATEWAYS)
+def test_gateway_builds_and_checks_nargin(name):
+    g = mh.Gateway(name)
+    assert hasattr(g.so, "mexFunction")
+    with pytest.raises(mh.MexError) as e:
+        g(1)                                   # no inputs at all
+    assert e.value.ident == "jstsp:nargin"
+
+
+def test_size_mismatch_is_a_matlab_error():
+    g = mh.Gateway("proposed_algorithm")
+    with pytest.raises(mh.MexError) as e:
+        g(1, np.zeros((4, 6)), np.zeros((4, 5)), np.zeros((4, 4)), np.zeros((3, 6)), 5, 1.0, 1.0, 1.0, "approximate")
+    assert e.value.ident == "jstsp:size"
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-device failure mode")
+def test_no_gpu_fails_loudly():
+    g = mh.Gateway("svt")
+    with pytest.raises(mh.MexError) as e:
+        g(1, np.eye(4) + 0j, 0.1)
+    assert e.value.ident == "jstsp:nogpu"
+
+
+class Script:
+    """Serves mexCallMATLAB from a RefRandom (the same seed drives the oracle) plus svd."""
+
+    def __init__(self, seed):
+        self.rng = mc.RefRandom(seed)
+
+    def __call__(self, name, args):
+        if name == "randn":
+            shape = tuple(int(a.reshape(-1)[0]) for a in args)
+            return [np.asarray(self.rng.randn(*shape)) if shape else np.asarray(self.rng.randn())]
+        if name == "rand":
+            return [np.asarray(self.rng.rand())]
+        if name == "randperm":
+            return [np.asarray(self.rng.randperm(int(args[0].reshape(-1)[0])), dtype=np.float64).reshape(1, -1)]
+        if name == "svd":
+            U, s, Vh = np.linalg.svd(args[0], full_matrices=True)
+            S = np.zeros(args[0].shape)
+            S[: s.size, : s.size] = np.diag(s)
+            return [U, S, Vh.conj().T]
+        raise KeyError(name)
+
+
+@pytest.mark.gpu
+def test_channel_gateway_reproduces_seeded_stream():
+    g = mh.Gateway("wideband_mmwave_channel")
+    g.set_matlab(Script(5))
+    out = g(6, 3, 16, 8, 2, 3, 16, 8)
+    ref = sm.wideband_mmwave_channel(3, 16, 8, 2, 3, 16, 8, mc.RefRandom(5))
+    assert len(out) == 6
+    for a, b in zip(out, ref):
+        assert a.shape == b.shape and _rel(a, b) < 1e-12
+
+
+@pytest.mark.gpu
+def test_training_gateway_reproduces_seeded_stream():
+    H = sm.wideband_mmwave_channel(2, 8, 4, 2, 3, 8, 4, mc.RefRandom(1))[0]
+    g = mh.Gateway("wideband_hybBF_comm_system_training")
+    g.set_matlab(Script(9))
+    Yp, Yc, Wt, Pb, Om, Lr = g(6, H, 12, 0.1, 0.75)
+    Yp0, Yc0, Wt0, Pb0, Om0, Lr0 = sm.wideband_hybBF_comm_system_training(H, 12, 0.1, 0.75, mc.RefRandom(9))
+    assert int(Lr[0, 0]) == Lr0 and np.array_equal(Om, Om0)            # mask bit-exact
+    assert np.all(Om.sum(axis=0) == Lr0)
+    for a, b in ((Yp, Yp0), (Yc, Yc0), (Wt, Wt0), (Pb, Pb0)):
+        assert a.shape == b.shape and _rel(a, b) < 1e-12
+
+
+@pytest.mark.gpu
+def test_hbf_gateways_match_oracle():
+    s = fx.TINY
+    t = fx.make_trial(s, 5.0, 3)
+    Psi_i = sm.psi_i_literal(t["pilots"], s.M)
+    g = mh.Gateway("proposed_hbf")
+    g.set_matlab(Script(11))
+    Y1, We1, Pb1, Om1, Yn1 = g(5, t["H"], t["N"], Psi_i, s.M, s.Mr_e, s.Mr, t["W"])
+    Y0, We0, Pb0, Om0, Yn0 = sm.proposed_hbf(t["H"], t["N"], Psi_i, s.M, s.Mr_e, s.Mr, t["W"], mc.RefRandom(11))
+    assert np.array_equal(Om1, Om0)
+    for a, b in ((Y1, Y0), (We1, We0), (Pb1, Pb0), (Yn1, Yn0)):
+        assert _rel(a, b) < 1e-12
+    g2 = mh.Gateway("hbf")
+    Yc1, Wc1, Pb2, Yn2 = g2(4, t["H"], t["N"], Psi_i, s.M, s.Nr, t["W"])
+    Yc0, Wc0, Pb0, Yn0 = sm.hbf(t["H"], t["N"], Psi_i, s.M, s.Nr, t["W"])
+    for a, b in ((Yc1, Yc0), (Wc1, Wc0), (Pb2, Pb0), (Yn2, Yn0)):
+        assert _rel(a, b) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("type_", ["approximate", "std", "anything-else-is-std"])
+def test_proposed_algorithm_gateway(type_):
+    t = fx.make_trial(fx.TINY, 5.0, 11)
+    g = mh.Gateway("proposed_algorithm")
+    S1, Y1, c1 = g(3, t["subY"], t["Omega"], t["A"], t["B"], 30, t["tau_Y"], t["tau_Z"], t["rho"], type_)
+    S0, Y0, c0 = est.proposed_algorithm_structured(t["subY"], t["Omega"], t["A"], t["B"], 30, t["tau_Y"], t["tau_Z"], t["rho"],
+                                                   "approximate" if type_ == "approximate" else "std")
+    assert _rel(S1, S0) < 1e-8 and _rel(Y1, Y0) < 1e-8
+    assert c1.shape == (30, 3)
+    np.testing.assert_allclose(c1[:, :2], c0[:, :2], rtol=1e-6)
+    (S_only,) = g(1, t["subY"], t["Omega"], t["A"], t["B"], 30, t["tau_Y"], t["tau_Z"], t["rho"], type_)
+    assert np.array_equal(S_only, S1)                                   # nargout does not change the result
+
+
+@pytest.mark.gpu
+def test_proposed_algorithm_angles_gateway():
+    t = fx.make_trial(fx.CONFIG0, 5.0, 12)
+    g = mh.Gateway("proposed_algorithm_angles")
+    S1, Y1 = g(2, t["subY"], t["Omega"], t["indx_S"].astype(np.float64), t["A"], t["B"], 40, t["tau_Y"], t["tau_Z"], t["rho"], "approximate", 20)
+    S0, Y0, _ = est.proposed_algorithm_structured(t["subY"], t["Omega"], t["A"], t["B"], 40, t["tau_Y"], t["tau_Z"], t["rho"], "approximate",
+                                                  indx_S=t["indx_S"])
+    assert _rel(S1, S0) < 1e-8 and _rel(Y1, Y0) < 1e-8
+
+
+@pytest.mark.gpu
+def test_svt_family_gateways():
+    t = fx.make_trial(fx.TINY, 5.0, 21)
+    Yh, Om = t["subY"], t["Omega"]
+    tau = 0.3 * np.linalg.norm(Yh, 2)
+    (X1,) = mh.Gateway("svt")(1, Yh, tau)
+    assert _rel(X1, est.svt_literal(Yh, tau)) < 1e-10
+    (X2,) = mh.Gateway("mc_svt")(1, Yh, Om, 25, tau, 0.1)
+    assert _rel(X2, est.mc_svt(Yh, Om, 25, tau, 0.1)) < 1e-9
+    Htrue = t["Ynoiseless"][: Yh.shape[0], :]
+    X3, c3 = mh.Gateway("mc_admm")(2, Htrue, Yh, Om, 25, tau, 0.1)
+    X0, c0 = est.mc_admm_structured(Htrue, Yh, Om, 25, tau, 0.1)
+    assert _rel(X3, X0) < 1e-9
+    np.testing.assert_allclose(c3.reshape(-1), c0, rtol=1e-6)
+    # real-valued (non-complex) inputs are accepted wherever complex is expected
+    (Xr,) = mh.Gateway("svt")(1, np.asarray(Yh.real), tau)
+    assert _rel(Xr, est.svt_literal(Yh.real + 0j, tau)) < 1e-10
+
+
+@pytest.mark.gpu
+def test_sparse_admm_gateway():
+    rng = np.random.default_rng(3)
+    Mr, Mt = 8, 4
+    Dr, Dt = sm.dft_dictionary(Mr, Mr), sm.dft_dictionary(Mt, Mt)
+    Htrue = rng.standard_normal((Mr, Mt)) + 1j * rng.standard_normal((Mr, Mt))
+    OH = Htrue + 0.05 * (rng.standard_normal((Mr, Mt)) + 1j * rng.standard_normal((Mr, Mt)))
+    S1, c1 = mh.Gateway("sparse_admm")(2, Htrue, OH, Dr, Dt, 20)
+    S0, c0 = est.sparse_admm_structured(Htrue, OH, Dr, Dt, 20)
+    assert _rel(S1, S0) < 1e-9
+    np.testing.assert_allclose(c1.reshape(-1), c0, rtol=1e-6)
+
+
+@pytest.mark.gpu
+def test_omp_gateway_cell_output_and_support():
+    rng = np.random.default_rng(5)
+    A = (rng.standard_normal((24, 40)) + 1j * rng.standard_normal((24, 40))) / np.sqrt(24)
+    x = np.zeros(40, complex)
+    x[[3, 17, 29]] = [1.0 + 0.5j, -0.8j, 0.6]
+    v = A @ x
+    g = mh.Gateway("OMP")
+    xh, idx, vecho, tgt = g(4, A, v, 3, 10.0)
+    x0, idx0, _, tgt0 = est.omp_literal(A, v, 3)
+    assert isinstance(idx, list) and [int(c[0, 0]) for c in idx] == [int(i) for i in idx0]     # 1 x m cell of double scalars, bit-exact
+    assert _rel(xh.reshape(-1), np.asarray(x0).reshape(-1)) < 1e-9 and _rel(tgt, tgt0) < 1e-12
+    assert np.array_equal(vecho.reshape(-1), v)
+
+
+@pytest.mark.gpu
+def test_vamp_gateway_uses_matlab_svd():
+    rng = np.random.default_rng(8)
+    m, n = 24, 48
+    A = (rng.standard_normal((m, n)) + 1j * rng.standard_normal((m, n))) / np.sqrt(m)
+    x = np.zeros(n, complex)
+    x[rng.choice(n, 5, replace=False)] = rng.standard_normal(5) + 1j * rng.standard_normal(5)
+    y = A @ x + 0.01 * (rng.standard_normal(m) + 1j * rng.standard_normal(m))
+    g = mh.Gateway("vamp")
+    g.set_matlab(Script(0))
+    (x1,) = g(1, y, A, 1.0, 5)
+    x0 = ovamp.vamp_literal(y, A, 1.0, 5)
+    assert _rel(x1.reshape(-1), np.asarray(x0).reshape(-1)) < 1e-6
