@@ -54,6 +54,8 @@ struct AdmmP {
 
 }  // namespace jstsp
 #include "admm_fast.cuh"
+#include "admm_tc.cuh"
+#include <type_traits>
 namespace jstsp {
 
 // ---------------------------------------------------------------------------------------
@@ -657,6 +659,13 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
                         VstepFastSmem<T>::bytes(N, G, p.GNG, P) <= h->smem_optin && XupdFastSmem<T>::bytes(N, p.NG, want_conv) <= h->smem_optin;
     const bool fast_xupd = fast_v;      // the pair shares the row-major T1 partial layout
     const bool fast_xs = approx && !no_fast && rows8 && segM && XsFastSmem<T>::bytes(N, p.NG, P, want_conv) <= h->smem_optin;
+    // tensor-core path (admm_tc.cuh): fp32, 'approximate', no diagnostics, 16 rows, whole 128-column chunks, 128-float blocks of 2P
+    constexpr int TC_NST = 4;
+    bool use_tc = false;
+    if constexpr (std::is_same<T, float>::value) {
+        use_tc = fast_v && !want_conv && N == 16 && M % tc::MC == 0 && P % 64 == 0 && getenv("JSTSP_DISABLE_TC") == nullptr &&
+                 tc::Geo<16, TC_NST>::SMEM <= h->smem_optin && tc::encode_fn() != nullptr;
+    }
     // chunk geometry
     const int XC = fast_xs ? cta_width(p.NG) : ExpandSmem<T, CB>::chunk_cols(p.NG);   // columns per CTA of k_xs
     const int nxc = ceil_div(M, XC);
@@ -673,6 +682,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
     int chunk_trials = batch;
     if (h->max_chunk > 0 && chunk_trials > h->max_chunk) chunk_trials = h->max_chunk;
     cx<T>* bt_ws = nullptr;
+    float* asop_ws = nullptr;            // tensor-core path: A S expanded into the pass-1 operand image (hi | lo)
     const int Wn = cta_width(p.NG);
     const long long Mpad = (long long)ceil_div(M, Wn) * Wn;      // B^T is stored in Wn-wide column tiles
     auto layout = [&](Arena& a, int nb, AdmmP<T>& q) {
@@ -692,7 +702,8 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
             q.pA = a.take<cx<T>>((size_t)G * N * (sharedA ? 1 : nb)); q.ld_pA = sharedA ? 0 : (long long)G * N;
             q.BBHinv = q.BBH;   // inverted in place
         }
-        if (fast_xs) bt_ws = a.take<cx<T>>((size_t)P * Mpad * (sharedB ? 1 : nb));
+        if (fast_xs && !use_tc) bt_ws = a.take<cx<T>>((size_t)P * Mpad * (sharedB ? 1 : nb));
+        if (use_tc) asop_ws = a.take<float>((size_t)nb * (P / 16) * (tc::Geo<16, TC_NST>::OP1 / 4));
         if (angles) q.smask = a.take<unsigned char>(GPn * nb);
         if (want_conv) {
             q.convd = a.take<double>((size_t)nb * imax * 3);
@@ -745,6 +756,9 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
     if (fast_xupd && (rc = set_smem(h, k_xupd_t1_fast<T>, sm_fx))) return rc;
     if (fast_v && (rc = set_smem(h, k_vstep_fast<T>, sm_fv))) return rc;
     if (fast_xs && (rc = set_smem(h, k_xs_fast<T>, sm_fs))) return rc;
+    if constexpr (std::is_same<T, float>::value) {
+        if (use_tc && (rc = set_smem(h, tc::k_fused_tc<16, TC_NST>, tc::Geo<16, TC_NST>::SMEM))) return rc;
+    }
 
     JSTSP_CUDA(h, cudaMemsetAsync(h->d_flag, 0, sizeof(int), st));
     const size_t esz = sizeof(cx<T>);
@@ -792,7 +806,11 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
         JSTSP_LAUNCH(h, PK_SETUP, (k_aha<T><<<nA, 256, 0, st>>>(q)));
         { dim3 g(ceil_div(P, 64), ceil_div(P, 64), nB); JSTSP_LAUNCH(h, PK_SETUP, (k_bbh<T><<<g, 256, 0, st>>>(q))); }
         const long long ld_Bt = d->ld_B ? (long long)P * Mpad : 0;
-        if (fast_xs) {
+        CUtensorMap mapB1, mapB2;
+        if constexpr (std::is_same<T, float>::value) {
+            if (use_tc && !tc::make_maps(q.B, q.ld_B, nB, P, M, &mapB1, &mapB2)) return fail(h, JSTSP_E_CUDA, "cuTensorMapEncodeTiled failed for the dictionary B");
+        }
+        if (fast_xs && !use_tc) {
             dim3 g(ceil_div(P, 32), (unsigned)(Mpad / 32), nB);
             JSTSP_LAUNCH(h, PK_SETUP, (k_transpose_b<T><<<g, 256, 0, st>>>(q.B, q.ld_B, bt_ws, ld_Bt, P, M, Wn)));
         }
@@ -813,7 +831,11 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
             if (angles) { dim3 g(1, nb); JSTSP_LAUNCH(h, PK_OTHER, (k_mask_grow<T><<<g, 64, 0, st>>>(q))); }
             {
                 dim3 g(q.nmc, nb);
-                if (fast_xupd) JSTSP_LAUNCH(h, PK_XUPD_T1, (k_xupd_t1_fast<T><<<g, kThreads, sm_fx, st>>>(q)));
+                if (use_tc) {
+                    if constexpr (std::is_same<T, float>::value)
+                        JSTSP_LAUNCH(h, PK_FUSED_TC, (tc::k_fused_tc<16, TC_NST><<<g, tc::THREADS, tc::Geo<16, TC_NST>::SMEM, st>>>(q, mapB1, mapB2, asop_ws, q.ld_B == 0 ? 1 : 0)));
+                }
+                else if (fast_xupd) JSTSP_LAUNCH(h, PK_XUPD_T1, (k_xupd_t1_fast<T><<<g, kThreads, sm_fx, st>>>(q)));
                 else JSTSP_LAUNCH(h, PK_XUPD_T1, (k_xupd_t1<T, KB><<<g, kThreads, sm_x, st>>>(q)));
             }
             if (it + 1 < imax) {
@@ -838,7 +860,12 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
                 if (approx) { dim3 g(npc, nb); JSTSP_LAUNCH(h, PK_Q, (k_q<T, CB><<<g, kThreads, sm_q, st>>>(q))); }
                 { dim3 g(ceil_div(P, kPV), nb); JSTSP_LAUNCH(h, PK_VUPD, (k_vupd<T><<<g, kThreads, sm_v, st>>>(q))); }
             }
-            {
+            if (use_tc) {
+                if constexpr (std::is_same<T, float>::value) {
+                    // Xs = (A S) B of this iteration is formed by the NEXT fused launch; hand it A S as the operand image
+                    if (it + 1 < imax) { dim3 g(4, nb); JSTSP_LAUNCH(h, PK_EXPAND, (tc::k_expand_as<16><<<g, 256, 0, st>>>(q.AS, asop_ws, P))); }
+                }
+            } else {
                 dim3 g(nxc, nb);
                 if (fast_xs) JSTSP_LAUNCH(h, PK_XS, (k_xs_fast<T><<<g, kThreads, sm_fs, st>>>(q, bt_ws, ld_Bt)));
                 else JSTSP_LAUNCH(h, PK_XS, (k_xs<T, CB><<<g, kThreads, sm_xs, st>>>(q)));

@@ -1,5 +1,5 @@
 """In-kernel phase timing of the ADMM fast-path kernels (developer tool, needs a B200).
-usage: JSTSP_DBG_KERNEL={0|2} python tools/phase_probe.py   (0 = k_xupd_t1_fast, 2 = k_xs_fast)"""
+usage: JSTSP_DBG_KERNEL={0|2|3} python tools/phase_probe.py   (0 = k_xupd_t1_fast, 2 = k_xs_fast, 3 = k_fused_tc; 0/2 need JSTSP_DISABLE_TC=1)"""
 import ctypes as C
 import os
 import sys
@@ -28,7 +28,15 @@ torch.cuda.synchronize()
 _lib.lib.jstsp_debug_buffer(eng.h.ptr, None)
 t = buf.cpu().numpy().reshape(ncta, 8)
 t = t[t[:, 0] > 0]
-names = {0: ["init+ring zero", "Z staging", "W Z + element-wise", "T1 main loop", "gram"], 2: ["init+ring zero", "AS staging", "main loop", "epilogue"]}[kid]
+if kid in (4, 5, 6):
+    cols = {4: ["MMA thread total", "wait full", "wait lo_ready", "wait kop_ready", "wait d2_empty"], 5: ["TMA thread total", "wait empty"],
+            6: ["wait hi_done (32 stages)", "rewrite body", "fence+arrive", "epilogues 0..2"]}[kid]
+    print(f"kernel 3 role stats (dbg {kid}), cycles per CTA: median / mean / p90")
+    for i, n in enumerate(cols):
+        v = t[:, i + 1].astype(np.float64)
+        print(f"  {n:26s} {np.median(v):10.0f} {v.mean():10.0f} {np.percentile(v, 90):10.0f}")
+    sys.exit(0)
+names = {3: ["pass-1 rewrites", "wait D1 + tmem ld", "element-wise", "pass-2 rewrites+epi", "last epilogue", "gram"], 0: ["init+ring zero", "Z staging", "W Z + element-wise", "T1 main loop", "gram"], 2: ["init+ring zero", "AS staging", "main loop", "epilogue"]}[kid]
 d = np.diff(t[:, : len(names) + 1], axis=1).astype(np.float64)
 print(f"kernel {kid}: {len(t)} CTAs, clock cycles per phase (median / mean / p90)")
 for i, n in enumerate(names):
