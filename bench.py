@@ -272,6 +272,7 @@ def main():
         "res": 8 * (G * P * P + G * N * P + G * G * P) * nb,          # V BBH, A^H T1, AHA (.)
         "q": 8 * (G * P * P + G * G * P) * nb,                        # Res BBH, AHA (.)
         "vupd": 8 * (N * G * P) * nb,                                # A S
+        "fused_tc": 8 * (2 * N * N * M + 2 * N * M * P) * nb,        # tcgen05 path: (A S) B, W Z, K B^H, next Gram in one kernel
     }
     tot_ms = sum(v[0] for v in prof.values()) or 1.0
     top = max((k for k in prof if k in kflops and prof[k][1] > 0), key=lambda k: prof[k][0], default=None)
@@ -280,10 +281,16 @@ def main():
         avg_ms = prof[top][0] / prof[top][1]
         achieved = kflops[top] / (avg_ms * 1e-3) / 1e12
         peak = pk["bf16_sus"] / 2.0 / 3.0          # TF32 dense = bf16/2; a 3xTF32-equivalent fp32 contraction is scored against TF32/3
-        roof = dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=None,
+        traffic = None                             # DRAM bytes per launch of that kernel from the committed ncu --set full capture (592 trials)
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tp):
+            t = json.load(open(tp)).get(top)
+            if t:
+                traffic = t["dram_bytes_per_launch_592_trials"] * nb / 592.0
+        roof = dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=traffic,
                     kernel=top, avg_launch_ms=avg_ms, share_of_step=prof[top][0] / tot_ms,
                     peak_source=f"{pk['src']} bf16_tflops_sustained/2 (TF32) /3 (3xTF32-equivalent fp32 accuracy), SURVEY.md 8(d)",
-                    pipe="fp32 FMA (CUDA cores)", fma_peak_tflops=72.0, frac_of_fma_peak=achieved / 72.0,
+                    pipe="tcgen05 kind::tf32 x3 (tensor cores)" if top == "fused_tc" else "fp32 FMA (CUDA cores)", fma_peak_tflops=72.0, frac_of_fma_peak=achieved / 72.0,
                     kernels={k: dict(ms_total=v[0], launches=v[1]) for k, v in prof.items() if v[1]})
     cpu = None
     if not args.no_cpu:

@@ -626,6 +626,12 @@ __global__ void k_convert(const Tsrc* src, Tdst* dst, size_t n) {
 // ---------------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------------
+// JSTSP_TC=1 / 0 selects / deselects the tcgen05 path (admm_tc.cuh) where its shape preconditions hold.
+// Default: off until it beats the FFMA kernels (both are parity-tested, tests/test_gpu_admm.py).
+static bool tc_enabled() {
+    const char* e = getenv("JSTSP_TC");
+    return e ? atoi(e) != 0 : false;
+}
 template <typename T>
 static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* subY_, const void* omega_, const int* indx_,
                     const void* A_, const void* B_, const double* tauY_, const double* tauS_, const double* rho_,
@@ -663,7 +669,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
     constexpr int TC_NST = 4;
     bool use_tc = false;
     if constexpr (std::is_same<T, float>::value) {
-        use_tc = fast_v && !want_conv && N == 16 && M % tc::MC == 0 && P % 64 == 0 && getenv("JSTSP_DISABLE_TC") == nullptr &&
+        use_tc = fast_v && !want_conv && N == 16 && M % tc::MC == 0 && P % 64 == 0 && tc_enabled() &&
                  tc::Geo<16, TC_NST>::SMEM <= h->smem_optin && tc::encode_fn() != nullptr;
     }
     // chunk geometry

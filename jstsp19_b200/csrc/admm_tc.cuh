@@ -211,17 +211,19 @@ __global__ void __launch_bounds__(THREADS, 2) k_fused_tc(AdmmP<float> p, const _
                 }
             };
             const bool dbg4 = p.dbg && p.dbg_kernel == 4;
-            long long w_full = 0, w_lo = 0, w_kop = 0, w_d2e = 0, t_begin = dbg4 ? clock64() : 0, tq = 0;
+            long long w_full = 0, w_lo = 0, w_kop = 0, w_d2e = 0, w_issue = 0, w_commit = 0, t_begin = dbg4 ? clock64() : 0, tq = 0;
             auto do_lo = [&](int gl) {
                 const int slot = gl % NST, use = gl / NST;
                 if (dbg4) tq = clock64();
                 mbar_wait(&lo_ready[slot], use & 1);
-                if (dbg4) w_lo += clock64() - tq;
+                if (dbg4) { long long t = clock64(); w_lo += t - tq; tq = t; }
                 tc_fence_after();
                 issue(gl, true);
+                if (dbg4) { long long t = clock64(); w_issue += t - tq; tq = t; }
                 umma_commit(&empty[slot]);
                 if (gl == S1 - 1) umma_commit(d1_full);
                 if (gl >= S1 && (gl - S1) % 4 == 3) umma_commit(&d2_full[((gl - S1) / 4) & 1]);
+                if (dbg4) w_commit += clock64() - tq;
             };
             int next_lo = 0;
             for (int g = 0; g < GT; ++g) {
@@ -241,15 +243,17 @@ __global__ void __launch_bounds__(THREADS, 2) k_fused_tc(AdmmP<float> p, const _
                 }
                 if (dbg4) tq = clock64();
                 mbar_wait(&full[slot], use & 1);
-                if (dbg4) w_full += clock64() - tq;
+                if (dbg4) { long long t = clock64(); w_full += t - tq; tq = t; }
                 tc_fence_after();
                 issue(g, false);
+                if (dbg4) { long long t = clock64(); w_issue += t - tq; tq = t; }
                 umma_commit(&hi_done[slot]);
+                if (dbg4) w_commit += clock64() - tq;
             }
             while (next_lo < GT) do_lo(next_lo++);
             if (dbg4) {
                 long long* o = p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8;
-                o[0] = 1; o[1] = clock64() - t_begin; o[2] = w_full; o[3] = w_lo; o[4] = w_kop; o[5] = w_d2e;
+                o[0] = 1; o[1] = clock64() - t_begin; o[2] = w_full; o[3] = w_lo; o[4] = w_kop; o[5] = w_d2e; o[6] = w_issue; o[7] = w_commit;
             }
         }
     } else {

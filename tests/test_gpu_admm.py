@@ -61,10 +61,13 @@ def test_std_branch_matches_oracle(precision):
     assert r["S"] < tol and r["Y"] < tol, r
 
 
-@pytest.mark.parametrize("precision", ["f64", "f32"])
-def test_metric_shape_batch(precision):
-    """Nt=64, Nr=16, K=16, L=4 (BASELINE.json configs[1]); 3 trials in one batched call, per-trial B."""
+@pytest.mark.parametrize("precision", ["f64", "f32", "f32-tcgen05"])
+def test_metric_shape_batch(precision, monkeypatch):
+    """Nt=64, Nr=16, K=16, L=4 (BASELINE.json configs[1]); 3 trials in one batched call, per-trial B.
+    "f32-tcgen05" runs the tensor-core kernel (admm_tc.cuh: 3xTF32 products, fp32 storage)."""
     import jstsp19_b200 as jb
+    monkeypatch.setenv("JSTSP_TC", "1" if precision.endswith("tcgen05") else "0")
+    precision = precision.split("-")[0]
     trials = [fx.make_trial(fx.METRIC, snr, 100 + k) for k, snr in enumerate([-15.0, 0.0, 15.0])]
     st = lambda k: np.stack([t[k] for t in trials])
     S1, Y1 = jb.proposed_algorithm(st("subY"), st("Omega"), st("A"), st("B"), 100,

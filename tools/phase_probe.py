@@ -1,5 +1,5 @@
 """In-kernel phase timing of the ADMM fast-path kernels (developer tool, needs a B200).
-usage: JSTSP_DBG_KERNEL={0|2|3} python tools/phase_probe.py   (0 = k_xupd_t1_fast, 2 = k_xs_fast, 3 = k_fused_tc; 0/2 need JSTSP_DISABLE_TC=1)"""
+usage: JSTSP_DBG_KERNEL={0|2|3} python tools/phase_probe.py   (0 = k_xupd_t1_fast, 2 = k_xs_fast, 3 = k_fused_tc; 3..6 need JSTSP_TC=1)"""
 import ctypes as C
 import os
 import sys
@@ -29,7 +29,7 @@ _lib.lib.jstsp_debug_buffer(eng.h.ptr, None)
 t = buf.cpu().numpy().reshape(ncta, 8)
 t = t[t[:, 0] > 0]
 if kid in (4, 5, 6):
-    cols = {4: ["MMA thread total", "wait full", "wait lo_ready", "wait kop_ready", "wait d2_empty"], 5: ["TMA thread total", "wait empty"],
+    cols = {4: ["MMA thread total", "wait full", "wait lo_ready", "wait kop_ready", "wait d2_empty", "issue (64 x 4 MMAs)", "commits"], 5: ["TMA thread total", "wait empty"],
             6: ["wait hi_done (32 stages)", "rewrite body", "fence+arrive", "epilogues 0..2"]}[kid]
     print(f"kernel 3 role stats (dbg {kid}), cycles per CTA: median / mean / p90")
     for i, n in enumerate(cols):

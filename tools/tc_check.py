@@ -21,6 +21,6 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         run()
     else:
-        for env in ({}, {"JSTSP_DISABLE_TC": "1"}):
+        for env in ({"JSTSP_TC": "1"}, {"JSTSP_TC": "0"}):
             print("env", env, flush=True)
             subprocess.run([sys.executable, __file__, "child"], env={**os.environ, **env})

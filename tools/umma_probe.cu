@@ -113,32 +113,32 @@ __global__ void __launch_bounds__(128) probe(const float* __restrict__ gA, const
 }
 
 // issue-rate probe: nrep x (4 k-steps) of M=128, N=nn MMAs on the same operands
-__global__ void __launch_bounds__(128) rate(int nn, int nrep, long long* cyc) {
+__global__ void __launch_bounds__(128) rate(int mm, int nn, int nrep, long long* cyc) {
     __shared__ __align__(128) float sA[128 * KS];
-    __shared__ __align__(128) float sB[64 * KS];
+    __shared__ __align__(128) float sB[224 * KS];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid / 32;
     if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(64u));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(256u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     for (int e = tid; e < 128 * KS; e += 128) sA[e] = 1.0f;
-    for (int e = tid; e < 64 * KS; e += 128) sB[e] = 0.5f;
+    for (int e = tid; e < 224 * KS; e += 128) sB[e] = 0.5f;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tm = tmem_base;
     if (tid == 0) {
-        const uint32_t idesc = make_idesc(128, nn, 0, 0);
+        const uint32_t idesc = make_idesc(mm, nn, 0, 0);
         long long t0 = clock64();
         for (int rep = 0; rep < nrep; ++rep) {
 #pragma unroll
             for (int ks = 0; ks < KS / 8; ++ks) {
                 uint64_t da = make_desc(smem_u32(sA) + ks * 2 * 2048, 2048, 128);
-                uint64_t db = make_desc(smem_u32(sB) + ks * 2 * 1024, 1024, 128);
+                uint64_t db = make_desc(smem_u32(sB) + ks * 2 * 3584, 3584, 128);      // 28 row groups per k group
                 umma_tf32(tm, da, db, idesc, 1u);
             }
         }
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(128) rate(int nn, int nrep, long long* cyc) {
     __syncthreads();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(64u));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(256u));
 }
 
 static float trunc_tf32(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xFFFFE000u; memcpy(&x, &u, 4); return x; }
@@ -184,14 +184,14 @@ int main() {
         printf("mode %d (%s A): max|D-trunc model| %.3e  max|D-rn model| %.3e  max|D-fp32| %.3e  (max|ref| %.2f)\n", mode, mode ? "MN-major" : "K-major", e_tr, e_rn, e_full, ref_max);
         if (e_tr > 2e-5 && e_rn > 2e-5) { printf("  MISMATCH in mode %d\n", mode); bad = 1; }
     }
-    for (int nn : {32, 64}) {
-        for (int nrep : {64, 512}) {
-            rate<<<1, 128>>>(nn, nrep, dc);
+    for (int mm : {128, 64})
+        for (int nn : {16, 32, 64, 96, 128, 192, 224}) {
+            const int nrep = 512;
+            rate<<<1, 128>>>(mm, nn, nrep, dc);
             CK(cudaDeviceSynchronize());
             long long c; CK(cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost));
-            printf("rate: M=128 N=%d K=8 SS tf32: %d MMAs in %lld cycles -> %.1f cycles/MMA\n", nn, nrep * 4, c, (double)c / (nrep * 4));
+            printf("rate: M=%d N=%d K=8 SS tf32: %.1f cycles/MMA\n", mm, nn, (double)c / (nrep * 4));
         }
-    }
     if (getenv("PROBE_MAP")) {
         // mapping dump for the MN-major view: B = selector of k, A = row index / k index
         for (int what = 0; what < 2; ++what) {
