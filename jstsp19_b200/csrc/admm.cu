@@ -38,6 +38,7 @@ struct AdmmP {
     double* gram;                       // [b][nmc][2*N*N] partial Gram of the next SVT input
     cx<T>* T1;                          // [b][nmc][N*P] partial K B^H
     cx<T> *V, *Res, *S, *AS;            // G x P (AS: N x P)
+    cx<T>* VB;                          // fast path: V BBH, row-major G x P, updated recursively
     cx<T>* AHA; long long ld_AHA;       // G x G
     cx<T>* BBH; long long ld_BBH;       // P x P
     cx<T>* pA;  long long ld_pA;        // 'std': pinv(A)  G x N
@@ -698,7 +699,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
         q.W = a.take<cx<T>>((size_t)N * N * nb * 2);           // double-buffered: the eigen-solve of iteration i+1 overlaps iteration i
         q.gram = a.take<double>((size_t)nb * q.nmc * 2 * N * N);
         q.T1 = a.take<cx<T>>((size_t)nb * q.nmc * N * P);
-        q.V = a.take<cx<T>>(GPn * nb); q.Res = a.take<cx<T>>(GPn * nb); q.S = a.take<cx<T>>(GPn * nb);
+        q.V = a.take<cx<T>>(GPn * nb); q.Res = a.take<cx<T>>(GPn * nb); q.S = a.take<cx<T>>(GPn * nb); q.VB = a.take<cx<T>>(GPn * nb);
         q.AS = a.take<cx<T>>((size_t)N * P * nb);
         q.dots = a.take<double>((size_t)nb * npc * 4);
         bool sharedA = d->ld_A == 0, sharedB = d->ld_B == 0;
@@ -806,6 +807,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
         JSTSP_CUDA(h, cudaMemsetAsync(q.gram, 0, sizeof(double) * (size_t)nb * q.nmc * 2 * N * N, st));
         JSTSP_CUDA(h, cudaMemsetAsync(q.V, 0, esz * GPn * nb, st));
         JSTSP_CUDA(h, cudaMemsetAsync(q.S, 0, esz * GPn * nb, st));
+        JSTSP_CUDA(h, cudaMemsetAsync(q.VB, 0, esz * GPn * nb, st));
         if (angles) JSTSP_CUDA(h, cudaMemsetAsync(q.smask, 0, GPn * nb, st));
         // one-off operators
         const int nA = d->ld_A ? nb : 1, nB = d->ld_B ? nb : 1;

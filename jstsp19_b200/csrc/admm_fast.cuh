@@ -303,10 +303,14 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_vstep_fast
     const cx<T>* BBH = p.BBH + (long long)b * p.ld_BBH;
     StreamPipe<T> pipe;
     uint32_t it = 0;
-    pipe.start(ring, bars, it, BBH, (long long)P, W, P, P);           // V BBH = sum_p V(:,p) conj(BBH(:,p)).' (BBH Hermitian)
     cx<T>* __restrict__ V = p.V + (size_t)b * G * P;
+    cx<T>* __restrict__ VBg = p.VB + (size_t)b * G * P;              // V BBH, row-major [G][P], carried across iterations
     const cx<T>* A = p.A + (long long)b * p.ld_A;
     const cx<T>* AHA = p.AHA + (long long)b * p.ld_AHA;
+    {   // BBH is streamed once the exchange rows (which alias the ring) are consumed: warm L2 meanwhile
+        const size_t bytes = sizeof(cx<T>) * (size_t)P * P;
+        for (size_t o = (size_t)threadIdx.x * 128; o < bytes; o += (size_t)kThreads * 128) prefetch_l2(reinterpret_cast<const char*>(BBH) + o);
+    }
     for (int t = threadIdx.x; t < N * G; t += kThreads) {
         const int n = t % N, g = t / N;
         const cx<T> a = A[t];
@@ -319,27 +323,16 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_vstep_fast
         A1re[(N + k) * RG + g] = -a.re; A1im[(N + k) * RG + g] = -a.im;
         Qre[k * RG + g] = a.re; Qim[k * RG + g] = a.im;
     }
-    double vv = 0.0;
-    for (int t = threadIdx.x; t < RG * Pc; t += kThreads) {
-        cx<T> v = mk<T>(T(0), T(0));
-        if (t < G * P) v = V[t];                                       // (g + G*o) == o*RG + g
-        Lre[t] = v.re; Lim[t] = v.im;
-        vv += (double)v.re * v.re + (double)v.im * v.im;
-    }
-    __syncthreads();
+    for (int t = threadIdx.x + G * P; t < RG * Pc; t += kThreads) { Lre[t] = T(0); Lim[t] = T(0); }   // padding columns of the streamed operand
     const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
     const int rg = warp % NGg, og = warp / NGg;
     const bool active = og < kWarps / NGg;
     const int o_0 = og * kOW + out_of<T>(lane, 0), o_1 = og * kOW + out_of<T>(lane, 1);
     T ar[kRB][2], ai[kRB][2];
-#pragma unroll
-    for (int r = 0; r < kRB; ++r) { ar[r][0] = ar[r][1] = ai[r][0] = ai[r][1] = T(0); }
-    it = pipe.template run<true>(Lre, Lim, RG, NGg, ar, ai);
-    // exchange rows: [0,N) = summed T1 (row-major partials), [N,N+G) = V BBH
-    if (active && og * kOW < pitch) {
-#pragma unroll
-        for (int r = 0; r < kRB; ++r) store_pair<T>(E + (size_t)(N + rg * kRB + r) * pitch + og * kOW, lane, ar[r][0], ai[r][0], ar[r][1], ai[r][1]);
-    }
+    // exchange rows: [0,N) = summed T1 (row-major partials), [N,N+G) = V BBH.
+    // V BBH is not recomputed: V_{i+1} = V_i + alpha Res_i  =>  V_{i+1} BBH = V_i BBH + alpha (Res_i BBH), and Res_i BBH is
+    // formed below for the line search anyway (.m:47-50) - one pass over BBH per iteration instead of two.
+    for (int t = threadIdx.x; t < G * P; t += kThreads) E[(size_t)(N + t / P) * pitch + (t % P)] = VBg[t];
     const cx<T>* T1 = p.T1 + (size_t)b * p.nmc * N * P;
     for (int t = threadIdx.x; t < N * P; t += kThreads) {
         T re = 0, im = 0;
@@ -352,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_vstep_fast
 #pragma unroll
     for (int r = 0; r < kRB; ++r) { rr_[r][0] = rr_[r][1] = ri_[r][0] = ri_[r][1] = T(0); }
     if (active && og * kOW < pitch) smem_contract<T>(A1re, A1im, RG, rg, E, pitch, og, N + G, rr_, ri_);
-    double rr = 0.0;
+    double rr = 0.0, vv = 0.0;
     if (active) {
 #pragma unroll
         for (int r = 0; r < kRB; ++r) {
@@ -390,6 +383,20 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_vstep_fast
             if (o_0 < P) rq += (double)rr_[r][0] * ar[r][0] + (double)ri_[r][0] * ai[r][0];
             if (o_1 < P) rq += (double)rr_[r][1] * ar[r][1] + (double)ri_[r][1] * ai[r][1];
         }
+        // |V|^2 of the iterate being left (third convergence diagnostic, .m:51)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int o = j == 0 ? o_0 : o_1;
+            if (o < P) {
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    cx<T> v[4];
+                    ld4c<T>(V + (size_t)o * G + rg * kRB + 4 * hf, v);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) vv += (double)v[u].re * v[u].re + (double)v[u].im * v[u].im;
+                }
+            }
+        }
     }
     for (int o = 16; o > 0; o >>= 1) { rr += __shfl_down_sync(0xffffffffu, rr, o); rq += __shfl_down_sync(0xffffffffu, rq, o); vv += __shfl_down_sync(0xffffffffu, vv, o); }
     if (lane == 0) { red[warp][0] = rr; red[warp][1] = rq; red[warp][2] = vv; }
@@ -408,6 +415,24 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_vstep_fast
     const T thr = (T)(p.tauS[b] / p.rho[b]);
     cx<T>* __restrict__ S = p.S + (size_t)b * G * P;
     const unsigned char* mask = p.angles ? p.smask + (size_t)b * G * P : nullptr;
+    if (active && og * kOW < pitch) {
+        // V BBH <- V BBH + alpha (Res BBH); Res BBH still sits in exchange rows [0,G)
+#pragma unroll
+        for (int r = 0; r < kRB; ++r) {
+            const int row = rg * kRB + r;
+            cx<T> b0, b1;
+            load_pair<T>(E + (size_t)row * pitch + og * kOW, lane, b0, b1);
+            if (o_1 < P) {
+                cx<T> v0, v1;
+                load_pair<T>(VBg + (size_t)row * P + og * kOW, lane, v0, v1);
+                store_pair<T>(VBg + (size_t)row * P + og * kOW, lane, v0.re + alpha * b0.re, v0.im + alpha * b0.im, v1.re + alpha * b1.re, v1.im + alpha * b1.im);
+            } else if (o_0 < P) {
+                cx<T>* q = VBg + (size_t)row * P + o_0;
+                *q = mk<T>(q->re + alpha * b0.re, q->im + alpha * b0.im);
+            }
+        }
+    }
+    __syncthreads();                                                   // exchange rows are rewritten with S below
     if (active) {
         T s_re[kRB][2], s_im[kRB][2];
 #pragma unroll
