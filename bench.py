@@ -147,7 +147,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--trials", type=int, default=592, help="trials per GPU per step (4 x 148 SMs)")
-    ap.add_argument("--e2e-trials", type=int, default=296)
+    ap.add_argument("--e2e-trials", type=int, default=1184, help="trials per end-to-end call (the library splits them into passes and overlaps the H2D of pass k+1 with the solve of pass k)")
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--cpu-trials", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
@@ -224,11 +224,17 @@ def main():
     e2e = None
     if not args.no_e2e:
         import ctypes as C
-        ne = min(args.e2e_trials, nb)
+        ne = args.e2e_trials
+        if ne > nb:      # more trials per call than the device-resident step: draw them with the same generator
+            esnr = torch.tensor([SNR_SWEEP[(first + k) % len(SNR_SWEEP)] for k in range(ne)], dtype=torch.float64)
+            edata = synth.make_batch(s, ne, esnr, seed=20190913, first_trial=rank * ne, device=dev, cdtype=cd)
+        else:
+            edata = data
         pin = lambda t: t[:ne].cpu().contiguous().pin_memory()
-        hsubY, hOm, hB = pin(data["subY"]), pin(data["Omega"]), pin(data["B"])
-        hA = data["A"].cpu().contiguous().pin_memory()
-        hty, hts, hrho = (data[k][:ne].cpu().contiguous().pin_memory() for k in ("tau_Y", "tau_Z", "rho"))
+        hsubY, hOm, hB = pin(edata["subY"]), pin(edata["Omega"]), pin(edata["B"])
+        hA = edata["A"].cpu().contiguous().pin_memory()
+        hty, hts, hrho = (edata[k][:ne].cpu().contiguous().pin_memory() for k in ("tau_Y", "tau_Z", "rho"))
+        del edata
         hS = torch.empty(ne, P, G, dtype=cd).pin_memory()
         d = _lib.AdmmDesc()
         d.N, d.M, d.G, d.P, d.imax, d.type, d.batch = N, M, G, P, IMAX, _lib.APPROXIMATE, ne
@@ -241,11 +247,11 @@ def main():
                                                    vp(hty), vp(hts), vp(hrho), vp(hS), None, None)
             eng.h.check(rc)
 
-        for _ in range(2):
+        for _ in range(3):
             host_step()
         barrier()
         t0 = time.perf_counter()
-        ksteps = max(2, args.steps // 2)
+        ksteps = max(3, args.steps // 2 + 1)
         for _ in range(ksteps):
             host_step()
         torch.cuda.synchronize()

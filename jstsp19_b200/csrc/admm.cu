@@ -688,10 +688,16 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
     size_t NM = (size_t)N * M, GPn = (size_t)G * P;
     int chunk_trials = batch;
     if (h->max_chunk > 0 && chunk_trials > h->max_chunk) chunk_trials = h->max_chunk;
+    // HOST buffers: passes of ~2 CTAs-per-SM worth of trials, so that the H2D copy of pass k+1 (copy stream, second staging
+    // set) overlaps the solve of pass k.  Smaller passes would leave SMs idle in the one-CTA-per-trial kernels.
+    const int pass_min = 2 * h->sm_count;
+    if (host && h->max_chunk == 0 && batch >= 2 * pass_min) chunk_trials = ceil_div(batch, batch / pass_min);
+    bool pingpong = host && chunk_trials < batch;
     cx<T>* bt_ws = nullptr;
     float* asop_ws = nullptr;            // tensor-core path: A S expanded into the pass-1 operand image (hi | lo)
     const int Wn = cta_width(p.NG);
     const long long Mpad = (long long)ceil_div(M, Wn) * Wn;      // B^T is stored in Wn-wide column tiles
+    int stage_set = 0;
     auto layout = [&](Arena& a, int nb, AdmmP<T>& q) {
         q.X = a.take<cx<T>>(NM * nb); q.V1 = a.take<cx<T>>(NM * nb); q.V2 = a.take<cx<T>>(NM * nb);
         q.C = a.take<cx<T>>(NM * nb); q.Xs = a.take<cx<T>>(NM * nb);
@@ -717,14 +723,18 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
             q.cgramA = a.take<double>((size_t)nb * 2 * q.nmc * 2 * N * N);
             q.cgramB = a.take<double>((size_t)nb * q.nxc * 2 * N * N);
         }
-        // staging for host inputs / outputs
+        // staging for host inputs / outputs (two sets when passes ping-pong)
         if (host) {
-            q.subY = a.take<cx<T>>(d->ld_subY ? NM * nb : NM);
-            q.omega = a.take<T>(d->ld_omega ? NM * nb : NM);
-            q.A = a.take<cx<T>>((size_t)N * G * (d->ld_A ? nb : 1));
-            q.B = a.take<cx<T>>((size_t)P * M * (d->ld_B ? nb : 1));
-            q.rho = a.take<double>(nb); q.tauY = a.take<double>(nb); q.tauS = a.take<double>(nb);
-            if (angles) q.indx = a.take<int>((size_t)d->n_indx * (d->ld_indx ? nb : 1));
+            for (int set = 0; set < (pingpong ? 2 : 1); ++set) {
+                const bool use = set == stage_set || !pingpong;
+                const cx<T>* s_subY = a.take<cx<T>>(d->ld_subY ? NM * nb : NM);
+                const T* s_omega = a.take<T>(d->ld_omega ? NM * nb : NM);
+                const cx<T>* s_A = a.take<cx<T>>((size_t)N * G * (d->ld_A ? nb : 1));
+                const cx<T>* s_B = a.take<cx<T>>((size_t)P * M * (d->ld_B ? nb : 1));
+                const double *s_rho = a.take<double>(nb), *s_tauY = a.take<double>(nb), *s_tauS = a.take<double>(nb);
+                const int* s_indx = angles ? a.take<int>((size_t)d->n_indx * (d->ld_indx ? nb : 1)) : nullptr;
+                if (use) { q.subY = s_subY; q.omega = s_omega; q.A = s_A; q.B = s_B; q.rho = s_rho; q.tauY = s_tauY; q.tauS = s_tauS; q.indx = s_indx; }
+            }
             if (Y_) q.Yout = a.take<cx<T>>(NM * nb);
         }
     };
@@ -733,6 +743,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
     JSTSP_CUDA(h, cudaMemGetInfo(&freeb, &totalb));
     size_t budget = (size_t)((freeb + h->ws_bytes) * 0.7);
     for (;;) {
+        pingpong = host && chunk_trials < batch;
         Arena probe(nullptr, 0); AdmmP<T> q = p; layout(probe, chunk_trials, q);
         if (probe.off <= budget || chunk_trials == 1) { int rc = ensure_workspace(h, probe.off); if (rc) return rc; break; }
         chunk_trials = (chunk_trials + 1) / 2;
@@ -769,26 +780,37 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
 
     JSTSP_CUDA(h, cudaMemsetAsync(h->d_flag, 0, sizeof(int), st));
     const size_t esz = sizeof(cx<T>);
+    int pass_idx = -1;
     for (int b0 = 0; b0 < batch; b0 += chunk_trials) {
         const int nb = (batch - b0) < chunk_trials ? (batch - b0) : chunk_trials;
+        ++pass_idx;
+        stage_set = pass_idx & 1;
         Arena ar(h->ws, h->ws_bytes);
         AdmmP<T> q = p;
-        layout(ar, nb, q);
+        layout(ar, chunk_trials, q);         // identical carve-up for every pass (the staging sets must not move)
         q.ld_subY = d->ld_subY; q.ld_omega = d->ld_omega; q.ld_A = d->ld_A; q.ld_B = d->ld_B; q.ld_indx = d->ld_indx; q.ld_Y = d->ld_Y;
         if (host) {
+            // inputs travel on the copy stream into staging set `pass & 1`; the solve of this pass waits for them, the copy
+            // of pass k+2 into the same set waits for the solve of pass k
+            cudaStream_t cs = pingpong ? h->copy : st;
+            if (pingpong && pass_idx >= 2) JSTSP_CUDA(h, cudaStreamWaitEvent(cs, h->ev_done[pass_idx & 1], 0));
             auto up = [&](const void* dst, const void* src, size_t elems_per, long long ld, size_t el) -> cudaError_t {
-                if (ld == 0) return cudaMemcpyAsync(const_cast<void*>(dst), src, elems_per * el, cudaMemcpyHostToDevice, st);
-                if ((size_t)ld == elems_per) return cudaMemcpyAsync(const_cast<void*>(dst), (const char*)src + (size_t)b0 * ld * el, elems_per * el * nb, cudaMemcpyHostToDevice, st);
-                return cudaMemcpy2DAsync(const_cast<void*>(dst), elems_per * el, (const char*)src + (size_t)b0 * ld * el, (size_t)ld * el, elems_per * el, nb, cudaMemcpyHostToDevice, st);
+                if (ld == 0) return cudaMemcpyAsync(const_cast<void*>(dst), src, elems_per * el, cudaMemcpyHostToDevice, cs);
+                if ((size_t)ld == elems_per) return cudaMemcpyAsync(const_cast<void*>(dst), (const char*)src + (size_t)b0 * ld * el, elems_per * el * nb, cudaMemcpyHostToDevice, cs);
+                return cudaMemcpy2DAsync(const_cast<void*>(dst), elems_per * el, (const char*)src + (size_t)b0 * ld * el, (size_t)ld * el, elems_per * el, nb, cudaMemcpyHostToDevice, cs);
             };
             JSTSP_CUDA(h, up(q.subY, subY_, NM, d->ld_subY, esz));
             JSTSP_CUDA(h, up(q.omega, omega_, NM, d->ld_omega, sizeof(T)));
             JSTSP_CUDA(h, up(q.A, A_, (size_t)N * G, d->ld_A, esz));
             JSTSP_CUDA(h, up(q.B, B_, (size_t)P * M, d->ld_B, esz));
-            JSTSP_CUDA(h, cudaMemcpyAsync(const_cast<double*>(q.rho), rho_ + b0, sizeof(double) * nb, cudaMemcpyHostToDevice, st));
-            JSTSP_CUDA(h, cudaMemcpyAsync(const_cast<double*>(q.tauY), tauY_ + b0, sizeof(double) * nb, cudaMemcpyHostToDevice, st));
-            JSTSP_CUDA(h, cudaMemcpyAsync(const_cast<double*>(q.tauS), tauS_ + b0, sizeof(double) * nb, cudaMemcpyHostToDevice, st));
+            JSTSP_CUDA(h, cudaMemcpyAsync(const_cast<double*>(q.rho), rho_ + b0, sizeof(double) * nb, cudaMemcpyHostToDevice, cs));
+            JSTSP_CUDA(h, cudaMemcpyAsync(const_cast<double*>(q.tauY), tauY_ + b0, sizeof(double) * nb, cudaMemcpyHostToDevice, cs));
+            JSTSP_CUDA(h, cudaMemcpyAsync(const_cast<double*>(q.tauS), tauS_ + b0, sizeof(double) * nb, cudaMemcpyHostToDevice, cs));
             if (angles) JSTSP_CUDA(h, up(q.indx, indx_, (size_t)d->n_indx, d->ld_indx, sizeof(int)));
+            if (pingpong) {
+                JSTSP_CUDA(h, cudaEventRecord(h->ev_in[pass_idx & 1], cs));
+                JSTSP_CUDA(h, cudaStreamWaitEvent(st, h->ev_in[pass_idx & 1], 0));
+            }
             if (q.ld_subY) q.ld_subY = NM; if (q.ld_omega) q.ld_omega = NM;
             if (q.ld_A) q.ld_A = (long long)N * G; if (q.ld_B) q.ld_B = (long long)P * M;
             if (q.ld_indx) q.ld_indx = d->n_indx;
@@ -915,8 +937,10 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
                 JSTSP_LAUNCH(h, PK_OTHER, (k_conv_out<T><<<nb, 128, 0, st>>>(q.convd, (T*)conv_ + (long long)b0 * ldc0, ldc0, imax)));
             }
         }
-        if (host) JSTSP_CUDA(h, cudaStreamSynchronize(st));
+        if (pingpong) JSTSP_CUDA(h, cudaEventRecord(h->ev_done[pass_idx & 1], st));
+        else if (host) JSTSP_CUDA(h, cudaStreamSynchronize(st));
     }
+    if (pingpong) JSTSP_CUDA(h, cudaStreamSynchronize(st));
     int bad = 0;
     if (host) {
         JSTSP_CUDA(h, cudaMemcpyAsync(&bad, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));

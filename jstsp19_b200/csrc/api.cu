@@ -23,6 +23,8 @@ extern "C" int jstsp_create(jstsp_handle** out, int device) {
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return JSTSP_E_CUDA; }
     h->own_stream = true;
     if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess) { delete h; return JSTSP_E_CUDA; }
+    if (cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking) != cudaSuccess) { delete h; return JSTSP_E_CUDA; }
+    for (int k = 0; k < 2; ++k) { cudaEventCreateWithFlags(&h->ev_in[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_done[k], cudaEventDisableTiming); }
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     if (cudaMalloc(&h->d_flag, sizeof(int)) != cudaSuccess) { delete h; return JSTSP_E_CUDA; }
@@ -40,6 +42,8 @@ extern "C" void jstsp_destroy(jstsp_handle* h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->side) cudaStreamDestroy(h->side);
+    if (h->copy) cudaStreamDestroy(h->copy);
+    for (int k = 0; k < 2; ++k) { if (h->ev_in[k]) cudaEventDestroy(h->ev_in[k]); if (h->ev_done[k]) cudaEventDestroy(h->ev_done[k]); }
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
