@@ -152,6 +152,9 @@ def main():
     ap.add_argument("--cpu-trials", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--entry", default="psi", choices=["psi", "dense"],
+                    help="psi: jstsp_proposed_algorithm_psi (dictionary given by its factors Dt, Psi_bar as the reference's drivers hold them); "
+                         "dense: jstsp_proposed_algorithm (dense B, the reference function's own argument list)")
     ap.add_argument("--shared-b", action="store_true", help="diagnostic: one pilot matrix B for all trials (L2-resident dictionary)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -183,9 +186,17 @@ def main():
     eng = AdmmEngine(local, args.precision)
     S = torch.empty(nb, P, G, dtype=cd, device=dev)
 
+    use_psi = args.entry == "psi"
+    if use_psi:
+        del data["B"]        # the structured entry never sees the dense dictionary
+
     def step():
-        eng.proposed_algorithm(data["subY"], data["Omega"], data["A"], data["B"], IMAX, data["tau_Y"], data["tau_Z"], data["rho"],
-                               "approximate", S_out=S)
+        if use_psi:
+            eng.proposed_algorithm_psi(data["subY"], data["Omega"], data["A"], data["Dt"], data["Psi"], IMAX, data["tau_Y"], data["tau_Z"], data["rho"],
+                                       "approximate", S_out=S)
+        else:
+            eng.proposed_algorithm(data["subY"], data["Omega"], data["A"], data["B"], IMAX, data["tau_Y"], data["tau_Z"], data["rho"],
+                                   "approximate", S_out=S)
 
     def barrier():
         if world > 1:
@@ -231,8 +242,9 @@ def main():
         else:
             edata = data
         pin = lambda t: t[:ne].cpu().contiguous().pin_memory()
-        hsubY, hOm, hB = pin(edata["subY"]), pin(edata["Omega"]), pin(edata["B"])
+        hsubY, hOm, hB = pin(edata["subY"]), pin(edata["Omega"]), pin(edata["Psi" if use_psi else "B"])
         hA = edata["A"].cpu().contiguous().pin_memory()
+        hDt = edata["Dt"].cpu().contiguous().pin_memory()
         hty, hts, hrho = (edata[k][:ne].cpu().contiguous().pin_memory() for k in ("tau_Y", "tau_Z", "rho"))
         del edata
         hS = torch.empty(ne, P, G, dtype=cd).pin_memory()
@@ -243,6 +255,11 @@ def main():
         vp = lambda t: C.c_void_p(t.data_ptr())
 
         def host_step():
+            if use_psi:
+                rc = _lib.lib.jstsp_proposed_algorithm_psi(eng.h.ptr, C.byref(d), dt, _lib.HOST, vp(hsubY), vp(hOm), None, vp(hA), vp(hDt), 0,
+                                                           vp(hB), s.Nt * M * s.L, s.Nt, s.L, vp(hty), vp(hts), vp(hrho), vp(hS), None, None)
+                eng.h.check(rc)
+                return
             rc = _lib.lib.jstsp_proposed_algorithm(eng.h.ptr, C.byref(d), dt, _lib.HOST, vp(hsubY), vp(hOm), vp(hA), vp(hB),
                                                    vp(hty), vp(hts), vp(hrho), vp(hS), None, None)
             eng.h.check(rc)
@@ -279,6 +296,7 @@ def main():
         "q": 8 * (G * P * P + G * G * P) * nb,                        # Res BBH, AHA (.)
         "vupd": 8 * (N * G * P) * nb,                                # A S
         "fused_tc": 8 * (2 * N * N * M + 2 * N * M * P) * nb,        # tcgen05 path: (A S) B, W Z, K B^H, next Gram in one kernel
+        "fused_psi": 8 * (2 * N * N * M + 2 * N * M * P) * nb,       # Psi-domain tcgen05 path: same products out of the bf16 pilot tile
     }
     tot_ms = sum(v[0] for v in prof.values()) or 1.0
     top = max((k for k in prof if k in kflops and prof[k][1] > 0), key=lambda k: prof[k][0], default=None)
@@ -296,7 +314,7 @@ def main():
         roof = dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=traffic,
                     kernel=top, avg_launch_ms=avg_ms, share_of_step=prof[top][0] / tot_ms,
                     peak_source=f"{pk['src']} bf16_tflops_sustained/2 (TF32) /3 (3xTF32-equivalent fp32 accuracy), SURVEY.md 8(d)",
-                    pipe="tcgen05 kind::tf32 x3 (tensor cores)" if top == "fused_tc" else "fp32 FMA (CUDA cores)", fma_peak_tflops=72.0, frac_of_fma_peak=achieved / 72.0,
+                    pipe={"fused_tc": "tcgen05 kind::tf32 x3 (tensor cores)", "fused_psi": "tcgen05 kind::f16, 3 bf16 terms x exact bf16 pilots (tensor cores)"}.get(top, "fp32 FMA (CUDA cores)"), fma_peak_tflops=72.0, frac_of_fma_peak=achieved / 72.0,
                     kernels={k: dict(ms_total=v[0], launches=v[1]) for k, v in prof.items() if v[1]})
     cpu = None
     if not args.no_cpu:
@@ -306,7 +324,8 @@ def main():
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=warm, ms_per_step=ms / args.steps,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32" if args.precision == "f32" else "f64",
                 data="synthetic",
-                config=dict(workload=WORKLOAD, trials_per_gpu_per_step=nb, imax=IMAX, shape=dict(N=N, M=M, G=G, P=P),
+                config=dict(workload=WORKLOAD, entry="jstsp_proposed_algorithm_psi (Dt, Psi_bar)" if use_psi else "jstsp_proposed_algorithm (dense B)",
+                            path=eng.h.last_path if use_psi else None, trials_per_gpu_per_step=nb, imax=IMAX, shape=dict(N=N, M=M, G=G, P=P),
                             l2="inputs larger than L2 (per-step inputs %.1f GB per GPU)" % (nb * (P * M + 2 * N * M) * (8 if args.precision == "f32" else 16) / 1e9),
                             parallelism=f"trials sharded over {world} GPU(s), one NCCL all-reduce of NMSE sums"),
                 clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu,

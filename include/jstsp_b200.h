@@ -113,6 +113,28 @@ int jstsp_proposed_algorithm_angles(jstsp_handle* h, const jstsp_admm_desc* d, i
                                     const double* tau_Y, const double* tau_S, const double* rho,
                                     void* S, void* Y, void* conv);
 
+/* The same estimator with the dictionary given by its factors, exactly as the reference's drivers hold them before
+ * they form B (plot_errorVSsnr.m:132-136, plot_errorVSdelays.m:130-134):
+ *     B((l-1)*Gt+1 : l*Gt, :) = Dt' * Psi_bar(:,:,l),   l = 1..L
+ *   Dt       Nt x Gt complex (output 6 of wideband_mmwave_channel.m:1), Gt = d->P / L, trial stride ld_Dt (0 = shared);
+ *   Psi_bar  Nt x M x L complex (output of proposed_hbf.m:1 / wideband_hybBF_comm_system_training.m:1), trial stride ld_Psi;
+ *   indx_S   NULL for proposed_algorithm, the ranking of proposed_algorithm_angles otherwise (d->n_indx, d->ld_indx);
+ *   d->ld_B is ignored; everything else as in jstsp_proposed_algorithm.
+ * When Psi_bar has the structure the drivers give it - Psi_bar(k,j,l) = e_k(j-l) (rows of toeplitz(s_k), proposed_hbf.m:15-18)
+ * with components that are exact in bf16 after one common scaling (4-QAM pilots, plot_errorVSsnr.m:63-67) - and the call is
+ * fp32 'approximate' with N = 16, Nt = 64, M % 128 == 0 and conv == NULL, both dictionary products of every iteration run on
+ * tcgen05 tensor cores out of a 34 KiB bf16 pilot tile per 128 columns (csrc/admm_psi.cuh) and the dense dictionary is never
+ * streamed.  Any other input is served by materialising B on the device and running the dense kernels of
+ * jstsp_proposed_algorithm; results agree to rounding either way.  jstsp_last_path reports which one ran. */
+int jstsp_proposed_algorithm_psi(jstsp_handle* h, const jstsp_admm_desc* d, int dtype, int mem,
+                                 const void* subY, const void* omega, const int* indx_S, const void* A,
+                                 const void* Dt, long long ld_Dt, const void* Psi_bar, long long ld_Psi, int Nt, int L,
+                                 const double* tau_Y, const double* tau_S, const double* rho,
+                                 void* S, void* Y, void* conv);
+/* Path taken by the last jstsp_proposed_algorithm_psi call on this handle: 1 = dense kernels on the materialised
+ * dictionary, 2 = Psi-domain tcgen05 kernel (0 = no call yet). */
+int jstsp_last_path(const jstsp_handle* h);
+
 /* ---- singular-value thresholding and the SVT-based benchmark solvers -------------- */
 /* X = svt(Y, tau)   replaces benchmark_algorithms/svt.m:1-15 (returns zeros when a
  * singular value is exactly 0, svt.m:7-13).  Y, X: Mr x Mt complex; tau: one double per trial. */

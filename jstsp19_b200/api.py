@@ -57,7 +57,7 @@ def _type_code(type_):
     return _lib.APPROXIMATE if type_ == "approximate" else _lib.STD
 
 
-def _admm(subY, Omega, indx_S, A, B, Imax, tau_Y, tau_S, rho, type_, precision, handle, nargout):
+def _admm(subY, Omega, indx_S, A, B, Imax, tau_Y, tau_S, rho, type_, precision, handle, nargout, psi=None):
     h = handle or default_handle()
     cd, rd = _CD[precision], _RD[precision]
     bs = _batch_of(subY, 2)
@@ -67,30 +67,47 @@ def _admm(subY, Omega, indx_S, A, B, Imax, tau_Y, tau_S, rho, type_, precision, 
     N, M = sY.shape[-1], sY.shape[-2]
     om = _cm(Omega, rd)
     Am = _cm(A, cd)
-    Bm = _cm(B, cd)
-    G, P = Am.shape[-2], Bm.shape[-1]
-    if Am.shape[-1] != N or Bm.shape[-2] != M or om.shape[-2:] != (M, N):
-        raise ValueError("inconsistent shapes: subY N x M, Omega N x M, A N x G, B P x M")
+    if psi is None:
+        Bm = _cm(B, cd)
+        G, P = Am.shape[-2], Bm.shape[-1]
+        bad = Bm.shape[-2] != M
+    else:
+        # Dt (Nt, Gt) [or (b, Nt, Gt)], Psi_bar (Nt, M, L) [or (b, Nt, M, L)] in MATLAB indexing -> column-major storage
+        Dt, Psi_bar = np.asarray(psi[0]), np.asarray(psi[1])
+        Dm = _cm(Dt, cd)
+        Pm = np.ascontiguousarray(np.moveaxis(Psi_bar, (-3, -2, -1), (-1, -2, -3)), dtype=cd)      # (..., L, M, Nt)
+        Nt, Gt, L = Dm.shape[-1], Dm.shape[-2], Pm.shape[-3]
+        G, P = Am.shape[-2], L * Gt
+        Bm = None
+        bad = Pm.shape[-1] != Nt or Pm.shape[-2] != M
+    if Am.shape[-1] != N or bad or om.shape[-2:] != (M, N):
+        raise ValueError("inconsistent shapes: subY N x M, Omega N x M, A N x G, B P x M (or Dt Nt x Gt, Psi_bar Nt x M x L)")
     d = AdmmDesc()
     d.N, d.M, d.G, d.P, d.imax, d.type, d.batch = N, M, G, P, int(Imax), _type_code(type_), batch
     d.ld_subY = N * M
     d.ld_omega = N * M if om.ndim == 3 else 0
     d.ld_A = N * G if Am.ndim == 3 else 0
-    d.ld_B = P * M if Bm.ndim == 3 else 0
+    d.ld_B = P * M if (Bm is not None and Bm.ndim == 3) else 0
     d.ld_S, d.ld_Y, d.ld_conv = G * P, N * M, 3 * int(Imax)
     tY, tS, rh = _per_trial(tau_Y, batch), _per_trial(tau_S, batch), _per_trial(rho, batch)
     S = np.empty((batch, P, G), dtype=cd)
     Y = np.empty((batch, M, N), dtype=cd) if nargout >= 2 else None
     conv = np.empty((batch, 3, int(Imax)), dtype=rd) if nargout >= 3 else None
     dp = lambda a: a.ctypes.data_as(C.c_void_p)
-    if indx_S is None:
-        rc = _lib.lib.jstsp_proposed_algorithm(h.ptr, C.byref(d), _DT[precision], _lib.HOST, _ptr(sY), _ptr(om), _ptr(Am), _ptr(Bm),
-                                               dp(tY), dp(tS), dp(rh), _ptr(S), _ptr(Y), _ptr(conv))
-    else:
+    ix = None
+    if indx_S is not None:
         ix = np.ascontiguousarray(np.asarray(indx_S).reshape(batch, -1) if np.asarray(indx_S).ndim > 1
                                   else np.asarray(indx_S).reshape(1, -1), dtype=np.int32)
         d.n_indx = ix.shape[1]
         d.ld_indx = ix.shape[1] if ix.shape[0] == batch and batch > 1 else 0
+    if psi is not None:
+        rc = _lib.lib.jstsp_proposed_algorithm_psi(h.ptr, C.byref(d), _DT[precision], _lib.HOST, _ptr(sY), _ptr(om), _ptr(ix), _ptr(Am),
+                                                   _ptr(Dm), Nt * Gt if Dm.ndim == 3 else 0, _ptr(Pm), Nt * M * L if Pm.ndim == 4 else 0, Nt, L,
+                                                   dp(tY), dp(tS), dp(rh), _ptr(S), _ptr(Y), _ptr(conv))
+    elif indx_S is None:
+        rc = _lib.lib.jstsp_proposed_algorithm(h.ptr, C.byref(d), _DT[precision], _lib.HOST, _ptr(sY), _ptr(om), _ptr(Am), _ptr(Bm),
+                                               dp(tY), dp(tS), dp(rh), _ptr(S), _ptr(Y), _ptr(conv))
+    else:
         rc = _lib.lib.jstsp_proposed_algorithm_angles(h.ptr, C.byref(d), _DT[precision], _lib.HOST, _ptr(sY), _ptr(om), _ptr(ix),
                                                       _ptr(Am), _ptr(Bm), dp(tY), dp(tS), dp(rh), _ptr(S), _ptr(Y), _ptr(conv))
     h.check(rc)
@@ -116,6 +133,15 @@ def proposed_algorithm_angles(subY, Omega, indx_S, A, B, Imax, tau_Y, tau_S, rho
     rho, type, greedy_nnz)  (basic_system_functions/proposed_algorithm_angles.m:1).  ``indx_S`` is 1-based
     like in MATLAB; ``greedy_nnz`` is accepted and ignored exactly like the reference does."""
     return _admm(subY, Omega, indx_S, A, B, Imax, tau_Y, tau_S, rho, type, precision, handle, nargout)
+
+
+def proposed_algorithm_psi(subY, Omega, A, Dt, Psi_bar, Imax, tau_Y, tau_S, rho, type, indx_S=None, *,
+                           precision="f64", handle=None, nargout=3):
+    """proposed_algorithm / proposed_algorithm_angles with the dictionary given by the factors the reference's drivers
+    hold before they form ``B((l-1)*Gt+1:l*Gt,:) = Dt'*Psi_bar(:,:,l)`` (plot_errorVSsnr.m:132-136): ``Dt`` (Nt x Gt) from
+    wideband_mmwave_channel.m:1 and ``Psi_bar`` (Nt x M x L) from proposed_hbf.m:1.  Same outputs as
+    ``proposed_algorithm(subY, Omega, A, B, ...)`` with that ``B``; Toeplitz 4-QAM pilots take the tensor-core path."""
+    return _admm(subY, Omega, indx_S, A, None, Imax, tau_Y, tau_S, rho, type, precision, handle, nargout, psi=(Dt, Psi_bar))
 
 
 def svt(Y, tau, *, precision="f64", handle=None):

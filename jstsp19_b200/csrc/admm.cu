@@ -36,7 +36,8 @@ struct AdmmP {
     cx<T> *X, *V1, *V2, *C, *Xs;        // N x M per trial
     cx<T>* W;                           // N x N per trial (SVT spectral weights)
     double* gram;                       // [b][nmc][2*N*N] partial Gram of the next SVT input
-    cx<T>* T1;                          // [b][nmc][N*P] partial K B^H
+    cx<T>* T1;                          // [b][nt1][N*P] partial K B^H
+    int nt1;                            // partials per trial summed by k_vstep_fast (0 = nmc)
     cx<T> *V, *Res, *S, *AS;            // G x P (AS: N x P)
     cx<T>* VB;                          // fast path: V BBH, row-major G x P, updated recursively
     cx<T>* AHA; long long ld_AHA;       // G x G
@@ -56,6 +57,7 @@ struct AdmmP {
 }  // namespace jstsp
 #include "admm_fast.cuh"
 #include "admm_tc.cuh"
+#include "admm_psi.cuh"
 #include <type_traits>
 namespace jstsp {
 
@@ -633,14 +635,26 @@ static bool tc_enabled() {
     const char* e = getenv("JSTSP_TC");
     return e ? atoi(e) != 0 : false;
 }
+// structured dictionary B = (I (x) Dt') Psi_bar of jstsp_proposed_algorithm_psi (host-level description)
+struct PsiArgs { const void* Dt; long long ld_Dt; const void* Psi; long long ld_Psi; int Nt, Gt, L; };
+static bool psi_fast_enabled() {
+    const char* e = getenv("JSTSP_PSI_DENSE");      // developer switch: force the materialised-B kernels
+    return !(e && atoi(e) != 0);
+}
 template <typename T>
 static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* subY_, const void* omega_, const int* indx_,
                     const void* A_, const void* B_, const double* tauY_, const double* tauS_, const double* rho_,
-                    void* S_, void* Y_, void* conv_, bool angles) {
+                    void* S_, void* Y_, void* conv_, bool angles, const PsiArgs* ps = nullptr) {
     constexpr int CB = DT<T>::CB, KB = DT<T>::KB;
     const int N = d->N, M = d->M, G = d->G, P = d->P, batch = d->batch, imax = d->imax;
     if (N <= 0 || M <= 0 || G <= 0 || P <= 0 || batch <= 0 || imax < 0) return fail(h, JSTSP_E_ARG, "non-positive dimension");
-    if (!subY_ || !omega_ || !A_ || !B_ || !tauY_ || !tauS_ || !rho_ || !S_) return fail(h, JSTSP_E_ARG, "NULL buffer");
+    if (!subY_ || !omega_ || !A_ || (!B_ && !ps) || !tauY_ || !tauS_ || !rho_ || !S_) return fail(h, JSTSP_E_ARG, "NULL buffer");
+    if (ps) {
+        if (!ps->Dt || !ps->Psi) return fail(h, JSTSP_E_ARG, "NULL buffer");
+        if (ps->Nt <= 0 || ps->Gt <= 0 || ps->L <= 0 || ps->L * ps->Gt != P) return fail(h, JSTSP_E_ARG, "structured dictionary: P must equal L * Gt");
+    }
+    // B is built on the device from (Dt, Psi_bar): one dictionary per trial unless both factors are shared
+    const long long ldB_in = ps ? ((ps->ld_Psi || ps->ld_Dt) ? (long long)P * M : 0) : d->ld_B;
     if (angles && (!indx_ || d->n_indx <= 0)) return fail(h, JSTSP_E_ARG, "indx_S missing");
     if (N > 64 || G > 64) return fail(h, JSTSP_E_UNSUPPORTED, "proposed_algorithm kernels cover N <= 64 and G <= 64 rows");
     const bool approx = d->type == JSTSP_APPROXIMATE;
@@ -659,7 +673,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
     const bool overlap_eig = getenv("JSTSP_NO_OVERLAP") == nullptr;
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     const bool segP = (P * esz0) % 16 == 0, segM = (M * esz0) % 16 == 0;
-    const bool b_ok = host || (al16(B_) && ((size_t)d->ld_B * esz0) % 16 == 0);
+    const bool b_ok = host || ps || (al16(B_) && ((size_t)d->ld_B * esz0) % 16 == 0);
     const bool rows8 = (N % 8 == 0) && (G % 8 == 0);
     const bool io_ok = host || (al16(subY_) && al16(omega_) && ((size_t)d->ld_subY * esz0) % 16 == 0 && ((size_t)d->ld_omega * sizeof(T)) % 16 == 0);
     const bool fast_v = approx && !no_fast && rows8 && segP && b_ok && io_ok && P <= cta_width(p.GNG) && P <= cta_width(p.NG) &&
@@ -672,6 +686,14 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
     if constexpr (std::is_same<T, float>::value) {
         use_tc = fast_v && !want_conv && N == 16 && M % tc::MC == 0 && P % 64 == 0 && tc_enabled() &&
                  tc::Geo<16, TC_NST>::SMEM <= h->smem_optin && tc::encode_fn() != nullptr;
+    }
+    // structured-dictionary tensor-core path (admm_psi.cuh): fp32, 'approximate', no diagnostics, 16 rows, 64 antennas, Toeplitz bf16-exact pilots
+    bool psi_shape = false;
+    if constexpr (std::is_same<T, float>::value) {
+        psi_shape = ps && fast_v && !want_conv && N == psi::N && M % tc::MC == 0 && ps->Nt == psi::NT && ps->Gt <= psi::NT && ps->L <= psi::MAXL && G <= psi::N &&
+                    psi_fast_enabled() && psi::SMEM <= h->smem_optin && tc::encode_fn() != nullptr &&
+                    (host || (al16(ps->Psi) && al16(ps->Dt)));
+        if (ps) use_tc = false;
     }
     // chunk geometry
     const int XC = fast_xs ? cta_width(p.NG) : ExpandSmem<T, CB>::chunk_cols(p.NG);   // columns per CTA of k_xs
@@ -694,6 +716,9 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
     if (host && h->max_chunk == 0 && batch >= 2 * pass_min) chunk_trials = ceil_div(batch, batch / pass_min);
     bool pingpong = host && chunk_trials < batch;
     cx<T>* bt_ws = nullptr;
+    cx<T>* b_ws = nullptr;               // structured entry: the materialised dictionary
+    psi::In pin{};                       // structured entry: device-side description (fp32 fast path)
+    const cx<T> *psi_dev = nullptr, *dt_dev = nullptr;
     float* asop_ws = nullptr;            // tensor-core path: A S expanded into the pass-1 operand image (hi | lo)
     const int Wn = cta_width(p.NG);
     const long long Mpad = (long long)ceil_div(M, Wn) * Wn;      // B^T is stored in Wn-wide column tiles
@@ -708,14 +733,31 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
         q.V = a.take<cx<T>>(GPn * nb); q.Res = a.take<cx<T>>(GPn * nb); q.S = a.take<cx<T>>(GPn * nb); q.VB = a.take<cx<T>>(GPn * nb);
         q.AS = a.take<cx<T>>((size_t)N * P * nb);
         q.dots = a.take<double>((size_t)nb * npc * 4);
-        bool sharedA = d->ld_A == 0, sharedB = d->ld_B == 0;
+        bool sharedA = d->ld_A == 0, sharedB = ldB_in == 0;
         q.AHA = a.take<cx<T>>((size_t)G * G * (sharedA ? 1 : nb)); q.ld_AHA = sharedA ? 0 : (long long)G * G;
         q.BBH = a.take<cx<T>>((size_t)P * P * (sharedB ? 1 : nb)); q.ld_BBH = sharedB ? 0 : (long long)P * P;
         if (!approx) {
             q.pA = a.take<cx<T>>((size_t)G * N * (sharedA ? 1 : nb)); q.ld_pA = sharedA ? 0 : (long long)G * N;
             q.BBHinv = q.BBH;   // inverted in place
         }
-        if (fast_xs && !use_tc) bt_ws = a.take<cx<T>>((size_t)P * Mpad * (sharedB ? 1 : nb));
+        if (fast_xs && !use_tc) bt_ws = a.take<cx<T>>((size_t)P * Mpad * (sharedB ? 1 : nb));    // (unused once the structured path is confirmed)
+        if (ps) {
+            b_ws = a.take<cx<T>>((size_t)P * M * (sharedB ? 1 : nb));
+            if (psi_shape) {
+                const int nE = ps->ld_Psi ? nb : 1;
+                pin.E = a.take<unsigned short>((size_t)nE * psi::NKG * (M + 8) * 8);
+                pin.scale = a.take<float>(nb);
+                pin.omask = a.take<unsigned short>((size_t)nb * M);
+                pin.QopS = a.take<unsigned char>((size_t)nb * ps->L * psi::QTAP);
+                pin.QopG = a.take<unsigned char>((size_t)nb * ps->L * psi::QTAP);
+                pin.T1p = reinterpret_cast<cx<float>*>(a.take<cx<T>>((size_t)nb * q.nmc * N * ps->L * psi::NT));
+                pin.XV = reinterpret_cast<cx<float>*>(a.take<cx<T>>(NM * nb));
+                pin.Gm = reinterpret_cast<cx<float>*>(a.take<cx<T>>(NM * nb));
+                pin.rr = a.take<double>((size_t)nb * ps->L);
+                pin.gg = a.take<double>((size_t)nb * q.nmc);
+                pin.bad = a.take<int>(1);
+            }
+        }
         if (use_tc) asop_ws = a.take<float>((size_t)nb * (P / 16) * (tc::Geo<16, TC_NST>::OP1 / 4));
         if (angles) q.smask = a.take<unsigned char>(GPn * nb);
         if (want_conv) {
@@ -730,9 +772,12 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
                 const cx<T>* s_subY = a.take<cx<T>>(d->ld_subY ? NM * nb : NM);
                 const T* s_omega = a.take<T>(d->ld_omega ? NM * nb : NM);
                 const cx<T>* s_A = a.take<cx<T>>((size_t)N * G * (d->ld_A ? nb : 1));
-                const cx<T>* s_B = a.take<cx<T>>((size_t)P * M * (d->ld_B ? nb : 1));
+                const cx<T>* s_B = ps ? nullptr : a.take<cx<T>>((size_t)P * M * (d->ld_B ? nb : 1));
+                const cx<T>* s_Psi = ps ? a.take<cx<T>>((size_t)ps->Nt * M * ps->L * (ps->ld_Psi ? nb : 1)) : nullptr;
+                const cx<T>* s_Dt = ps ? a.take<cx<T>>((size_t)ps->Nt * ps->Gt * (ps->ld_Dt ? nb : 1)) : nullptr;
                 const double *s_rho = a.take<double>(nb), *s_tauY = a.take<double>(nb), *s_tauS = a.take<double>(nb);
                 const int* s_indx = angles ? a.take<int>((size_t)d->n_indx * (d->ld_indx ? nb : 1)) : nullptr;
+                if (use) { psi_dev = s_Psi; dt_dev = s_Dt; }
                 if (use) { q.subY = s_subY; q.omega = s_omega; q.A = s_A; q.B = s_B; q.rho = s_rho; q.tauY = s_tauY; q.tauS = s_tauS; q.indx = s_indx; }
             }
             if (Y_) q.Yout = a.take<cx<T>>(NM * nb);
@@ -776,6 +821,12 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
     if (fast_xs && (rc = set_smem(h, k_xs_fast<T>, sm_fs))) return rc;
     if constexpr (std::is_same<T, float>::value) {
         if (use_tc && (rc = set_smem(h, tc::k_fused_tc<16, TC_NST>, tc::Geo<16, TC_NST>::SMEM))) return rc;
+        if (psi_shape) {
+            if ((rc = set_smem(h, psi::k_fused_psi, psi::SMEM))) return rc;
+            if ((rc = set_smem(h, psi::k_psi_g, psi::G_SMEM))) return rc;
+            if ((rc = set_smem(h, psi::k_psi_res, sizeof(psi::SmallSmem)))) return rc;
+            if ((rc = set_smem(h, psi::k_psi_step, sizeof(psi::SmallSmem)))) return rc;
+        }
     }
 
     JSTSP_CUDA(h, cudaMemsetAsync(h->d_flag, 0, sizeof(int), st));
@@ -788,7 +839,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
         Arena ar(h->ws, h->ws_bytes);
         AdmmP<T> q = p;
         layout(ar, chunk_trials, q);         // identical carve-up for every pass (the staging sets must not move)
-        q.ld_subY = d->ld_subY; q.ld_omega = d->ld_omega; q.ld_A = d->ld_A; q.ld_B = d->ld_B; q.ld_indx = d->ld_indx; q.ld_Y = d->ld_Y;
+        q.ld_subY = d->ld_subY; q.ld_omega = d->ld_omega; q.ld_A = d->ld_A; q.ld_B = ldB_in; q.ld_indx = d->ld_indx; q.ld_Y = d->ld_Y;
         if (host) {
             // inputs travel on the copy stream into staging set `pass & 1`; the solve of this pass waits for them, the copy
             // of pass k+2 into the same set waits for the solve of pass k
@@ -802,7 +853,11 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
             JSTSP_CUDA(h, up(q.subY, subY_, NM, d->ld_subY, esz));
             JSTSP_CUDA(h, up(q.omega, omega_, NM, d->ld_omega, sizeof(T)));
             JSTSP_CUDA(h, up(q.A, A_, (size_t)N * G, d->ld_A, esz));
-            JSTSP_CUDA(h, up(q.B, B_, (size_t)P * M, d->ld_B, esz));
+            if (!ps) JSTSP_CUDA(h, up(q.B, B_, (size_t)P * M, d->ld_B, esz));
+            else {
+                JSTSP_CUDA(h, up(psi_dev, ps->Psi, (size_t)ps->Nt * M * ps->L, ps->ld_Psi, esz));
+                JSTSP_CUDA(h, up(dt_dev, ps->Dt, (size_t)ps->Nt * ps->Gt, ps->ld_Dt, esz));
+            }
             JSTSP_CUDA(h, cudaMemcpyAsync(const_cast<double*>(q.rho), rho_ + b0, sizeof(double) * nb, cudaMemcpyHostToDevice, cs));
             JSTSP_CUDA(h, cudaMemcpyAsync(const_cast<double*>(q.tauY), tauY_ + b0, sizeof(double) * nb, cudaMemcpyHostToDevice, cs));
             JSTSP_CUDA(h, cudaMemcpyAsync(const_cast<double*>(q.tauS), tauS_ + b0, sizeof(double) * nb, cudaMemcpyHostToDevice, cs));
@@ -819,28 +874,72 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
             q.subY = (const cx<T>*)subY_ + (long long)b0 * d->ld_subY;
             q.omega = (const T*)omega_ + (long long)b0 * d->ld_omega;
             q.A = (const cx<T>*)A_ + (long long)b0 * d->ld_A;
-            q.B = (const cx<T>*)B_ + (long long)b0 * d->ld_B;
+            if (!ps) q.B = (const cx<T>*)B_ + (long long)b0 * d->ld_B;
             q.rho = rho_ + b0; q.tauY = tauY_ + b0; q.tauS = tauS_ + b0;
             if (angles) q.indx = indx_ + (long long)b0 * d->ld_indx;
             q.Yout = Y_ ? (cx<T>*)Y_ + (long long)b0 * d->ld_Y : nullptr;
         }
+        bool use_psi = false;
+        psi::Maps pmaps;
+        if (ps) {
+            const long long ldP = ps->ld_Psi ? (host ? (long long)ps->Nt * M * ps->L : ps->ld_Psi) : 0, ldD = ps->ld_Dt ? (host ? (long long)ps->Nt * ps->Gt : ps->ld_Dt) : 0;
+            const cx<T>* Pd = host ? psi_dev : (const cx<T>*)ps->Psi + (long long)b0 * ps->ld_Psi;
+            const cx<T>* Dd = host ? dt_dev : (const cx<T>*)ps->Dt + (long long)b0 * ps->ld_Dt;
+            if constexpr (std::is_same<T, float>::value) {
+                if (psi_shape) {
+                    // pack the pilots (bf16 image) and the mask (bits) and check their structure on the device
+                    pin.Psi = Pd; pin.ld_Psi = ldP; pin.Dt = Dd; pin.ld_Dt = ldD; pin.Nt = ps->Nt; pin.Gt = ps->Gt; pin.L = ps->L;
+                    const int nE = ps->ld_Psi ? nb : 1;
+                    JSTSP_CUDA(h, cudaMemsetAsync(pin.bad, 0, sizeof(int), st));
+                    { dim3 g(ceil_div(M + 8, 16), nE); JSTSP_LAUNCH(h, PK_SETUP, (psi::k_pack_psi<<<g, 256, 0, st>>>(pin, M))); }
+                    if (nE == 1 && nb > 1) JSTSP_LAUNCH(h, PK_SETUP, (psi::k_spread_scale<<<ceil_div(nb, 256), 256, 0, st>>>(pin.scale, nb)));
+                    { dim3 g(ceil_div(M, 256), nb); JSTSP_LAUNCH(h, PK_SETUP, (psi::k_pack_omega<<<g, 256, 0, st>>>(pin, q.omega, q.ld_omega, M))); }
+                    int bad_h = 0;
+                    JSTSP_CUDA(h, cudaMemcpyAsync(&bad_h, pin.bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+                    JSTSP_CUDA(h, cudaStreamSynchronize(st));
+                    use_psi = bad_h == 0;       // otherwise: no Toeplitz / bf16-exact pilots or a non-binary mask -> dense kernels on the materialised B
+                    if (use_psi) {
+                        bool ok = psi::make_map_e(pin.E, nE, M, &pmaps.E) && psi::make_map_state(q.X, (long long)NM, nb, M, &pmaps.X) &&
+                                  psi::make_map_state(q.V1, (long long)NM, nb, M, &pmaps.V1) && psi::make_map_state(q.V2, (long long)NM, nb, M, &pmaps.V2) &&
+                                  psi::make_map_state(pin.XV, (long long)NM, nb, M, &pmaps.XV) && psi::make_map_state(pin.Gm, (long long)NM, nb, M, &pmaps.G) &&
+                                  psi::make_map_state(q.subY, q.ld_subY, nb, M, &pmaps.SY);
+                        if (!ok) return fail(h, JSTSP_E_CUDA, "cuTensorMapEncodeTiled failed for the structured path");
+                    }
+                    h->last_path = use_psi ? 2 : 1;
+                }
+            }
+            if (!use_psi) {
+                // dense dictionary from its factors, operand of the dense kernels
+                const int nBd = ldB_in ? nb : 1;
+                const size_t smb = sizeof(cx<T>) * ((size_t)ps->Nt * ps->Gt + (size_t)ps->Nt * 64);
+                if ((rc = set_smem(h, psi::k_build_b<T>, smb))) return rc;
+                { dim3 g(ceil_div(M, 64), ps->L, nBd); JSTSP_LAUNCH(h, PK_SETUP, (psi::k_build_b<T><<<g, 256, smb, st>>>(Pd, ldP, Dd, ldD, b_ws, ldB_in ? (long long)P * M : 0, ps->Nt, ps->Gt, ps->L, M))); }
+                q.B = b_ws; q.ld_B = ldB_in ? (long long)P * M : 0;
+            }
+        }
+        q.nt1 = use_psi ? 1 : 0;
         // state = 0 (proposed_algorithm.m:8-12)
         JSTSP_CUDA(h, cudaMemsetAsync(q.X, 0, (size_t)((char*)(q.Xs + NM * nb) - (char*)q.X), st));   // X,V1,V2,C,Xs are adjacent
         JSTSP_CUDA(h, cudaMemsetAsync(q.gram, 0, sizeof(double) * (size_t)nb * q.nmc * 2 * N * N, st));
         JSTSP_CUDA(h, cudaMemsetAsync(q.V, 0, esz * GPn * nb, st));
         JSTSP_CUDA(h, cudaMemsetAsync(q.S, 0, esz * GPn * nb, st));
-        JSTSP_CUDA(h, cudaMemsetAsync(q.VB, 0, esz * GPn * nb, st));
+        if (!use_psi) JSTSP_CUDA(h, cudaMemsetAsync(q.VB, 0, esz * GPn * nb, st));
         if (angles) JSTSP_CUDA(h, cudaMemsetAsync(q.smask, 0, GPn * nb, st));
-        // one-off operators
-        const int nA = d->ld_A ? nb : 1, nB = d->ld_B ? nb : 1;
-        JSTSP_LAUNCH(h, PK_SETUP, (k_aha<T><<<nA, 256, 0, st>>>(q)));
-        { dim3 g(ceil_div(P, 64), ceil_div(P, 64), nB); JSTSP_LAUNCH(h, PK_SETUP, (k_bbh<T><<<g, 256, 0, st>>>(q))); }
-        const long long ld_Bt = d->ld_B ? (long long)P * Mpad : 0;
+        if constexpr (std::is_same<T, float>::value) {
+            if (use_psi) JSTSP_CUDA(h, cudaMemsetAsync(pin.XV, 0, esz * NM * nb, st));
+        }
+        // one-off operators (the structured path needs neither A^H A nor B B^H)
+        const int nA = d->ld_A ? nb : 1, nB = ldB_in ? nb : 1;
+        if (!use_psi) {
+            JSTSP_LAUNCH(h, PK_SETUP, (k_aha<T><<<nA, 256, 0, st>>>(q)));
+            dim3 g(ceil_div(P, 64), ceil_div(P, 64), nB); JSTSP_LAUNCH(h, PK_SETUP, (k_bbh<T><<<g, 256, 0, st>>>(q)));
+        }
+        const long long ld_Bt = ldB_in ? (long long)P * Mpad : 0;
         CUtensorMap mapB1, mapB2;
         if constexpr (std::is_same<T, float>::value) {
             if (use_tc && !tc::make_maps(q.B, q.ld_B, nB, P, M, &mapB1, &mapB2)) return fail(h, JSTSP_E_CUDA, "cuTensorMapEncodeTiled failed for the dictionary B");
         }
-        if (fast_xs && !use_tc) {
+        if (fast_xs && !use_tc && !use_psi) {
             dim3 g(ceil_div(P, 32), (unsigned)(Mpad / 32), nB);
             JSTSP_LAUNCH(h, PK_SETUP, (k_transpose_b<T><<<g, 256, 0, st>>>(q.B, q.ld_B, bt_ws, ld_Bt, P, M, Wn)));
         }
@@ -861,7 +960,11 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
             if (angles) { dim3 g(1, nb); JSTSP_LAUNCH(h, PK_OTHER, (k_mask_grow<T><<<g, 64, 0, st>>>(q))); }
             {
                 dim3 g(q.nmc, nb);
-                if (use_tc) {
+                if (use_psi) {
+                    if constexpr (std::is_same<T, float>::value)
+                        JSTSP_LAUNCH(h, PK_FUSED_PSI, (psi::k_fused_psi<<<g, tc::THREADS, psi::SMEM, st>>>(q, pmaps, pin)));
+                }
+                else if (use_tc) {
                     if constexpr (std::is_same<T, float>::value)
                         JSTSP_LAUNCH(h, PK_FUSED_TC, (tc::k_fused_tc<16, TC_NST><<<g, tc::THREADS, tc::Geo<16, TC_NST>::SMEM, st>>>(q, mapB1, mapB2, asop_ws, q.ld_B == 0 ? 1 : 0)));
                 }
@@ -883,14 +986,23 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
                     JSTSP_LAUNCH(h, PK_EIG, (k_svt_weights<T><<<nb, 128, sm_j, st>>>(qe)));
                 }
             }
-            if (fast_v) {
+            if (use_psi) {
+                // Res and the operand of G ; G = (A Res) B and |G|^2 ; alpha, V, S, XV and the operand of the next Xs
+                if constexpr (std::is_same<T, float>::value) {
+                    dim3 gs(pin.L, nb), gc(q.nmc, nb);
+                    JSTSP_LAUNCH(h, PK_PSI_AUX, (psi::k_psi_res<<<gs, 256, sizeof(psi::SmallSmem), st>>>(q, pin)));
+                    JSTSP_LAUNCH(h, PK_PSI_G, (psi::k_psi_g<<<gc, tc::THREADS, psi::G_SMEM, st>>>(q, pmaps, pin)));
+                    JSTSP_LAUNCH(h, PK_PSI_AUX, (psi::k_psi_step<<<gs, 256, sizeof(psi::SmallSmem), st>>>(q, pin, it + 1 < imax ? 1 : 0)));
+                }
+            } else if (fast_v) {
                 JSTSP_LAUNCH(h, PK_RES, (k_vstep_fast<T><<<nb, kThreads, sm_fv, st>>>(q)));
             } else {
                 { dim3 g(approx ? npc : ceil_div(P, PCr), nb); JSTSP_LAUNCH(h, PK_RES, (k_res<T, CB><<<g, kThreads, sm_res, st>>>(q))); }
                 if (approx) { dim3 g(npc, nb); JSTSP_LAUNCH(h, PK_Q, (k_q<T, CB><<<g, kThreads, sm_q, st>>>(q))); }
                 { dim3 g(ceil_div(P, kPV), nb); JSTSP_LAUNCH(h, PK_VUPD, (k_vupd<T><<<g, kThreads, sm_v, st>>>(q))); }
             }
-            if (use_tc) {
+            if (use_psi) {
+            } else if (use_tc) {
                 if constexpr (std::is_same<T, float>::value) {
                     // Xs = (A S) B of this iteration is formed by the NEXT fused launch; hand it A S as the operand image
                     if (it + 1 < imax) { dim3 g(4, nb); JSTSP_LAUNCH(h, PK_EXPAND, (tc::k_expand_as<16><<<g, 256, 0, st>>>(q.AS, asop_ws, P))); }
@@ -977,3 +1089,22 @@ extern "C" int jstsp_proposed_algorithm_angles(jstsp_handle* h, const jstsp_admm
     if (dtype == JSTSP_F64) return run_admm<double>(h, d, mem, subY, omega, indx_S, A, B, tau_Y, tau_S, rho, S, Y, conv, true);
     return fail(h, JSTSP_E_ARG, "unknown dtype");
 }
+
+extern "C" int jstsp_proposed_algorithm_psi(jstsp_handle* h, const jstsp_admm_desc* d, int dtype, int mem,
+                                            const void* subY, const void* omega, const int* indx_S, const void* A,
+                                            const void* Dt, long long ld_Dt, const void* Psi_bar, long long ld_Psi, int Nt, int L,
+                                            const double* tau_Y, const double* tau_S, const double* rho,
+                                            void* S, void* Y, void* conv) {
+    if (!h) return JSTSP_E_ARG;
+    if (!d) return fail(h, JSTSP_E_ARG, "NULL descriptor");
+    if (L <= 0 || Nt <= 0 || d->P % L != 0) return fail(h, JSTSP_E_ARG, "structured dictionary: P must be a multiple of L");
+    JSTSP_CUDA(h, cudaSetDevice(h->device));
+    PsiArgs ps{Dt, ld_Dt, Psi_bar, ld_Psi, Nt, d->P / L, L};
+    h->last_path = 1;
+    const bool angles = indx_S != nullptr;
+    if (dtype == JSTSP_F32) return run_admm<float>(h, d, mem, subY, omega, indx_S, A, nullptr, tau_Y, tau_S, rho, S, Y, conv, angles, &ps);
+    if (dtype == JSTSP_F64) return run_admm<double>(h, d, mem, subY, omega, indx_S, A, nullptr, tau_Y, tau_S, rho, S, Y, conv, angles, &ps);
+    return fail(h, JSTSP_E_ARG, "unknown dtype");
+}
+
+extern "C" int jstsp_last_path(const jstsp_handle* h) { return h ? h->last_path : 0; }

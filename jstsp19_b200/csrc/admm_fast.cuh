@@ -333,10 +333,11 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1) k_vstep_fast
     // V BBH is not recomputed: V_{i+1} = V_i + alpha Res_i  =>  V_{i+1} BBH = V_i BBH + alpha (Res_i BBH), and Res_i BBH is
     // formed below for the line search anyway (.m:47-50) - one pass over BBH per iteration instead of two.
     for (int t = threadIdx.x; t < G * P; t += kThreads) E[(size_t)(N + t / P) * pitch + (t % P)] = VBg[t];
-    const cx<T>* T1 = p.T1 + (size_t)b * p.nmc * N * P;
+    const int nt1 = p.nt1 ? p.nt1 : p.nmc;
+    const cx<T>* T1 = p.T1 + (size_t)b * nt1 * N * P;
     for (int t = threadIdx.x; t < N * P; t += kThreads) {
         T re = 0, im = 0;
-        for (int k = 0; k < p.nmc; ++k) { cx<T> v = T1[(size_t)k * N * P + t]; re += v.re; im += v.im; }
+        for (int k = 0; k < nt1; ++k) { cx<T> v = T1[(size_t)k * N * P + t]; re += v.re; im += v.im; }
         E[(size_t)(t / P) * pitch + (t % P)] = mk<T>(re, im);
     }
     __syncthreads();

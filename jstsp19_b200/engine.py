@@ -76,6 +76,41 @@ class AdmmEngine:
         self.h.check(rc)
         return S_out
 
+    def proposed_algorithm_psi(self, subY, Omega, A, Dt, Psi, imax, tau_Y, tau_S, rho, type="approximate", indx_S=None,
+                               S_out=None, Y_out=None):
+        """Same estimator with the dictionary given by its factors (jstsp_proposed_algorithm_psi):
+        Dt (b|1,Gt,Nt) and Psi_bar (b|1,L,M,Nt) in per-trial column-major storage; B = (I (x) Dt') Psi_bar is never an input."""
+        cd, rdt = _CD[self.precision], _RD[self.precision]
+        b, M, N = subY.shape
+        G = A.shape[-2]
+        Gt, Nt = Dt.shape[-2], Dt.shape[-1]
+        L = Psi.shape[-3]
+        P = L * Gt
+        for t, dt in ((subY, cd), (A, cd), (Dt, cd), (Psi, cd), (Omega, rdt), (tau_Y, torch.float64), (tau_S, torch.float64), (rho, torch.float64)):
+            if t.dtype != dt or not t.is_contiguous() or t.device != self.device:
+                raise ValueError("engine tensors must be contiguous, on the engine's device, and of the engine's precision")
+        if Psi.shape[-1] != Nt or Psi.shape[-2] != M:
+            raise ValueError("Psi_bar must be (b|1, L, M, Nt)")
+        if S_out is None:
+            S_out = torch.empty(b, P, G, dtype=cd, device=self.device)
+        d = AdmmDesc()
+        d.N, d.M, d.G, d.P, d.imax, d.batch = N, M, G, P, int(imax), b
+        d.type = _lib.APPROXIMATE if type == "approximate" else _lib.STD
+        d.ld_subY = N * M
+        d.ld_omega = N * M if Omega.shape[0] == b else 0
+        d.ld_A = N * G if A.shape[0] == b else 0
+        d.ld_S, d.ld_Y, d.ld_conv = G * P, N * M, 0
+        if indx_S is not None:
+            d.n_indx = indx_S.shape[-1]
+            d.ld_indx = indx_S.shape[-1] if indx_S.dim() == 2 and indx_S.shape[0] == b else 0
+        self._bind_stream()
+        rc = _lib.lib.jstsp_proposed_algorithm_psi(self.h.ptr, C.byref(d), _DT[self.precision], _lib.DEVICE, _p(subY), _p(Omega), _p(indx_S), _p(A),
+                                                   _p(Dt), Nt * Gt if (Dt.dim() == 3 and Dt.shape[0] == b and b > 1) else 0,
+                                                   _p(Psi), Nt * M * L if (Psi.dim() == 4 and Psi.shape[0] == b and b > 1) else 0, Nt, L,
+                                                   _p(tau_Y), _p(tau_S), _p(rho), _p(S_out), _p(Y_out), None)
+        self.h.check(rc)
+        return S_out
+
     @property
     def launches(self):
         return self.h.launches

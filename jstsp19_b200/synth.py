@@ -117,7 +117,9 @@ def build_from_draws(s: Shape, coef, u_r, u_t, noise_unit, sym_idx, mask_rank, s
     cm = lambda x: x.transpose(1, 2).contiguous().to(cdtype)           # per-trial column-major
     return dict(subY=cm(subY), Omega=Omega.transpose(1, 2).contiguous().to(rd), A=A.T.contiguous().to(cdtype)[None],
                 B=cm(B), Zbar=cm(Zbar), tau_Y=tau_Y.double().contiguous(), tau_Z=tau_Z.double().contiguous(),
-                rho=rho.double().contiguous(), H=H)
+                rho=rho.double().contiguous(), H=H,
+                # factors of B as the drivers hold them: Dt (1,Gt,Nt) and Psi_bar (b,L,M,Nt), per-trial column-major
+                Dt=Dt.T.contiguous().to(cdtype)[None], Psi=Psi.transpose(2, 3).contiguous().to(cdtype))
 
 
 def make_batch(s: Shape, batch, snr_db, seed, first_trial=0, device="cuda", cdtype=torch.complex64):

@@ -1,0 +1,122 @@
+"""GPU parity of jstsp_proposed_algorithm_psi: the estimator fed with the dictionary's factors (Dt, Psi_bar) as the
+reference's drivers hold them before they form B (plot_errorVSsnr.m:132-136), against the fp64 oracle that follows
+proposed_algorithm.m on the dense B built by those very lines.  Covers the Psi-domain tcgen05 kernel (path 2) and the
+materialised-B route taken for anything without the Toeplitz / 4-QAM structure (path 1)."""
+import numpy as np
+import pytest
+
+from oracle import estimators as est
+from oracle import fixtures as fx
+from oracle import system_model as sm
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"f64": dict(S=1e-9, nmse=1e-9), "f32": dict(S=2e-5, nmse=1e-4)}
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def _oracle(t, B=None, Imax=100, indx_S=None):
+    S0, Y0, _ = est.proposed_algorithm_structured(t["subY"], t["Omega"], t["A"], t["B"] if B is None else B, Imax, t["tau_Y"], t["tau_Z"],
+                                                   t["rho"], "approximate", want_conv=False, indx_S=indx_S)
+    return S0, Y0
+
+
+def _metric_trials():
+    return [fx.make_trial(fx.METRIC, snr, 100 + k) for k, snr in enumerate([-15.0, 0.0, 15.0])]
+
+
+def test_metric_shape_tensor_core_path():
+    """Nt=64, Nr=16, K=16, L=4, per-trial 4-QAM Toeplitz pilots: must take the Psi-domain tcgen05 kernel and match the oracle."""
+    import jstsp19_b200 as jb
+    from jstsp19_b200._lib import default_handle
+    trials = _metric_trials()
+    st = lambda k: np.stack([t[k] for t in trials])
+    S1, Y1 = jb.proposed_algorithm_psi(st("subY"), st("Omega"), st("A"), trials[0]["Dt"], st("Psi_bar"), 100,
+                                       [t["tau_Y"] for t in trials], [t["tau_Z"] for t in trials], [t["rho"] for t in trials],
+                                       "approximate", precision="f32", nargout=2)
+    assert default_handle().last_path == 2, "structured pilots did not reach the tensor-core kernel"
+    for k, t in enumerate(trials):
+        S0, Y0 = _oracle(t)
+        n0, n1 = est.nmse(S0, t["Zbar"]), est.nmse(S1[k].astype(np.complex128), t["Zbar"])
+        assert _rel(S1[k], S0) < TOL["f32"]["S"], (k, _rel(S1[k], S0))
+        assert _rel(Y1[k], Y0) < TOL["f32"]["S"], (k, _rel(Y1[k], Y0))
+        assert abs(n1 - n0) / n0 < TOL["f32"]["nmse"], (k, n0, n1)
+
+
+def test_metric_shape_shared_pilots_and_angles():
+    """One pilot matrix for all trials (ld_Psi = 0) + the growing support mask of proposed_algorithm_angles."""
+    import jstsp19_b200 as jb
+    from jstsp19_b200._lib import default_handle
+    t = fx.make_trial(fx.METRIC, 5.0, 31)
+    subY = np.stack([t["subY"], 0.5 * t["subY"]])
+    Om = np.stack([t["Omega"]] * 2)
+    ix = np.stack([t["indx_S"]] * 2)
+    S1 = jb.proposed_algorithm_psi(subY, Om, t["A"], t["Dt"], t["Psi_bar"], 40, [t["tau_Y"]] * 2, [t["tau_Z"]] * 2, [t["rho"]] * 2,
+                                   "approximate", ix, precision="f32", nargout=1)
+    assert default_handle().last_path == 2
+    for k in range(2):
+        tk = dict(t, subY=subY[k])
+        S0, _ = _oracle(tk, Imax=40, indx_S=t["indx_S"])
+        assert _rel(S1[k], S0) < TOL["f32"]["S"], (k, _rel(S1[k], S0))
+
+
+def test_unstructured_pilots_take_dense_route():
+    """Gaussian pilots (wideband_hybBF_comm_system_training.m:20-21 style, not exact in bf16) and a non-Toeplitz Psi_bar:
+    same entry point, dense kernels on the device-built B, same answer."""
+    import jstsp19_b200 as jb
+    from jstsp19_b200._lib import default_handle
+    t = fx.make_trial(fx.METRIC, 5.0, 41)
+    rng = np.random.default_rng(7)
+    for kind in ("gaussian", "not_toeplitz"):
+        if kind == "gaussian":
+            pil = (rng.standard_normal(t["pilots"].shape) + 1j * rng.standard_normal(t["pilots"].shape)) / np.sqrt(2.0)
+            Psi = sm.psi_bar_from_pilots(pil, fx.METRIC.M, fx.METRIC.L)
+        else:
+            Psi = t["Psi_bar"].copy()
+            Psi[5, 700, 2] = -Psi[5, 700, 2]
+        B = sm.dictionary_B(t["Dt"], Psi)
+        S1 = jb.proposed_algorithm_psi(t["subY"], t["Omega"], t["A"], t["Dt"], Psi, 30, t["tau_Y"], t["tau_Z"], t["rho"], "approximate",
+                                       precision="f32", nargout=1)
+        assert default_handle().last_path == 1, kind
+        S0, _ = _oracle(t, B=B, Imax=30)
+        assert _rel(S1, S0) < TOL["f32"]["S"], (kind, _rel(S1, S0))
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_default_shape_factors_equal_dense(precision):
+    """plot_errorVSsnr.m default sizes (Nt=4: outside the tensor-core kernel's shape) with diagnostics: factors == dense B."""
+    import jstsp19_b200 as jb
+    t = fx.make_trial(fx.CONFIG0, 5.0, 11)
+    args = (100, t["tau_Y"], t["tau_Z"], t["rho"], "approximate")
+    Sa, Ya, ca = jb.proposed_algorithm_psi(t["subY"], t["Omega"], t["A"], t["Dt"], t["Psi_bar"], *args, precision=precision)
+    Sb, Yb, cb = jb.proposed_algorithm(t["subY"], t["Omega"], t["A"], t["B"], *args, precision=precision)
+    tol = 1e-10 if precision == "f64" else 2e-5
+    assert _rel(Sa, Sb) < tol and _rel(Ya, Yb) < tol
+    S0, Y0 = _oracle(t)
+    assert _rel(Sa, S0) < TOL[precision]["S"]
+
+
+def test_device_engine_matches_host_call():
+    """Device-resident tensors through engine.AdmmEngine.proposed_algorithm_psi == the HOST-buffer call."""
+    import torch
+    import jstsp19_b200 as jb
+    from jstsp19_b200.engine import AdmmEngine
+    trials = _metric_trials()[:2]
+    st = lambda k: np.stack([t[k] for t in trials])
+    tY, tZ, rh = ([t[k] for t in trials] for k in ("tau_Y", "tau_Z", "rho"))
+    S_host = jb.proposed_algorithm_psi(st("subY"), st("Omega"), st("A"), trials[0]["Dt"], st("Psi_bar"), 25, tY, tZ, rh, "approximate",
+                                       precision="f32", nargout=1)
+    dev = torch.device("cuda", 0)
+    cm = lambda x: torch.from_numpy(np.ascontiguousarray(np.swapaxes(x, -1, -2))).to(dev)
+    eng = AdmmEngine(0, "f32")
+    Psi = torch.from_numpy(np.ascontiguousarray(np.moveaxis(st("Psi_bar"), (-3, -2, -1), (-1, -2, -3)))).to(torch.complex64).to(dev)
+    f64 = lambda v: torch.tensor(v, dtype=torch.float64, device=dev)
+    S_dev = eng.proposed_algorithm_psi(cm(st("subY")).to(torch.complex64), cm(st("Omega")).to(torch.float32), cm(st("A")).to(torch.complex64),
+                                       cm(trials[0]["Dt"]).to(torch.complex64)[None].contiguous(), Psi.contiguous(), 25, f64(tY), f64(tZ), f64(rh))
+    torch.cuda.synchronize()
+    assert eng.h.last_path == 2
+    S_dev = np.swapaxes(S_dev.cpu().numpy(), -1, -2)
+    assert _rel(S_dev, S_host) < 1e-6

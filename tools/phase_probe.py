@@ -19,11 +19,17 @@ eng = AdmmEngine(0, "f32")
 kid = int(os.environ.get("JSTSP_DBG_KERNEL", "0"))
 ncta = nb * 8
 buf = torch.zeros(ncta * 8, dtype=torch.int64, device=dev)
+psi = os.environ.get("PSI", "0") == "1"
+def solve():
+    if psi:
+        eng.proposed_algorithm_psi(data["subY"], data["Omega"], data["A"], data["Dt"], data["Psi"], 3, data["tau_Y"], data["tau_Z"], data["rho"])
+    else:
+        eng.proposed_algorithm(data["subY"], data["Omega"], data["A"], data["B"], 3, data["tau_Y"], data["tau_Z"], data["rho"])
 for it in range(2):
-    eng.proposed_algorithm(data["subY"], data["Omega"], data["A"], data["B"], 3, data["tau_Y"], data["tau_Z"], data["rho"])
+    solve()
 torch.cuda.synchronize()
 _lib.lib.jstsp_debug_buffer(eng.h.ptr, C.c_void_p(buf.data_ptr()))
-eng.proposed_algorithm(data["subY"], data["Omega"], data["A"], data["B"], 3, data["tau_Y"], data["tau_Z"], data["rho"])
+solve()
 torch.cuda.synchronize()
 _lib.lib.jstsp_debug_buffer(eng.h.ptr, None)
 t = buf.cpu().numpy().reshape(ncta, 8)
