@@ -63,8 +63,9 @@ constexpr int OFF_OP = TILE, OFF_S0 = OFF_OP + OPREG, OFF_S1 = OFF_S0 + SLOT, OF
 constexpr size_t SMEM = (size_t)OFF_BAR + BARS;
 static_assert(KOP <= OPREG && 2 * QSLOT <= OPREG && SLOT <= OPREG, "operand region too small");
 static_assert(OFF_OP % 1024 == 0 && OFF_S0 % 1024 == 0 && OFF_S1 % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte alignment");
-// G kernel: tile | two half-tap slots | output tile
-constexpr int G_OFF_OP = TILE, G_OFF_OUT = G_OFF_OP + 2 * QSLOT, G_OFF_BAR = G_OFF_OUT + SLOT;
+// G kernel: tile | four half-tap slots | output tile
+constexpr int G_NSLOT = 4;
+constexpr int G_OFF_OP = TILE, G_OFF_OUT = G_OFF_OP + G_NSLOT * QSLOT, G_OFF_BAR = G_OFF_OUT + SLOT;
 constexpr size_t G_SMEM = (size_t)G_OFF_BAR + BARS;
 static_assert(G_OFF_OUT % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte alignment");
 
@@ -219,51 +220,81 @@ __device__ __forceinline__ void put_q(unsigned char* img, int n, int k, float qr
     put(2 * n, 2 * k, qr); put(2 * n, 2 * k + 1, -qi);
     put(2 * n + 1, 2 * k, qi); put(2 * n + 1, 2 * k + 1, qr);
 }
-struct SmallSmem {
-    cx<float> D[NT * NT];        // Dt(:, 0..Gt-1)
+constexpr int DLD = NT + 2;      // padded leading dimension of Dt in shared memory: FWD reads (stride 2 * DLD) hit distinct banks, BWD float4 reads stay aligned
+struct __align__(16) SmallSmem {
+    cx<float> D[DLD * NT];       // Dt(:, 0..Gt-1), column g at D + DLD g
     cx<float> A[N * N];          // A, N x G (G <= N)
     cx<float> U[N * NT];         // ping
     cx<float> V[N * NT];         // pong
     double red[8];
 };
-// out[n + N g] = scale * sum_k in[n + N k] * (CONJ ? conj(D[g', k']) ...) - the two Dt rotations
-//   FWD:  out(n,g) = sum_k in(n,k) Dt(k,g)            (T1'_l Dt)
-//   BWD:  out(n,k) = sum_g in(n,g) conj(Dt(k,g))      ((A S_l) Dt')
+// The two Dt rotations, register-tiled 2 rows x 2 outputs per thread (256 threads = 8 row pairs x 32 output pairs):
+//   FWD:  out(n,g) = scale sum_k in(n,k) Dt(k,g)            (T1'_l Dt)
+//   BWD:  out(n,k) = scale sum_g in(n,g) conj(Dt(k,g))      ((A S_l) Dt')
+// in / out are N x 64 column-major (element (n,c) at [n + N c]); D is Dt, NT x Gt column-major.
 template <bool FWD>
 __device__ __forceinline__ void rotate(const cx<float>* __restrict__ D, const cx<float>* __restrict__ in, cx<float>* __restrict__ out, int Gt, float sc) {
-    const int n = threadIdx.x % N;
+    const int n0 = 2 * (threadIdx.x % 8), o0 = 2 * (threadIdx.x / 8);
     const int nout = FWD ? Gt : NT, nin = FWD ? NT : Gt;
-    for (int o = threadIdx.x / N; o < nout; o += 256 / N) {
-        float re = 0.f, im = 0.f;
-        for (int i = 0; i < nin; ++i) {
-            const cx<float> a = in[n + N * i];
-            const cx<float> d = FWD ? D[i + NT * o] : D[o + NT * i];
-            cmac<float>(re, im, a.re, a.im, d.re, FWD ? d.im : -d.im);
+    if (o0 >= nout) return;
+    const bool two = o0 + 1 < nout;
+    float r00 = 0.f, i00 = 0.f, r01 = 0.f, i01 = 0.f, r10 = 0.f, i10 = 0.f, r11 = 0.f, i11 = 0.f;     // [row][output]
+#pragma unroll 8
+    for (int i = 0; i < nin; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(in + n0 + N * i);                             // rows n0, n0+1 of column i
+        float d0r, d0i, d1r, d1i;
+        if (FWD) {
+            const cx<float> d0 = D[i + DLD * o0], d1 = D[i + DLD * (two ? o0 + 1 : o0)];
+            d0r = d0.re; d0i = d0.im; d1r = d1.re; d1i = d1.im;
+        } else {
+            const float4 d = *reinterpret_cast<const float4*>(D + o0 + DLD * i);                         // Dt(o0, i), Dt(o0+1, i)  (DLD is even)
+            d0r = d.x; d0i = -d.y; d1r = d.z; d1i = -d.w;
         }
-        out[n + N * o] = mk<float>(sc * re, sc * im);
+        cmac<float>(r00, i00, a.x, a.y, d0r, d0i); cmac<float>(r10, i10, a.z, a.w, d0r, d0i);
+        cmac<float>(r01, i01, a.x, a.y, d1r, d1i); cmac<float>(r11, i11, a.z, a.w, d1r, d1i);
     }
+    *reinterpret_cast<float4*>(out + n0 + N * o0) = make_float4(sc * r00, sc * i00, sc * r10, sc * i10);
+    if (two) *reinterpret_cast<float4*>(out + n0 + N * (o0 + 1)) = make_float4(sc * r01, sc * i01, sc * r11, sc * i11);
 }
-// out (R x cols) = (HERM ? A^H : A) * in, A is N x G column-major; in/out element (r, c) at [r + N c]
+// out (N x cols) = (HERM ? A^H : A) * in, A is N x G column-major (zero-padded to N x N); in/out element (r, c) at [r + N c];
+// rows of the result beyond the operator's row count are written as zeros.  Same 2 x 2 register tile.
 template <bool HERM>
 __device__ __forceinline__ void apply_a(const cx<float>* __restrict__ A, int G, const cx<float>* __restrict__ in, cx<float>* __restrict__ out, int cols) {
-    const int r = threadIdx.x % N;
-    const int nr = HERM ? G : N, ni = HERM ? N : G;
-    for (int c = threadIdx.x / N; c < cols; c += 256 / N) {
-        float re = 0.f, im = 0.f;
-        if (r < nr)
-            for (int i = 0; i < ni; ++i) {
-                const cx<float> a = HERM ? A[i + N * r] : A[r + N * i];
-                const cx<float> x = in[i + N * c];
-                cmac<float>(re, im, a.re, HERM ? -a.im : a.im, x.re, x.im);
-            }
-        out[r + N * c] = mk<float>(re, im);
+    const int r0 = 2 * (threadIdx.x % 8), c0 = 2 * (threadIdx.x / 8);
+    if (c0 >= cols) return;
+    const bool two = c0 + 1 < cols;
+    const int c1 = two ? c0 + 1 : c0;
+    const int ni = HERM ? N : G;
+    float r00 = 0.f, i00 = 0.f, r01 = 0.f, i01 = 0.f, r10 = 0.f, i10 = 0.f, r11 = 0.f, i11 = 0.f;     // [row][column]
+#pragma unroll 4
+    for (int i = 0; i < ni; ++i) {
+        const cx<float> x0 = in[i + N * c0], x1 = in[i + N * c1];
+        float a0r, a0i, a1r, a1i;
+        if (HERM) { const cx<float> a0 = A[i + N * r0], a1 = A[i + N * (r0 + 1)]; a0r = a0.re; a0i = -a0.im; a1r = a1.re; a1i = -a1.im; }
+        else { const float4 a = *reinterpret_cast<const float4*>(A + r0 + N * i); a0r = a.x; a0i = a.y; a1r = a.z; a1i = a.w; }
+        cmac<float>(r00, i00, a0r, a0i, x0.re, x0.im); cmac<float>(r10, i10, a1r, a1i, x0.re, x0.im);
+        cmac<float>(r01, i01, a0r, a0i, x1.re, x1.im); cmac<float>(r11, i11, a1r, a1i, x1.re, x1.im);
     }
+    *reinterpret_cast<float4*>(out + r0 + N * c0) = make_float4(r00, i00, r10, i10);
+    if (two) *reinterpret_cast<float4*>(out + r0 + N * c1) = make_float4(r01, i01, r11, i11);
 }
 __device__ __forceinline__ void load_small(SmallSmem& sm, const In& in, const AdmmP<float>& p, int b) {
     const cx<float>* D = in.Dt + (long long)b * in.ld_Dt;
     const cx<float>* A = p.A + (long long)b * p.ld_A;
-    for (int t = threadIdx.x; t < NT * in.Gt; t += 256) sm.D[t] = D[t];
+    for (int t = threadIdx.x; t < NT * in.Gt; t += 256) sm.D[(t % NT) + DLD * (t / NT)] = D[t];
     for (int t = threadIdx.x; t < N * N; t += 256) sm.A[t] = t < N * p.G ? A[t] : mk<float>(0.f, 0.f);
+}
+
+// sm.U (N x NT) -> operand image of one tap: assembled in shared memory (over Dt, which is no longer needed), written out coalesced
+__device__ __forceinline__ void write_image(SmallSmem& sm, unsigned char* __restrict__ gimg) {
+    static_assert(sizeof(sm.D) >= QTAP, "image does not fit over Dt");
+    unsigned char* img = reinterpret_cast<unsigned char*>(sm.D);
+    const int n = threadIdx.x % N;
+    for (int k = threadIdx.x / N; k < NT; k += 256 / N) { const cx<float> q = sm.U[n + N * k]; put_q(img, n, k, q.re, q.im); }
+    __syncthreads();
+    const uint4* src = reinterpret_cast<const uint4*>(img);
+    uint4* dst = reinterpret_cast<uint4*>(gimg);
+    for (int t = threadIdx.x; t < QTAP / 16; t += 256) dst[t] = src[t];
 }
 
 // Res_l = A' (scale T1'_l Dt) ; |Res_l|^2 ; operand image of G_l = (A Res_l) Dt'           (proposed_algorithm.m:47)
@@ -274,11 +305,15 @@ __global__ void __launch_bounds__(256) k_psi_res(AdmmP<float> p, In in) {
     const int b = blockIdx.y, l = blockIdx.x, Gt = in.Gt, Pp = in.L * NT, G = p.G;
     load_small(sm, in, p, b);
     const cx<float>* src = in.T1p + (size_t)b * p.nmc * N * Pp;
-    for (int t = threadIdx.x; t < N * NT; t += 256) {
-        const int n = t / NT, k = t % NT;
-        float re = 0.f, im = 0.f;
-        for (int c = 0; c < p.nmc; ++c) { const cx<float> v = src[(size_t)c * N * Pp + (size_t)n * Pp + l * NT + k]; re += v.re; im += v.im; }
-        sm.U[n + N * k] = mk<float>(re, im);
+    for (int t = threadIdx.x; t < N * NT / 2; t += 256) {        // two adjacent k per thread: 16-byte coalesced loads
+        const int n = t / (NT / 2), k = 2 * (t % (NT / 2));
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+        for (int c = 0; c < p.nmc; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(src + (size_t)c * N * Pp + (size_t)n * Pp + l * NT + k);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        sm.U[n + N * k] = mk<float>(acc.x, acc.y); sm.U[n + N * (k + 1)] = mk<float>(acc.z, acc.w);
     }
     __syncthreads();
     const float sc = in.scale[b];
@@ -300,9 +335,7 @@ __global__ void __launch_bounds__(256) k_psi_res(AdmmP<float> p, In in) {
     if (threadIdx.x == 0) { double s = 0; for (int w = 0; w < 8; ++w) s += sm.red[w]; in.rr[(size_t)b * in.L + l] = s; }
     rotate<false>(sm.D, sm.V, sm.U, Gt, sc);                     // scale (A Res_l) Dt'             N x NT
     __syncthreads();
-    unsigned char* img = in.QopG + ((size_t)b * in.L + l) * QTAP;
-    const int n = threadIdx.x % N;
-    for (int k = threadIdx.x / N; k < NT; k += 256 / N) { const cx<float> q = sm.U[n + N * k]; put_q(img, n, k, q.re, q.im); }
+    write_image(sm, in.QopG + ((size_t)b * in.L + l) * QTAP);
 }
 
 // alpha = |Res|^2 / |G|^2 ; V += alpha Res ; S = soft(V) [masked] ; XV += alpha G ; operand image of Xs = (A S) B
@@ -313,11 +346,12 @@ __global__ void __launch_bounds__(256) k_psi_step(AdmmP<float> p, In in, int mak
     __shared__ float s_alpha;
     const int b = blockIdx.y, l = blockIdx.x, Gt = in.Gt, G = p.G, L = in.L;
     if (make_q) load_small(sm, in, p, b);
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {                                       // alpha = res'res / (res' R res)  (.m:48)
         double a = 0, c = 0;
-        for (int i = 0; i < L; ++i) a += in.rr[(size_t)b * L + i];
-        for (int i = 0; i < p.nmc; ++i) c += in.gg[(size_t)b * p.nmc + i];
-        s_alpha = (float)(a / c);                                 // alpha = res'res / (res' R res)  (.m:48)
+        for (int i = threadIdx.x; i < L; i += 32) a += in.rr[(size_t)b * L + i];
+        for (int i = threadIdx.x; i < p.nmc; i += 32) c += in.gg[(size_t)b * p.nmc + i];
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); c += __shfl_down_sync(0xffffffffu, c, o); }
+        if (threadIdx.x == 0) s_alpha = (float)(a / c);
     }
     __syncthreads();
     const float alpha = s_alpha;
@@ -353,27 +387,27 @@ __global__ void __launch_bounds__(256) k_psi_step(AdmmP<float> p, In in, int mak
     __syncthreads();
     rotate<false>(sm.D, sm.V, sm.U, Gt, in.scale[b]);            // scale (A S_l) Dt'               N x NT
     __syncthreads();
-    unsigned char* img = in.QopS + ((size_t)b * L + l) * QTAP;
-    const int n = threadIdx.x % N;
-    for (int k = threadIdx.x / N; k < NT; k += 256 / N) { const cx<float> q = sm.U[n + N * k]; put_q(img, n, k, q.re, q.im); }
+    write_image(sm, in.QopS + ((size_t)b * L + l) * QTAP);
 }
 
 // ---- shared pieces of the two tensor-core kernels ---------------------------------------------------------------------------
 // producer: stream the operand image of `taps` taps in half-tap slots
+template <int NSLOT>
 __device__ __forceinline__ void stream_q(const unsigned char* img, unsigned char* slots, uint64_t* q_full, uint64_t* q_empty, int taps) {
     for (int i = 0; i < 2 * taps; ++i) {
-        const int slot = i & 1;
-        if (i >= 2) mbar_wait(&q_empty[slot], ((i >> 1) - 1) & 1);
+        const int slot = i % NSLOT;
+        if (i >= NSLOT) mbar_wait(&q_empty[slot], ((i / NSLOT) - 1) & 1);
         mbar_expect_tx(&q_full[slot], QSLOT);
         tma_bulk_g2s(slots + slot * QSLOT, img + (size_t)i * QSLOT, QSLOT, &q_full[slot]);
     }
 }
 // MMA thread: D[l & 1][m][(split,n,c)] += e(chunk - l)^T Q'_l^T for l < taps
+template <int NSLOT>
 __device__ __forceinline__ void issue_pass1(uint32_t tile_a, uint32_t slots_a, const uint32_t (&D)[2], uint64_t* q_full, uint64_t* q_empty, int taps, int L) {
     constexpr uint32_t id1 = instr_desc_bf16(128, NS, 0);
     for (int i = 0; i < 2 * taps; ++i) {
-        const int slot = i & 1, l = i >> 1, hf = i & 1;
-        mbar_wait(&q_full[slot], (i >> 1) & 1);
+        const int slot = i % NSLOT, l = i >> 1, hf = i & 1;
+        mbar_wait(&q_full[slot], (i / NSLOT) & 1);
         tc::tc_fence_after();
         const uint32_t a0 = tile_a + (uint32_t)(L - 1 - l) * 16, b0 = slots_a + slot * QSLOT;
 #pragma unroll
@@ -410,14 +444,14 @@ __global__ void __launch_bounds__(THREADS, 2) k_psi_g(AdmmP<float> p, const __gr
     unsigned char* slots = smem + G_OFF_OP;
     unsigned char* outt = smem + G_OFF_OUT;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_OFF_BAR);
-    uint64_t *tile_full = bars, *q_full = bars + 1, *q_empty = bars + 3, *d1_full = bars + 5;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
-    double* red = reinterpret_cast<double*>(bars + 8);
+    uint64_t *tile_full = bars, *q_full = bars + 1, *q_empty = bars + 1 + G_NSLOT, *d1_full = bars + 1 + 2 * G_NSLOT;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 + 2 * G_NSLOT);
+    double* red = reinterpret_cast<double*>(bars + 4 + 2 * G_NSLOT);
     const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
     const int b = blockIdx.y, chunk = blockIdx.x, c0 = chunk * MC, L = in.L;
     if (tid == 0) {
         mbar_init(tile_full, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
+        for (int s = 0; s < G_NSLOT; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
         mbar_init(d1_full, 1);
         mbar_fence_init();
     }
@@ -434,13 +468,13 @@ __global__ void __launch_bounds__(THREADS, 2) k_psi_g(AdmmP<float> p, const __gr
         if (lane == 0) {
             mbar_expect_tx(tile_full, TILE);
             tc::tma_4d(tile, &maps.E, 0, c0, 0, in.ld_Psi ? b : 0, tile_full);
-            stream_q(in.QopG + (size_t)b * L * QTAP, slots, q_full, q_empty, L);
+            stream_q<G_NSLOT>(in.QopG + (size_t)b * L * QTAP, slots, q_full, q_empty, L);
         }
         __syncwarp();
     } else if (warp == NWW + 1) {
         if (lane == 0) {
             mbar_wait(tile_full, 0);
-            issue_pass1(smem_u32(tile), smem_u32(slots), D, q_full, q_empty, L, L);
+            issue_pass1<G_NSLOT>(smem_u32(tile), smem_u32(slots), D, q_full, q_empty, L, L);
             tc::umma_commit(d1_full);
         }
         __syncwarp();
@@ -525,7 +559,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_fused_psi(AdmmP<float> p, const 
                 mbar_expect_tx(&ld_full[2], SLOT);
                 tc::tma_3d(opnd, &maps.XV, 0, c0, b, &ld_full[2]);
             }
-            stream_q(in.QopS + (size_t)b * L * QTAP, opnd, q_full, q_empty, S1t);
+            stream_q<2>(in.QopS + (size_t)b * L * QTAP, opnd, q_full, q_empty, S1t);
         }
         __syncwarp();
     } else if (warp == NWW + 1) {
@@ -534,7 +568,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_fused_psi(AdmmP<float> p, const 
             constexpr uint32_t id2 = instr_desc_bf16(128, NS, 1);
             const uint32_t tile_a = smem_u32(tile), op_a = smem_u32(opnd);
             mbar_wait(tile_full, 0);
-            issue_pass1(tile_a, op_a, D, q_full, q_empty, S1t, L);
+            issue_pass1<2>(tile_a, op_a, D, q_full, q_empty, S1t, L);
             if (S1t > 0) tc::umma_commit(d1_full);
             mbar_wait(kop_ready, 0);                         // the workers have drained D and written the K operand
             tc::tc_fence_after();

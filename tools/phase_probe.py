@@ -42,7 +42,7 @@ if kid in (4, 5, 6):
         v = t[:, i + 1].astype(np.float64)
         print(f"  {n:26s} {np.median(v):10.0f} {v.mean():10.0f} {np.percentile(v, 90):10.0f}")
     sys.exit(0)
-names = {3: ["pass-1 rewrites", "wait D1 + tmem ld", "element-wise", "pass-2 rewrites+epi", "last epilogue", "gram"], 0: ["init+ring zero", "Z staging", "W Z + element-wise", "T1 main loop", "gram"], 2: ["init+ring zero", "AS staging", "main loop", "epilogue"]}[kid]
+names = {3: ["X,V1 tiles, Z, W Z, pass-1 wait", "V2,subY,XV tiles, update, K operand", "pass-2 epilogues", "V2 store + gram"] if psi else ["pass-1 rewrites", "wait D1 + tmem ld", "element-wise", "pass-2 rewrites+epi", "last epilogue", "gram"], 0: ["init+ring zero", "Z staging", "W Z + element-wise", "T1 main loop", "gram"], 2: ["init+ring zero", "AS staging", "main loop", "epilogue"]}[kid]
 d = np.diff(t[:, : len(names) + 1], axis=1).astype(np.float64)
 print(f"kernel {kid}: {len(t)} CTAs, clock cycles per phase (median / mean / p90)")
 for i, n in enumerate(names):
