@@ -755,7 +755,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
                 pin.Gm = reinterpret_cast<cx<float>*>(a.take<cx<T>>(NM * nb));
                 pin.rr = a.take<double>((size_t)nb * ps->L);
                 pin.gg = a.take<double>((size_t)nb * q.nmc);
-                pin.bad = a.take<int>(1);
+                pin.bad = a.take<int>(2);
             }
         }
         if (use_tc) asop_ws = a.take<float>((size_t)nb * (P / 16) * (tc::Geo<16, TC_NST>::OP1 / 4));
@@ -890,14 +890,18 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
                     // pack the pilots (bf16 image) and the mask (bits) and check their structure on the device
                     pin.Psi = Pd; pin.ld_Psi = ldP; pin.Dt = Dd; pin.ld_Dt = ldD; pin.Nt = ps->Nt; pin.Gt = ps->Gt; pin.L = ps->L;
                     const int nE = ps->ld_Psi ? nb : 1;
-                    JSTSP_CUDA(h, cudaMemsetAsync(pin.bad, 0, sizeof(int), st));
+                    JSTSP_CUDA(h, cudaMemsetAsync(pin.bad, 0, 2 * sizeof(int), st));
                     { dim3 g(ceil_div(M + 8, 16), nE); JSTSP_LAUNCH(h, PK_SETUP, (psi::k_pack_psi<<<g, 256, 0, st>>>(pin, M))); }
                     if (nE == 1 && nb > 1) JSTSP_LAUNCH(h, PK_SETUP, (psi::k_spread_scale<<<ceil_div(nb, 256), 256, 0, st>>>(pin.scale, nb)));
                     { dim3 g(ceil_div(M, 256), nb); JSTSP_LAUNCH(h, PK_SETUP, (psi::k_pack_omega<<<g, 256, 0, st>>>(pin, q.omega, q.ld_omega, M))); }
-                    int bad_h = 0;
-                    JSTSP_CUDA(h, cudaMemcpyAsync(&bad_h, pin.bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+                    const bool dft_shape = ps->Gt == psi::NT && getenv("JSTSP_PSI_NOFFT") == nullptr;
+                    if (dft_shape) JSTSP_LAUNCH(h, PK_SETUP, (psi::k_check_dt<<<ps->ld_Dt ? nb : 1, 256, 0, st>>>(pin)));
+                    int bad_h[2] = {0, 0};
+                    JSTSP_CUDA(h, cudaMemcpyAsync(bad_h, pin.bad, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
                     JSTSP_CUDA(h, cudaStreamSynchronize(st));
-                    use_psi = bad_h == 0;       // otherwise: no Toeplitz / bf16-exact pilots or a non-binary mask -> dense kernels on the materialised B
+                    pin.t1_red = getenv("JSTSP_PSI_T1RED") ? atoi(getenv("JSTSP_PSI_T1RED")) : 0;
+                    pin.dft = dft_shape && bad_h[1] == 0;      // unitary DFT grid: the Dt rotations run as FFTs
+                    use_psi = bad_h[0] == 0;       // otherwise: no Toeplitz / bf16-exact pilots or a non-binary mask -> dense kernels on the materialised B
                     if (use_psi) {
                         bool ok = psi::make_map_e(pin.E, nE, M, &pmaps.E) && psi::make_map_state(q.X, (long long)NM, nb, M, &pmaps.X) &&
                                   psi::make_map_state(q.V1, (long long)NM, nb, M, &pmaps.V1) && psi::make_map_state(q.V2, (long long)NM, nb, M, &pmaps.V2) &&
@@ -926,7 +930,10 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
         if (!use_psi) JSTSP_CUDA(h, cudaMemsetAsync(q.VB, 0, esz * GPn * nb, st));
         if (angles) JSTSP_CUDA(h, cudaMemsetAsync(q.smask, 0, GPn * nb, st));
         if constexpr (std::is_same<T, float>::value) {
-            if (use_psi) JSTSP_CUDA(h, cudaMemsetAsync(pin.XV, 0, esz * NM * nb, st));
+            if (use_psi) {
+                JSTSP_CUDA(h, cudaMemsetAsync(pin.XV, 0, esz * NM * nb, st));
+                JSTSP_CUDA(h, cudaMemsetAsync(pin.T1p, 0, esz * (size_t)nb * N * pin.L * psi::NT, st));
+            }
         }
         // one-off operators (the structured path needs neither A^H A nor B B^H)
         const int nA = d->ld_A ? nb : 1, nB = ldB_in ? nb : 1;

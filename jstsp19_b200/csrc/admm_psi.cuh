@@ -116,12 +116,14 @@ struct In {                      // the structured dictionary of one pass (devic
     unsigned short* omask;       // [b][M] bit n = Omega(n, m) != 0
     unsigned char* QopS;         // [b][L][QTAP] pass-1 operand image of Q_S = scale (A S)(I (x) Dt')
     unsigned char* QopG;         // [b][L][QTAP] same for (A Res)
-    cx<float>* T1p;              // [b][nmc][N][L*Nt] partial (K - XV) Psi^H
+    cx<float>* T1p;              // [b][N][L*Nt] (K - XV) Psi^H, accumulated over the chunks of an iteration
     cx<float>* XV;               // [b][M][N] A V B
     cx<float>* Gm;               // [b][M][N] G = (A Res) B of the current iteration
     double* rr;                  // [b][L]   |Res_l|^2
     double* gg;                  // [b][nmc] |G(:,chunk)|^2
-    int* bad;                    // number of structure violations seen by the packing kernels
+    int* bad;                    // [0] structure violations seen by the packing kernels, [1] entries of Dt that differ from the unitary 64-point DFT
+    int t1_red;                  // 1: T1' is accumulated over chunks by red.global.add into [b][N][L*Nt]; 0: per-chunk partials [b][nmc][N][L*Nt]
+    int dft;                     // Dt is the unitary DFT grid of wideband_mmwave_channel.m:9-10 with Gt = Nt = 64: rotations run as radix-4 FFTs
 };
 struct Maps { CUtensorMap E, X, V1, V2, XV, G, SY; };
 
@@ -226,6 +228,7 @@ struct __align__(16) SmallSmem {
     cx<float> A[N * N];          // A, N x G (G <= N)
     cx<float> U[N * NT];         // ping
     cx<float> V[N * NT];         // pong
+    cx<float> tw[NT];            // exp(-2 pi j t / 64)
     double red[8];
 };
 // The two Dt rotations, register-tiled 2 rows x 2 outputs per thread (256 threads = 8 row pairs x 32 output pairs):
@@ -278,10 +281,62 @@ __device__ __forceinline__ void apply_a(const cx<float>* __restrict__ A, int G, 
     *reinterpret_cast<float4*>(out + r0 + N * c0) = make_float4(r00, i00, r10, i10);
     if (two) *reinterpret_cast<float4*>(out + r0 + N * c1) = make_float4(r01, i01, r11, i11);
 }
+
+// Dt == exp(-2 pi j k g / 64) / 8 ?  (Dr/Dt of wideband_mmwave_channel.m:9-10 with Gt = Mt = 64).  grid nDt, block 256
+__global__ void __launch_bounds__(256) k_check_dt(In in) {
+    const cx<float>* D = in.Dt + (long long)blockIdx.x * in.ld_Dt;
+    int nbad = 0;
+    for (int t = threadIdx.x; t < NT * NT; t += 256) {
+        const int k = t % NT, g = t / NT;
+        double sn, cs;
+        sincospi(-2.0 * (double)((k * g) % NT) / NT, &sn, &cs);
+        const cx<float> d = D[t];
+        if (fabs((double)d.re - 0.125 * cs) > 1e-7 || fabs((double)d.im - 0.125 * sn) > 1e-7) ++nbad;
+    }
+    if (nbad) atomicAdd(in.bad + 1, nbad);
+}
+// 64-point FFT of the N rows of `in` (element (n,k) at [n + N k]) into `out`, scaled; INV: exp(+...) kernel.  256 threads, radix-4 DIF:
+// one butterfly per thread and stage, digit-reversed positions resolved by the last stage's stores.  `in` is used as scratch.
+template <bool INV>
+__device__ __forceinline__ void fft64(cx<float>* __restrict__ in, cx<float>* __restrict__ out, const cx<float>* __restrict__ tw, float scale) {
+    const int n = threadIdx.x % N, j = threadIdx.x / N;          // j = 0..15
+    auto twid = [&](int t) { cx<float> w = tw[t]; if (INV) w.im = -w.im; return w; };
+    auto bfly = [&](cx<float> x0, cx<float> x1, cx<float> x2, cx<float> x3, cx<float> (&a)[4]) {
+        const float s02r = x0.re + x2.re, s02i = x0.im + x2.im, d02r = x0.re - x2.re, d02i = x0.im - x2.im;
+        const float s13r = x1.re + x3.re, s13i = x1.im + x3.im, d13r = x1.re - x3.re, d13i = x1.im - x3.im;
+        a[0] = mk<float>(s02r + s13r, s02i + s13i);
+        a[2] = mk<float>(s02r - s13r, s02i - s13i);
+        // forward: a1 = d02 - j d13, a3 = d02 + j d13 ; inverse: the other way round      (-j (r + j i) = i - j r)
+        const cx<float> m = mk<float>(d02r + d13i, d02i - d13r), q = mk<float>(d02r - d13i, d02i + d13r);
+        a[1] = INV ? q : m; a[3] = INV ? m : q;
+    };
+    cx<float> a[4];
+    // stage 0: length 64, i = j
+    bfly(in[n + N * j], in[n + N * (j + 16)], in[n + N * (j + 32)], in[n + N * (j + 48)], a);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) in[n + N * (j + 16 * q)] = q ? a[q] * twid(q * j) : a[q];
+    __syncthreads();
+    {   // stage 1: length 16, group j / 4, i = j % 4
+        const int base = 16 * (j / 4), i = j % 4;
+        cx<float> x0 = in[n + N * (base + i)], x1 = in[n + N * (base + i + 4)], x2 = in[n + N * (base + i + 8)], x3 = in[n + N * (base + i + 12)];
+        bfly(x0, x1, x2, x3, a);
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) in[n + N * (base + i + 4 * q)] = q ? a[q] * twid(4 * q * i) : a[q];
+    }
+    __syncthreads();
+    {   // stage 2: length 4, group j; position 4 j + q holds output index rev4(4 j + q) = 16 q + 4 (j % 4) + j / 4
+        bfly(in[n + N * (4 * j)], in[n + N * (4 * j + 1)], in[n + N * (4 * j + 2)], in[n + N * (4 * j + 3)], a);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) out[n + N * (16 * q + 4 * (j % 4) + j / 4)] = mk<float>(scale * a[q].re, scale * a[q].im);
+    }
+}
 __device__ __forceinline__ void load_small(SmallSmem& sm, const In& in, const AdmmP<float>& p, int b) {
     const cx<float>* D = in.Dt + (long long)b * in.ld_Dt;
     const cx<float>* A = p.A + (long long)b * p.ld_A;
-    for (int t = threadIdx.x; t < NT * in.Gt; t += 256) sm.D[(t % NT) + DLD * (t / NT)] = D[t];
+    if (in.dft) { if (threadIdx.x < NT) { float sn, cs; sincospif(-2.0f * (float)threadIdx.x / NT, &sn, &cs); sm.tw[threadIdx.x] = mk<float>(cs, sn); } }
+    else for (int t = threadIdx.x; t < NT * in.Gt; t += 256) sm.D[(t % NT) + DLD * (t / NT)] = D[t];
     for (int t = threadIdx.x; t < N * N; t += 256) sm.A[t] = t < N * p.G ? A[t] : mk<float>(0.f, 0.f);
 }
 
@@ -304,36 +359,69 @@ __global__ void __launch_bounds__(256) k_psi_res(AdmmP<float> p, In in) {
     SmallSmem& sm = *reinterpret_cast<SmallSmem*>(sm_raw);
     const int b = blockIdx.y, l = blockIdx.x, Gt = in.Gt, Pp = in.L * NT, G = p.G;
     load_small(sm, in, p, b);
-    const cx<float>* src = in.T1p + (size_t)b * p.nmc * N * Pp;
-    for (int t = threadIdx.x; t < N * NT / 2; t += 256) {        // two adjacent k per thread: 16-byte coalesced loads
-        const int n = t / (NT / 2), k = 2 * (t % (NT / 2));
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-        for (int c = 0; c < p.nmc; ++c) {
-            const float4 v = *reinterpret_cast<const float4*>(src + (size_t)c * N * Pp + (size_t)n * Pp + l * NT + k);
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    if (in.t1_red) {
+        cx<float>* src = in.T1p + (size_t)b * N * Pp;
+        for (int t = threadIdx.x; t < N * NT / 2; t += 256) {    // two adjacent k per thread: 16-byte accesses; the accumulator is handed back zeroed
+            const int n = t / (NT / 2), k = 2 * (t % (NT / 2));
+            float4* q = reinterpret_cast<float4*>(src + (size_t)n * Pp + l * NT + k);
+            const float4 v = *q;
+            *q = make_float4(0.f, 0.f, 0.f, 0.f);
+            sm.U[n + N * k] = mk<float>(v.x, v.y); sm.U[n + N * (k + 1)] = mk<float>(v.z, v.w);
         }
-        sm.U[n + N * k] = mk<float>(acc.x, acc.y); sm.U[n + N * (k + 1)] = mk<float>(acc.z, acc.w);
+    } else {
+        const cx<float>* src = in.T1p + (size_t)b * p.nmc * N * Pp;
+        for (int t = threadIdx.x; t < N * NT / 2; t += 256) {
+            const int n = t / (NT / 2), k = 2 * (t % (NT / 2));
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+            for (int c = 0; c < p.nmc; ++c) {
+                const float4 v = *reinterpret_cast<const float4*>(src + (size_t)c * N * Pp + (size_t)n * Pp + l * NT + k);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            sm.U[n + N * k] = mk<float>(acc.x, acc.y); sm.U[n + N * (k + 1)] = mk<float>(acc.z, acc.w);
+        }
     }
     __syncthreads();
     const float sc = in.scale[b];
-    rotate<true>(sm.D, sm.U, sm.V, Gt, sc);                      // T1_l = scale T1'_l Dt           N x Gt
-    __syncthreads();
-    apply_a<true>(sm.A, G, sm.V, sm.U, Gt);                      // Res_l = A' T1_l                 G x Gt (rows >= G zero)
-    __syncthreads();
     cx<float>* Res = p.Res + (size_t)b * G * p.P + (size_t)G * Gt * l;
     double rr = 0.0;
-    for (int t = threadIdx.x; t < N * Gt; t += 256) {
-        const int r = t % N, c = t / N;
-        const cx<float> v = sm.U[t];
-        if (r < G) { Res[r + (size_t)G * c] = v; rr += (double)v.re * v.re + (double)v.im * v.im; }
+    if (in.dft) {
+        // Dt is unitary: Res_l = (A' T1'_l) Dt (one FFT) and (A Res_l) Dt' = A A' T1'_l (no rotation at all)
+        apply_a<true>(sm.A, G, sm.U, sm.V, NT);                  // A' T1'_l                        G x NT (rows >= G zero)
+        __syncthreads();
+        apply_a<false>(sm.A, G, sm.V, sm.U, NT);                 // A A' T1'_l                      N x NT
+        __syncthreads();
+        for (int t = threadIdx.x; t < N * NT; t += 256) { cx<float> v = sm.U[t]; sm.U[t] = mk<float>(sc * sc * v.re, sc * sc * v.im); }
+        // (write_image below reads sm.U after its own barrier; the FFT works on sm.V and leaves Res in sm.D's first 8 KiB)
+        cx<float>* R = sm.D;
+        fft64<false>(sm.V, R, sm.tw, 0.125f * sc);
+        __syncthreads();
+        for (int t = threadIdx.x; t < N * Gt; t += 256) {
+            const int r = t % N, c = t / N;
+            const cx<float> v = R[t];
+            if (r < G) { Res[r + (size_t)G * c] = v; rr += (double)v.re * v.re + (double)v.im * v.im; }
+        }
+        for (int o = 16; o > 0; o >>= 1) rr += __shfl_down_sync(0xffffffffu, rr, o);
+        if (threadIdx.x % 32 == 0) sm.red[threadIdx.x / 32] = rr;
+        __syncthreads();
+        if (threadIdx.x == 0) { double s = 0; for (int w = 0; w < 8; ++w) s += sm.red[w]; in.rr[(size_t)b * in.L + l] = s; }
+    } else {
+        rotate<true>(sm.D, sm.U, sm.V, Gt, sc);                  // T1_l = scale T1'_l Dt           N x Gt
+        __syncthreads();
+        apply_a<true>(sm.A, G, sm.V, sm.U, Gt);                  // Res_l = A' T1_l                 G x Gt (rows >= G zero)
+        __syncthreads();
+        for (int t = threadIdx.x; t < N * Gt; t += 256) {
+            const int r = t % N, c = t / N;
+            const cx<float> v = sm.U[t];
+            if (r < G) { Res[r + (size_t)G * c] = v; rr += (double)v.re * v.re + (double)v.im * v.im; }
+        }
+        for (int o = 16; o > 0; o >>= 1) rr += __shfl_down_sync(0xffffffffu, rr, o);
+        if (threadIdx.x % 32 == 0) sm.red[threadIdx.x / 32] = rr;
+        apply_a<false>(sm.A, G, sm.U, sm.V, Gt);                 // A Res_l                         N x Gt
+        __syncthreads();
+        if (threadIdx.x == 0) { double s = 0; for (int w = 0; w < 8; ++w) s += sm.red[w]; in.rr[(size_t)b * in.L + l] = s; }
+        rotate<false>(sm.D, sm.V, sm.U, Gt, sc);                 // scale (A Res_l) Dt'             N x NT
     }
-    for (int o = 16; o > 0; o >>= 1) rr += __shfl_down_sync(0xffffffffu, rr, o);
-    if (threadIdx.x % 32 == 0) sm.red[threadIdx.x / 32] = rr;
-    apply_a<false>(sm.A, G, sm.U, sm.V, Gt);                     // A Res_l                         N x Gt
-    __syncthreads();
-    if (threadIdx.x == 0) { double s = 0; for (int w = 0; w < 8; ++w) s += sm.red[w]; in.rr[(size_t)b * in.L + l] = s; }
-    rotate<false>(sm.D, sm.V, sm.U, Gt, sc);                     // scale (A Res_l) Dt'             N x NT
     __syncthreads();
     write_image(sm, in.QopG + ((size_t)b * in.L + l) * QTAP);
 }
@@ -370,14 +458,21 @@ __global__ void __launch_bounds__(256) k_psi_step(AdmmP<float> p, In in, int mak
         V[t] = v; S[t] = s;
         if (make_q) sm.U[(t % G) + N * (t / G)] = s;
     }
-    {   // XV += alpha G on this tap's share of the columns
+    {   // XV += alpha G on this tap's share of the columns, four independent 16-byte accesses in flight per thread
         const int M = p.M, per = (M + L - 1) / L, m0 = l * per, m1 = (m0 + per) < M ? (m0 + per) : M;
         float4* xv = reinterpret_cast<float4*>(in.XV + (size_t)b * N * M);
         const float4* g = reinterpret_cast<const float4*>(in.Gm + (size_t)b * N * M);
-        for (int t = m0 * (N / 2) + threadIdx.x; t < m1 * (N / 2); t += 256) {
-            float4 x = xv[t]; const float4 y = g[t];
-            x.x += alpha * y.x; x.y += alpha * y.y; x.z += alpha * y.z; x.w += alpha * y.w;
-            xv[t] = x;
+        const int t1 = m1 * (N / 2);
+        for (int t = m0 * (N / 2) + threadIdx.x; t < t1; t += 4 * 256) {
+            float4 x[4], y[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (t + u * 256 < t1) { x[u] = xv[t + u * 256]; y[u] = g[t + u * 256]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (t + u * 256 < t1) {
+                    x[u].x += alpha * y[u].x; x[u].y += alpha * y[u].y; x[u].z += alpha * y[u].z; x[u].w += alpha * y[u].w;
+                    xv[t + u * 256] = x[u];
+                }
         }
     }
     if (!make_q) return;
@@ -385,7 +480,8 @@ __global__ void __launch_bounds__(256) k_psi_step(AdmmP<float> p, In in, int mak
     __syncthreads();
     apply_a<false>(sm.A, G, sm.U, sm.V, Gt);                     // A S_l                           N x Gt   (.m:58, left factor)
     __syncthreads();
-    rotate<false>(sm.D, sm.V, sm.U, Gt, in.scale[b]);            // scale (A S_l) Dt'               N x NT
+    if (in.dft) fft64<true>(sm.V, sm.U, sm.tw, 0.125f * in.scale[b]);
+    else rotate<false>(sm.D, sm.V, sm.U, Gt, in.scale[b]);       // scale (A S_l) Dt'               N x NT
     __syncthreads();
     write_image(sm, in.QopS + ((size_t)b * L + l) * QTAP);
 }
@@ -717,7 +813,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_fused_psi(AdmmP<float> p, const 
         JSTSP_STAMP(p, 3, cta_id, 2);
 
         // ---- pass 2 epilogues: T1'_l partial, row-major [N][L * Nt] complex ----
-        float* __restrict__ T1f = reinterpret_cast<float*>(in.T1p + ((size_t)b * p.nmc + chunk) * (size_t)N * Pp);
+        float* __restrict__ T1f = reinterpret_cast<float*>(in.T1p + (in.t1_red ? (size_t)b : (size_t)b * p.nmc + chunk) * (size_t)N * Pp);
         for (int l = 0; l < L; ++l) {
             mbar_wait(&d2_full[l & 1], (l >> 1) & 1);
             tc::tc_fence_after();
@@ -738,7 +834,8 @@ __global__ void __launch_bounds__(THREADS, 2) k_fused_psi(AdmmP<float> p, const 
                 const float vre = acc[2 * r], vim = acc[2 * r + 1];
                 const float other = __shfl_xor_sync(0xffffffffu, vim, 1);
                 const float out = (lane & 1) ? (other - vre) : (vre + other);
-                T1f[(size_t)(n0 + r) * 2 * Pp + KC * l + m] = out;
+                if (in.t1_red) atomicAdd(T1f + (size_t)(n0 + r) * 2 * Pp + KC * l + m, out);      // zeroed again by k_psi_res
+                else T1f[(size_t)(n0 + r) * 2 * Pp + KC * l + m] = out;
             }
         }
         JSTSP_STAMP(p, 3, cta_id, 3);

@@ -17,3 +17,8 @@ for imax in (1, 2, 3, 100):
         rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
         n0, n1 = est.nmse(S0, t["Zbar"]), est.nmse(S1[k].astype(np.complex128), t["Zbar"])
         print(f"  trial {k}: relS {rel(S1[k], S0):.3e} relY {rel(Y1[k], Y0):.3e} rel_nmse {abs(n1 - n0) / n0:.3e}", flush=True)
+# generic-rotation route (JSTSP_PSI_NOFFT=1) must agree with the FFT route
+if os.environ.get("JSTSP_PSI_NOFFT") is None:
+    import subprocess
+    print("--- with JSTSP_PSI_NOFFT=1 ---", flush=True)
+    subprocess.run([sys.executable, __file__], env={**os.environ, "JSTSP_PSI_NOFFT": "1"})
