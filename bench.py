@@ -11,6 +11,9 @@ One "step" = one batched solve of ``--trials`` independent trials per GPU.
   e2e   : same metric through the reference-facing C-ABI call with HOST (pinned)
           buffers - H2D of subY/Omega/A/B/params and D2H of S inside the timed region.
   roofline / cpu_baseline : see DESIGN.md sections 5-6.
+``--entry psi`` (default) feeds the estimator with the dictionary's factors (Dt, Psi_bar) exactly as the reference's drivers hold
+them before they form B (plot_errorVSsnr.m:132-136) - jstsp_proposed_algorithm_psi; ``--entry dense`` passes the dense B
+(jstsp_proposed_algorithm, the reference function's own argument list).  Both are timed; `other_entry` carries the second one.
 ``--impl reference`` times the CPU restatement of the reference's MATLAB path (oracle port,
 all host threads) on a bounded sample of the same workload.
 """
@@ -155,6 +158,7 @@ def main():
     ap.add_argument("--entry", default="psi", choices=["psi", "dense"],
                     help="psi: jstsp_proposed_algorithm_psi (dictionary given by its factors Dt, Psi_bar as the reference's drivers hold them); "
                          "dense: jstsp_proposed_algorithm (dense B, the reference function's own argument list)")
+    ap.add_argument("--no-dense", action="store_true", help="skip the short dense-B entry measurement that accompanies --entry psi")
     ap.add_argument("--shared-b", action="store_true", help="diagnostic: one pilot matrix B for all trials (L2-resident dictionary)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -187,8 +191,6 @@ def main():
     S = torch.empty(nb, P, G, dtype=cd, device=dev)
 
     use_psi = args.entry == "psi"
-    if use_psi:
-        del data["B"]        # the structured entry never sees the dense dictionary
 
     def step():
         if use_psi:
@@ -225,6 +227,30 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     value = nb * world * args.steps / (ms * 1e-3)
+
+    # the other entry point on the same trials, for the record (short: 2 warm-up + 3 timed steps, rank 0's view)
+    other = None
+    if use_psi and not args.no_dense:
+        def dense_step():
+            eng.proposed_algorithm(data["subY"], data["Omega"], data["A"], data["B"], IMAX, data["tau_Y"], data["tau_Z"], data["rho"], "approximate", S_out=S2)
+        S2 = torch.empty_like(S)
+        for _ in range(2):
+            dense_step()
+        barrier()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for _ in range(3):
+            dense_step()
+        d1.record()
+        barrier()
+        dms = torch.tensor([d0.elapsed_time(d1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dms, op=dist.ReduceOp.MAX)
+        diff = (torch.linalg.matrix_norm(S2 - S) / torch.linalg.matrix_norm(S2)).max()
+        other = dict(entry="jstsp_proposed_algorithm (dense B, the reference function's own argument list)", value=nb * world * 3 / (float(dms.item()) * 1e-3),
+                     unit=UNIT, ms_per_step=float(dms.item()) / 3, max_rel_diff_S_between_entries=float(diff.item()))
+        del S2
+    data.pop("B", None)
 
     # parity / sanity: NMSE of this rank's trials, reduced over ranks (the one NCCL exchange of a sweep point)
     mc = MonteCarlo(dev)
@@ -297,7 +323,12 @@ def main():
         "vupd": 8 * (N * G * P) * nb,                                # A S
         "fused_tc": 8 * (2 * N * N * M + 2 * N * M * P) * nb,        # tcgen05 path: (A S) B, W Z, K B^H, next Gram in one kernel
         "fused_psi": 8 * (2 * N * N * M + 2 * N * M * P) * nb,       # Psi-domain tcgen05 path: same products out of the bf16 pilot tile
+        "psi_g": 8 * (N * M * P) * nb,                               # G = (A Res) B for the line search
     }
+    # algorithmic HBM bytes per launch of the Psi-domain fused kernel: state X,V1,V2,subY,XV in + X,V1,V2 out,
+    # mask bits, bf16 pilot image (2 x 2 x Nt x (M+L-1)), operand Q in and T1' out (8 N P each)
+    kbytes = {"fused_psi": (8 * 8 * N * M + N * M // 8 + 4 * s.Nt * (M + s.L - 1) + 16 * N * P) * nb,
+              "psi_g": (8 * N * M + 4 * s.Nt * (M + s.L - 1) + 8 * N * P) * nb}
     tot_ms = sum(v[0] for v in prof.values()) or 1.0
     top = max((k for k in prof if k in kflops and prof[k][1] > 0), key=lambda k: prof[k][0], default=None)
     roof = None
@@ -316,6 +347,10 @@ def main():
                     peak_source=f"{pk['src']} bf16_tflops_sustained/2 (TF32) /3 (3xTF32-equivalent fp32 accuracy), SURVEY.md 8(d)",
                     pipe={"fused_tc": "tcgen05 kind::tf32 x3 (tensor cores)", "fused_psi": "tcgen05 kind::f16, 3 bf16 terms x exact bf16 pilots (tensor cores)"}.get(top, "fp32 FMA (CUDA cores)"), fma_peak_tflops=72.0, frac_of_fma_peak=achieved / 72.0,
                     kernels={k: dict(ms_total=v[0], launches=v[1]) for k, v in prof.items() if v[1]})
+        if top in kbytes:
+            hb = kbytes[top] / (avg_ms * 1e-3) / 1e9
+            roof["hbm_view"] = dict(bound="hbm", achieved=hb, peak=pk["hbm"], unit="GB/s", frac=hb / pk["hbm"], algorithmic_bytes_per_launch=kbytes[top],
+                                    note="the same launch scored against measured HBM copy bandwidth; ncu shows this kernel latency-bound (DRAM 36 %, tensor pipe 17 % busy)")
     cpu = None
     if not args.no_cpu:
         r, dt = cpu_port_rate(args.cpu_trials)
@@ -330,7 +365,7 @@ def main():
                             parallelism=f"trials sharded over {world} GPU(s), one NCCL all-reduce of NMSE sums"),
                 clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu,
                 algorithmic_gflop_per_estimate=F_est / 1e9, achieved_tflops_whole_step=F_est * value / 1e12,
-                nmse=stats)
+                nmse=stats, other_entry=other)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -147,6 +147,20 @@ def test_proposed_algorithm_angles_gateway():
 
 
 @pytest.mark.gpu
+def test_proposed_algorithm_psi_gateway():
+    """Factors (Dt, Psi_bar) instead of B, with and without the indx_S ranking: same numbers as the oracle on the dense B."""
+    t = fx.make_trial(fx.CONFIG0, 5.0, 12)
+    g = mh.Gateway("proposed_algorithm_psi")
+    S1, Y1 = g(2, t["subY"], t["Omega"], t["A"], t["Dt"], t["Psi_bar"], 40, t["tau_Y"], t["tau_Z"], t["rho"], "approximate")
+    S0, Y0, _ = est.proposed_algorithm_structured(t["subY"], t["Omega"], t["A"], t["B"], 40, t["tau_Y"], t["tau_Z"], t["rho"], "approximate", want_conv=False)
+    assert _rel(S1, S0) < 1e-8 and _rel(Y1, Y0) < 1e-8
+    (S2,) = g(1, t["subY"], t["Omega"], t["A"], t["Dt"], t["Psi_bar"], 40, t["tau_Y"], t["tau_Z"], t["rho"], "approximate", t["indx_S"].astype(np.float64))
+    S3, _, _ = est.proposed_algorithm_structured(t["subY"], t["Omega"], t["A"], t["B"], 40, t["tau_Y"], t["tau_Z"], t["rho"], "approximate",
+                                                 indx_S=t["indx_S"], want_conv=False)
+    assert _rel(S2, S3) < 1e-8
+
+
+@pytest.mark.gpu
 def test_svt_family_gateways():
     t = fx.make_trial(fx.TINY, 5.0, 21)
     Yh, Om = t["subY"], t["Omega"]
