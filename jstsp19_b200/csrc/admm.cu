@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(128) k_svt_weights(AdmmP<T> p) {
         __syncthreads();
         jacobi_similarity_block(sm, n, reinterpret_cast<double*>(smem + JacobiSmem::bytes(n)));
     }
-    const int sweeps = jacobi_hermitian_block(sm, n, 24, warm);
+    // fp32 solves: W is rounded to fp32 (6e-8), so a sweep that starts at a relative off-diagonal norm of 1e-5 (and ends near 1e-10) is the last
+    const int sweeps = jacobi_hermitian_block(sm, n, 24, warm, sizeof(T) == 4 ? 1e-10 : 1e-20);
     for (int t = threadIdx.x; t < nn; t += blockDim.x) { Up[t] = sm.Ure[t]; Up[nn + t] = sm.Uim[t]; }
     if (p.dbg && p.dbg_kernel == 5 && threadIdx.x == 0) { p.dbg[(size_t)b * 8 + 1] = clock64(); p.dbg[(size_t)b * 8 + 2] = sweeps; }
     const double tau = p.tauY[b] / p.rho[b];

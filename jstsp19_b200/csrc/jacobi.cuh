@@ -34,15 +34,13 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
     const int ex = ((__double2hiint(x) >> 20) & 0x7ff) - 1023;
     const int hshift = ex >> 1;
     const double xs = scalbn(x, -2 * hshift);                 // in [1, 4)
-    double r = (double)rsqrtf((float)xs);
-    r = r * (1.5 - 0.5 * xs * r * r);
+    double r = (double)rsqrtf((float)xs);                     // relative error <= 2^-22: two Newton steps (e <- 1.5 e^2) reach 1e-26
     r = r * (1.5 - 0.5 * xs * r * r);
     r = r * (1.5 - 0.5 * xs * r * r);
     return scalbn(r, -hshift);
 }
 __device__ __forceinline__ double fast_rcp_ge1(double d) {     // d >= 1 ; huge d (> fp32 range) returns 0
-    double r = (double)__frcp_rn((float)d);
-    r = r * (2.0 - d * r);
+    double r = (double)__frcp_rn((float)d);                   // relative error <= 2^-24: two Newton steps (e <- e^2) reach 1e-29
     r = r * (2.0 - d * r);
     r = r * (2.0 - d * r);
     return r;
@@ -60,7 +58,9 @@ __device__ __forceinline__ void rr_pair(int npad, int s, int k, int& p, int& q) 
 // All threads of the block must call; uses __syncthreads().
 // keep_U: U already holds a unitary matrix Q and A holds Q^H G Q (warm start); the rotations are
 // accumulated onto Q so that U ends as the eigenvector matrix of G.
-__device__ inline int jacobi_hermitian_block(JacobiSmem& sm, int n, int max_sweeps = 24, bool keep_U = false) {
+// stop_rel2: the iteration stops after a sweep that STARTED with off-diagonal mass <= stop_rel2 * |A|_F^2 (quadratic convergence:
+// that sweep ends near the square of its starting level).
+__device__ inline int jacobi_hermitian_block(JacobiSmem& sm, int n, int max_sweeps = 24, bool keep_U = false, double stop_rel2 = 1e-20) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int npad = n + (n & 1), h = npad / 2;
     if (!keep_U) for (int i = tid; i < n * n; i += nt) { sm.Ure[i] = (i % n == i / n) ? 1.0 : 0.0; sm.Uim[i] = 0.0; }
@@ -165,7 +165,7 @@ __device__ inline int jacobi_hermitian_block(JacobiSmem& sm, int n, int max_swee
             for (int k = 0; k < h; ++k) off += sm.offacc[k];
             // `off` is the off-diagonal mass seen BEFORE this sweep's rotations; Jacobi converges
             // quadratically, so a sweep that started below 1e-10 (relative) ends at rounding level.
-            sm.red[2] = (off <= 1e-20 * sm.red[0]) ? 1.0 : 0.0;
+            sm.red[2] = (off <= stop_rel2 * sm.red[0]) ? 1.0 : 0.0;
         }
         __syncthreads();
         if (sm.red[2] != 0.0) { ++sweep; break; }
