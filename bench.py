@@ -140,10 +140,33 @@ def run_reference(args):
                 cpu_baseline=dict(value=val, unit=UNIT, cores=cores, kind="port",
                                   sample=f"{n_total} trials of the workload, structured fp64 NumPy restatement of proposed_algorithm.m (no MATLAB/Octave in the image)"),
                 e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL prints its version banner on stdout at communicator creation) must not pollute the ONE JSON line:
+    everything written to fd 1 goes to stderr, the result line goes to the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -366,7 +389,7 @@ def main():
                 clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu,
                 algorithmic_gflop_per_estimate=F_est / 1e9, achieved_tflops_whole_step=F_est * value / 1e12,
                 nmse=stats, other_entry=other)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
