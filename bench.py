@@ -97,9 +97,19 @@ class ClockSampler:
         return out
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU legs are meant to use every host core (rank 0 alone runs them)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1, user_api="blas")
+    except Exception:
+        pass
+
+
 def cpu_port_rate(n_trials, seed0=9000):
     """Oracle port (structured fp64 NumPy restatement of proposed_algorithm.m) on the host cores."""
     import numpy as np
+    use_all_host_threads()
     from oracle import estimators as est
     from oracle import fixtures as fx
     trials = [fx.make_trial(fx.METRIC, SNR_SWEEP[k % len(SNR_SWEEP)], seed0 + k) for k in range(n_trials)]
