@@ -63,8 +63,9 @@ constexpr int OFF_OP = TILE, OFF_S0 = OFF_OP + OPREG, OFF_S1 = OFF_S0 + SLOT, OF
 constexpr size_t SMEM = (size_t)OFF_BAR + BARS;
 static_assert(KOP <= OPREG && 2 * QSLOT <= OPREG && SLOT <= OPREG, "operand region too small");
 static_assert(OFF_OP % 1024 == 0 && OFF_S0 % 1024 == 0 && OFF_S1 % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte alignment");
-// G kernel: tile | four half-tap slots | output tile
-constexpr int G_NSLOT = 4;
+// G kernel: tile | two half-tap slots | output tile; 128 TMEM columns -> three CTAs per SM
+constexpr int G_NSLOT = 2;
+constexpr int G_TMEM_COLS = 128;
 constexpr int G_OFF_OP = TILE, G_OFF_OUT = G_OFF_OP + G_NSLOT * QSLOT, G_OFF_BAR = G_OFF_OUT + SLOT;
 constexpr size_t G_SMEM = (size_t)G_OFF_BAR + BARS;
 static_assert(G_OFF_OUT % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte alignment");
@@ -210,12 +211,14 @@ __global__ void __launch_bounds__(256) k_build_b(const cx<T>* __restrict__ Psi, 
 // X (N x NT, element (n,k) at X[n + N k]) -> three-term bf16 operand image of pass 1 for tap l.
 // image per trial: [tap][ks 0..7][kg 0..1][row group 0..11][8 rows][8 kc], row = 32 split + 2 n + c, kc = 16 ks + 8 kg + i
 //   rows (n,re) = [Qr, -Qi], rows (n,im) = [Qi, Qr] along kc = (k,re),(k,im)       -> D[m][(n,c)] = (Q e)^T
-__device__ __forceinline__ void put_q(unsigned char* img, int n, int k, float qr, float qi) {
+// rot = 0: rows [hi | mid | lo].  rot = 2 (odd taps of the G operand): rows [mid | lo | hi], so that with the accumulator shifted by 32
+// columns mid and lo of every tap share columns while hi alternates between two column blocks (k_psi_g).
+__device__ __forceinline__ void put_q(unsigned char* img, int n, int k, float qr, float qi, int rot) {
     auto put = [&](int row, int kc, float v) {
         unsigned short s[3]; split3(v, s);
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
-            const int r = 32 * u + row;
+            const int r = 32 * ((u + rot) % 3) + row;
             *reinterpret_cast<unsigned short*>(img + (size_t)(kc / 16) * QKS + ((kc % 16) / 8) * (NRG * 128) + (r / 8) * 128 + (r % 8) * 16 + (kc % 8) * 2) = s[u];
         }
     };
@@ -223,18 +226,20 @@ __device__ __forceinline__ void put_q(unsigned char* img, int n, int k, float qr
     put(2 * n + 1, 2 * k, qi); put(2 * n + 1, 2 * k + 1, qr);
 }
 constexpr int DLD = NT + 2;      // padded leading dimension of Dt in shared memory: FWD reads (stride 2 * DLD) hit distinct banks, BWD float4 reads stay aligned
+constexpr int LDU = N + 2;       // padded leading dimension of the N x 64 work matrices: column pairs land in distinct banks, float4 row pairs stay aligned
 struct __align__(16) SmallSmem {
-    cx<float> D[DLD * NT];       // Dt(:, 0..Gt-1), column g at D + DLD g
-    cx<float> A[N * N];          // A, N x G (G <= N)
-    cx<float> U[N * NT];         // ping
-    cx<float> V[N * NT];         // pong
+    cx<float> D[DLD * NT];       // Dt(:, 0..Gt-1), column g at D + DLD g; later the operand image / Res staging
+    cx<float> A[N * N];          // A, N x G (zero-padded to N x N), element (n,g) at [n + N g]
+    cx<float> AH[N * N];         // A', element (g,n) at [g + N n]
+    cx<float> U[LDU * NT];       // ping: element (r,c) at [r + LDU c]
+    cx<float> V[LDU * NT];       // pong
     cx<float> tw[NT];            // exp(-2 pi j t / 64)
     double red[8];
 };
 // The two Dt rotations, register-tiled 2 rows x 2 outputs per thread (256 threads = 8 row pairs x 32 output pairs):
 //   FWD:  out(n,g) = scale sum_k in(n,k) Dt(k,g)            (T1'_l Dt)
 //   BWD:  out(n,k) = scale sum_g in(n,g) conj(Dt(k,g))      ((A S_l) Dt')
-// in / out are N x 64 column-major (element (n,c) at [n + N c]); D is Dt, NT x Gt column-major.
+// in / out are N x 64 with leading dimension LDU; D is Dt, NT x Gt with leading dimension DLD.
 template <bool FWD>
 __device__ __forceinline__ void rotate(const cx<float>* __restrict__ D, const cx<float>* __restrict__ in, cx<float>* __restrict__ out, int Gt, float sc) {
     const int n0 = 2 * (threadIdx.x % 8), o0 = 2 * (threadIdx.x / 8);
@@ -244,7 +249,7 @@ __device__ __forceinline__ void rotate(const cx<float>* __restrict__ D, const cx
     float r00 = 0.f, i00 = 0.f, r01 = 0.f, i01 = 0.f, r10 = 0.f, i10 = 0.f, r11 = 0.f, i11 = 0.f;     // [row][output]
 #pragma unroll 8
     for (int i = 0; i < nin; ++i) {
-        const float4 a = *reinterpret_cast<const float4*>(in + n0 + N * i);                             // rows n0, n0+1 of column i
+        const float4 a = *reinterpret_cast<const float4*>(in + n0 + LDU * i);                           // rows n0, n0+1 of column i
         float d0r, d0i, d1r, d1i;
         if (FWD) {
             const cx<float> d0 = D[i + DLD * o0], d1 = D[i + DLD * (two ? o0 + 1 : o0)];
@@ -256,30 +261,28 @@ __device__ __forceinline__ void rotate(const cx<float>* __restrict__ D, const cx
         cmac<float>(r00, i00, a.x, a.y, d0r, d0i); cmac<float>(r10, i10, a.z, a.w, d0r, d0i);
         cmac<float>(r01, i01, a.x, a.y, d1r, d1i); cmac<float>(r11, i11, a.z, a.w, d1r, d1i);
     }
-    *reinterpret_cast<float4*>(out + n0 + N * o0) = make_float4(sc * r00, sc * i00, sc * r10, sc * i10);
-    if (two) *reinterpret_cast<float4*>(out + n0 + N * (o0 + 1)) = make_float4(sc * r01, sc * i01, sc * r11, sc * i11);
+    *reinterpret_cast<float4*>(out + n0 + LDU * o0) = make_float4(sc * r00, sc * i00, sc * r10, sc * i10);
+    if (two) *reinterpret_cast<float4*>(out + n0 + LDU * (o0 + 1)) = make_float4(sc * r01, sc * i01, sc * r11, sc * i11);
 }
-// out (N x cols) = (HERM ? A^H : A) * in, A is N x G column-major (zero-padded to N x N); in/out element (r, c) at [r + N c];
-// rows of the result beyond the operator's row count are written as zeros.  Same 2 x 2 register tile.
-template <bool HERM>
-__device__ __forceinline__ void apply_a(const cx<float>* __restrict__ A, int G, const cx<float>* __restrict__ in, cx<float>* __restrict__ out, int cols) {
+// out (N x cols) = Mx * in, Mx an N x N matrix with element (r,i) at [r + N i] (sm.A, or sm.AH for A'; unused rows / columns are zero),
+// in / out with leading dimension LDU.  2 x 2 register tile, two inner indices per step, 16-byte shared-memory accesses only.
+__device__ __forceinline__ void apply_a(const cx<float>* __restrict__ Mx, const cx<float>* __restrict__ in, cx<float>* __restrict__ out, int cols) {
     const int r0 = 2 * (threadIdx.x % 8), c0 = 2 * (threadIdx.x / 8);
     if (c0 >= cols) return;
     const bool two = c0 + 1 < cols;
     const int c1 = two ? c0 + 1 : c0;
-    const int ni = HERM ? N : G;
     float r00 = 0.f, i00 = 0.f, r01 = 0.f, i01 = 0.f, r10 = 0.f, i10 = 0.f, r11 = 0.f, i11 = 0.f;     // [row][column]
-#pragma unroll 4
-    for (int i = 0; i < ni; ++i) {
-        const cx<float> x0 = in[i + N * c0], x1 = in[i + N * c1];
-        float a0r, a0i, a1r, a1i;
-        if (HERM) { const cx<float> a0 = A[i + N * r0], a1 = A[i + N * (r0 + 1)]; a0r = a0.re; a0i = -a0.im; a1r = a1.re; a1i = -a1.im; }
-        else { const float4 a = *reinterpret_cast<const float4*>(A + r0 + N * i); a0r = a.x; a0i = a.y; a1r = a.z; a1i = a.w; }
-        cmac<float>(r00, i00, a0r, a0i, x0.re, x0.im); cmac<float>(r10, i10, a1r, a1i, x0.re, x0.im);
-        cmac<float>(r01, i01, a0r, a0i, x1.re, x1.im); cmac<float>(r11, i11, a1r, a1i, x1.re, x1.im);
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+        const float4 x0 = *reinterpret_cast<const float4*>(in + i + LDU * c0), x1 = *reinterpret_cast<const float4*>(in + i + LDU * c1);   // rows i, i+1
+        const float4 a = *reinterpret_cast<const float4*>(Mx + r0 + N * i), bq = *reinterpret_cast<const float4*>(Mx + r0 + N * (i + 1));  // rows r0, r0+1
+        cmac<float>(r00, i00, a.x, a.y, x0.x, x0.y); cmac<float>(r10, i10, a.z, a.w, x0.x, x0.y);
+        cmac<float>(r01, i01, a.x, a.y, x1.x, x1.y); cmac<float>(r11, i11, a.z, a.w, x1.x, x1.y);
+        cmac<float>(r00, i00, bq.x, bq.y, x0.z, x0.w); cmac<float>(r10, i10, bq.z, bq.w, x0.z, x0.w);
+        cmac<float>(r01, i01, bq.x, bq.y, x1.z, x1.w); cmac<float>(r11, i11, bq.z, bq.w, x1.z, x1.w);
     }
-    *reinterpret_cast<float4*>(out + r0 + N * c0) = make_float4(r00, i00, r10, i10);
-    if (two) *reinterpret_cast<float4*>(out + r0 + N * c1) = make_float4(r01, i01, r11, i11);
+    *reinterpret_cast<float4*>(out + r0 + LDU * c0) = make_float4(r00, i00, r10, i10);
+    if (two) *reinterpret_cast<float4*>(out + r0 + LDU * c1) = make_float4(r01, i01, r11, i11);
 }
 
 // Dt == exp(-2 pi j k g / 64) / 8 ?  (Dr/Dt of wideband_mmwave_channel.m:9-10 with Gt = Mt = 64).  grid nDt, block 256
@@ -312,24 +315,24 @@ __device__ __forceinline__ void fft64(cx<float>* __restrict__ in, cx<float>* __r
     };
     cx<float> a[4];
     // stage 0: length 64, i = j
-    bfly(in[n + N * j], in[n + N * (j + 16)], in[n + N * (j + 32)], in[n + N * (j + 48)], a);
+    bfly(in[n + LDU * j], in[n + LDU * (j + 16)], in[n + LDU * (j + 32)], in[n + LDU * (j + 48)], a);
     __syncthreads();
 #pragma unroll
-    for (int q = 0; q < 4; ++q) in[n + N * (j + 16 * q)] = q ? a[q] * twid(q * j) : a[q];
+    for (int q = 0; q < 4; ++q) in[n + LDU * (j + 16 * q)] = q ? a[q] * twid(q * j) : a[q];
     __syncthreads();
     {   // stage 1: length 16, group j / 4, i = j % 4
         const int base = 16 * (j / 4), i = j % 4;
-        cx<float> x0 = in[n + N * (base + i)], x1 = in[n + N * (base + i + 4)], x2 = in[n + N * (base + i + 8)], x3 = in[n + N * (base + i + 12)];
+        cx<float> x0 = in[n + LDU * (base + i)], x1 = in[n + LDU * (base + i + 4)], x2 = in[n + LDU * (base + i + 8)], x3 = in[n + LDU * (base + i + 12)];
         bfly(x0, x1, x2, x3, a);
         __syncthreads();
 #pragma unroll
-        for (int q = 0; q < 4; ++q) in[n + N * (base + i + 4 * q)] = q ? a[q] * twid(4 * q * i) : a[q];
+        for (int q = 0; q < 4; ++q) in[n + LDU * (base + i + 4 * q)] = q ? a[q] * twid(4 * q * i) : a[q];
     }
     __syncthreads();
     {   // stage 2: length 4, group j; position 4 j + q holds output index rev4(4 j + q) = 16 q + 4 (j % 4) + j / 4
-        bfly(in[n + N * (4 * j)], in[n + N * (4 * j + 1)], in[n + N * (4 * j + 2)], in[n + N * (4 * j + 3)], a);
+        bfly(in[n + LDU * (4 * j)], in[n + LDU * (4 * j + 1)], in[n + LDU * (4 * j + 2)], in[n + LDU * (4 * j + 3)], a);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) out[n + N * (16 * q + 4 * (j % 4) + j / 4)] = mk<float>(scale * a[q].re, scale * a[q].im);
+        for (int q = 0; q < 4; ++q) out[n + LDU * (16 * q + 4 * (j % 4) + j / 4)] = mk<float>(scale * a[q].re, scale * a[q].im);
     }
 }
 __device__ __forceinline__ void load_small(SmallSmem& sm, const In& in, const AdmmP<float>& p, int b) {
@@ -337,15 +340,18 @@ __device__ __forceinline__ void load_small(SmallSmem& sm, const In& in, const Ad
     const cx<float>* A = p.A + (long long)b * p.ld_A;
     if (in.dft) { if (threadIdx.x < NT) { float sn, cs; sincospif(-2.0f * (float)threadIdx.x / NT, &sn, &cs); sm.tw[threadIdx.x] = mk<float>(cs, sn); } }
     else for (int t = threadIdx.x; t < NT * in.Gt; t += 256) sm.D[(t % NT) + DLD * (t / NT)] = D[t];
-    for (int t = threadIdx.x; t < N * N; t += 256) sm.A[t] = t < N * p.G ? A[t] : mk<float>(0.f, 0.f);
+    for (int t = threadIdx.x; t < N * N; t += 256) {
+        const cx<float> a = t < N * p.G ? A[t] : mk<float>(0.f, 0.f);
+        sm.A[t] = a; sm.AH[(t / N) + N * (t % N)] = mk<float>(a.re, -a.im);
+    }
 }
 
 // sm.U (N x NT) -> operand image of one tap: assembled in shared memory (over Dt, which is no longer needed), written out coalesced
-__device__ __forceinline__ void write_image(SmallSmem& sm, unsigned char* __restrict__ gimg) {
+__device__ __forceinline__ void write_image(SmallSmem& sm, unsigned char* __restrict__ gimg, int rot) {
     static_assert(sizeof(sm.D) >= QTAP, "image does not fit over Dt");
     unsigned char* img = reinterpret_cast<unsigned char*>(sm.D);
     const int n = threadIdx.x % N;
-    for (int k = threadIdx.x / N; k < NT; k += 256 / N) { const cx<float> q = sm.U[n + N * k]; put_q(img, n, k, q.re, q.im); }
+    for (int k = threadIdx.x / N; k < NT; k += 256 / N) { const cx<float> q = sm.U[n + LDU * k]; put_q(img, n, k, q.re, q.im, rot); }
     __syncthreads();
     const uint4* src = reinterpret_cast<const uint4*>(img);
     uint4* dst = reinterpret_cast<uint4*>(gimg);
@@ -354,10 +360,12 @@ __device__ __forceinline__ void write_image(SmallSmem& sm, unsigned char* __rest
 
 // Res_l = A' (scale T1'_l Dt) ; |Res_l|^2 ; operand image of G_l = (A Res_l) Dt'           (proposed_algorithm.m:47)
 // grid (L, nb), block 256
-__global__ void __launch_bounds__(256) k_psi_res(AdmmP<float> p, In in) {
+__global__ void __launch_bounds__(256, 4) k_psi_res(AdmmP<float> p, In in) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     SmallSmem& sm = *reinterpret_cast<SmallSmem*>(sm_raw);
     const int b = blockIdx.y, l = blockIdx.x, Gt = in.Gt, Pp = in.L * NT, G = p.G;
+    const int cta_id = blockIdx.y * gridDim.x + blockIdx.x;
+    JSTSP_STAMP(p, 6, cta_id, 0);
     load_small(sm, in, p, b);
     if (in.t1_red) {
         cx<float>* src = in.T1p + (size_t)b * N * Pp;
@@ -366,69 +374,68 @@ __global__ void __launch_bounds__(256) k_psi_res(AdmmP<float> p, In in) {
             float4* q = reinterpret_cast<float4*>(src + (size_t)n * Pp + l * NT + k);
             const float4 v = *q;
             *q = make_float4(0.f, 0.f, 0.f, 0.f);
-            sm.U[n + N * k] = mk<float>(v.x, v.y); sm.U[n + N * (k + 1)] = mk<float>(v.z, v.w);
+            sm.U[n + LDU * k] = mk<float>(v.x, v.y); sm.U[n + LDU * (k + 1)] = mk<float>(v.z, v.w);
         }
     } else {
-        const cx<float>* src = in.T1p + (size_t)b * p.nmc * N * Pp;
-        for (int t = threadIdx.x; t < N * NT / 2; t += 256) {
+        // sum of the chunk partials: the 8 loads of a position are issued before the first add
+        const cx<float>* src = in.T1p + (size_t)b * p.nmc * N * Pp + l * NT;
+        for (int t = threadIdx.x; t < N * NT / 2; t += 256) {    // two adjacent k per thread: 16-byte coalesced loads
             const int n = t / (NT / 2), k = 2 * (t % (NT / 2));
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-            for (int c = 0; c < p.nmc; ++c) {
-                const float4 v = *reinterpret_cast<const float4*>(src + (size_t)c * N * Pp + (size_t)n * Pp + l * NT + k);
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            for (int cb = 0; cb < p.nmc; cb += 8) {
+                float4 v[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    v[c] = cb + c < p.nmc ? *reinterpret_cast<const float4*>(src + (size_t)(cb + c) * N * Pp + (size_t)n * Pp + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) { acc.x += v[c].x; acc.y += v[c].y; acc.z += v[c].z; acc.w += v[c].w; }
             }
-            sm.U[n + N * k] = mk<float>(acc.x, acc.y); sm.U[n + N * (k + 1)] = mk<float>(acc.z, acc.w);
+            sm.U[n + LDU * k] = mk<float>(acc.x, acc.y); sm.U[n + LDU * (k + 1)] = mk<float>(acc.z, acc.w);
         }
     }
     __syncthreads();
     const float sc = in.scale[b];
     cx<float>* Res = p.Res + (size_t)b * G * p.P + (size_t)G * Gt * l;
     double rr = 0.0;
+    JSTSP_STAMP(p, 6, cta_id, 1);
+    cx<float>* R = sm.D;                                         // Res_l staging (leading dimension LDU); Dt is dead in the FFT route, unused here otherwise
     if (in.dft) {
         // Dt is unitary: Res_l = (A' T1'_l) Dt (one FFT) and (A Res_l) Dt' = A A' T1'_l (no rotation at all)
-        apply_a<true>(sm.A, G, sm.U, sm.V, NT);                  // A' T1'_l                        G x NT (rows >= G zero)
+        apply_a(sm.AH, sm.U, sm.V, NT);                          // A' T1'_l                        G x NT (rows >= G zero)
         __syncthreads();
-        apply_a<false>(sm.A, G, sm.V, sm.U, NT);                 // A A' T1'_l                      N x NT
+        apply_a(sm.A, sm.V, sm.U, NT);                           // A A' T1'_l                      N x NT
         __syncthreads();
-        for (int t = threadIdx.x; t < N * NT; t += 256) { cx<float> v = sm.U[t]; sm.U[t] = mk<float>(sc * sc * v.re, sc * sc * v.im); }
-        // (write_image below reads sm.U after its own barrier; the FFT works on sm.V and leaves Res in sm.D's first 8 KiB)
-        cx<float>* R = sm.D;
-        fft64<false>(sm.V, R, sm.tw, 0.125f * sc);
+        for (int t = threadIdx.x; t < N * NT; t += 256) { const int i = (t % N) + LDU * (t / N); cx<float> v = sm.U[i]; sm.U[i] = mk<float>(sc * sc * v.re, sc * sc * v.im); }
+        JSTSP_STAMP(p, 6, cta_id, 2);
+        fft64<false>(sm.V, R, sm.tw, 0.125f * sc);               // (write_image reads sm.U after its own barrier)
         __syncthreads();
-        for (int t = threadIdx.x; t < N * Gt; t += 256) {
-            const int r = t % N, c = t / N;
-            const cx<float> v = R[t];
-            if (r < G) { Res[r + (size_t)G * c] = v; rr += (double)v.re * v.re + (double)v.im * v.im; }
-        }
-        for (int o = 16; o > 0; o >>= 1) rr += __shfl_down_sync(0xffffffffu, rr, o);
-        if (threadIdx.x % 32 == 0) sm.red[threadIdx.x / 32] = rr;
-        __syncthreads();
-        if (threadIdx.x == 0) { double s = 0; for (int w = 0; w < 8; ++w) s += sm.red[w]; in.rr[(size_t)b * in.L + l] = s; }
+        JSTSP_STAMP(p, 6, cta_id, 3);
     } else {
         rotate<true>(sm.D, sm.U, sm.V, Gt, sc);                  // T1_l = scale T1'_l Dt           N x Gt
         __syncthreads();
-        apply_a<true>(sm.A, G, sm.V, sm.U, Gt);                  // Res_l = A' T1_l                 G x Gt (rows >= G zero)
+        apply_a(sm.AH, sm.V, sm.U, Gt);                          // Res_l = A' T1_l                 G x Gt (rows >= G zero)
         __syncthreads();
-        for (int t = threadIdx.x; t < N * Gt; t += 256) {
-            const int r = t % N, c = t / N;
-            const cx<float> v = sm.U[t];
-            if (r < G) { Res[r + (size_t)G * c] = v; rr += (double)v.re * v.re + (double)v.im * v.im; }
-        }
-        for (int o = 16; o > 0; o >>= 1) rr += __shfl_down_sync(0xffffffffu, rr, o);
-        if (threadIdx.x % 32 == 0) sm.red[threadIdx.x / 32] = rr;
-        apply_a<false>(sm.A, G, sm.U, sm.V, Gt);                 // A Res_l                         N x Gt
-        __syncthreads();
-        if (threadIdx.x == 0) { double s = 0; for (int w = 0; w < 8; ++w) s += sm.red[w]; in.rr[(size_t)b * in.L + l] = s; }
-        rotate<false>(sm.D, sm.V, sm.U, Gt, sc);                 // scale (A Res_l) Dt'             N x NT
+        R = sm.U;
     }
+    for (int t = threadIdx.x; t < N * Gt; t += 256) {
+        const int r = t % N, c = t / N;
+        const cx<float> v = R[r + LDU * c];
+        if (r < G) { Res[r + (size_t)G * c] = v; rr += (double)v.re * v.re + (double)v.im * v.im; }
+    }
+    for (int o = 16; o > 0; o >>= 1) rr += __shfl_down_sync(0xffffffffu, rr, o);
+    if (threadIdx.x % 32 == 0) sm.red[threadIdx.x / 32] = rr;
+    if (!in.dft) apply_a(sm.A, sm.U, sm.V, Gt);                  // A Res_l                         N x Gt
     __syncthreads();
-    write_image(sm, in.QopG + ((size_t)b * in.L + l) * QTAP);
+    if (threadIdx.x == 0) { double s = 0; for (int w = 0; w < 8; ++w) s += sm.red[w]; in.rr[(size_t)b * in.L + l] = s; }
+    if (!in.dft) { rotate<false>(sm.D, sm.V, sm.U, Gt, sc); __syncthreads(); }     // scale (A Res_l) Dt'   N x NT
+    JSTSP_STAMP(p, 6, cta_id, 4);
+    write_image(sm, in.QopG + ((size_t)b * in.L + l) * QTAP, (l & 1) ? 2 : 0);
+    JSTSP_STAMP(p, 6, cta_id, 5);
 }
 
 // alpha = |Res|^2 / |G|^2 ; V += alpha Res ; S = soft(V) [masked] ; XV += alpha G ; operand image of Xs = (A S) B
 // (proposed_algorithm.m:48-58, proposed_algorithm_angles.m:68).  grid (L, nb), block 256
-__global__ void __launch_bounds__(256) k_psi_step(AdmmP<float> p, In in, int make_q) {
+__global__ void __launch_bounds__(256, 4) k_psi_step(AdmmP<float> p, In in, int make_q) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     SmallSmem& sm = *reinterpret_cast<SmallSmem*>(sm_raw);
     __shared__ float s_alpha;
@@ -456,7 +463,7 @@ __global__ void __launch_bounds__(256) k_psi_step(AdmmP<float> p, In in, int mak
         cx<float> s = mk<float>(soft1<float>(v.re, thr), soft1<float>(v.im, thr));
         if (mask && !mask[t]) s = mk<float>(0.f, 0.f);
         V[t] = v; S[t] = s;
-        if (make_q) sm.U[(t % G) + N * (t / G)] = s;
+        if (make_q) sm.U[(t % G) + LDU * (t / G)] = s;
     }
     {   // XV += alpha G on this tap's share of the columns, four independent 16-byte accesses in flight per thread
         const int M = p.M, per = (M + L - 1) / L, m0 = l * per, m1 = (m0 + per) < M ? (m0 + per) : M;
@@ -476,14 +483,14 @@ __global__ void __launch_bounds__(256) k_psi_step(AdmmP<float> p, In in, int mak
         }
     }
     if (!make_q) return;
-    if (G < N) for (int t = threadIdx.x; t < N * Gt; t += 256) if (t % N >= G) sm.U[t] = mk<float>(0.f, 0.f);
+    if (G < N) for (int t = threadIdx.x; t < N * Gt; t += 256) if (t % N >= G) sm.U[(t % N) + LDU * (t / N)] = mk<float>(0.f, 0.f);
     __syncthreads();
-    apply_a<false>(sm.A, G, sm.U, sm.V, Gt);                     // A S_l                           N x Gt   (.m:58, left factor)
+    apply_a(sm.A, sm.U, sm.V, Gt);                     // A S_l                           N x Gt   (.m:58, left factor)
     __syncthreads();
     if (in.dft) fft64<true>(sm.V, sm.U, sm.tw, 0.125f * in.scale[b]);
     else rotate<false>(sm.D, sm.V, sm.U, Gt, in.scale[b]);       // scale (A S_l) Dt'               N x NT
     __syncthreads();
-    write_image(sm, in.QopS + ((size_t)b * L + l) * QTAP);
+    write_image(sm, in.QopS + ((size_t)b * L + l) * QTAP, 0);
 }
 
 // ---- shared pieces of the two tensor-core kernels ---------------------------------------------------------------------------
@@ -533,8 +540,11 @@ __device__ __forceinline__ void read_pass1(const uint32_t (&D)[2], uint32_t lane
 }
 
 // ---- G = (A Res) B on the chunk, |G|^2 partial ------------------------------------------------------------------------------
-// grid (M / 128, nb), 320 threads: warps 0-7 workers, warp 8 TMA producer, warp 9 MMA issuer
-__global__ void __launch_bounds__(THREADS, 2) k_psi_g(AdmmP<float> p, const __grid_constant__ Maps maps, In in) {
+// grid (M / 128, nb), 320 threads: warps 0-7 workers, warp 8 TMA producer, warp 9 MMA issuer; 74 KiB and 128 TMEM columns per CTA,
+// three CTAs per SM.  Accumulator columns: [0,32) hi of even taps, [32,64) mid, [64,96) lo, [96,128) hi of odd taps - even taps
+// accumulate into [0,96) with operand rows [hi|mid|lo], odd taps into [32,128) with rows [mid|lo|hi] (k_psi_res writes them so),
+// which keeps the large hi chains short (the tensor core truncates when it adds) in half the columns.
+__global__ void __launch_bounds__(THREADS, 3) k_psi_g(AdmmP<float> p, const __grid_constant__ Maps maps, In in) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* tile = smem;
     unsigned char* slots = smem + G_OFF_OP;
@@ -551,15 +561,16 @@ __global__ void __launch_bounds__(THREADS, 2) k_psi_g(AdmmP<float> p, const __gr
         mbar_init(d1_full, 1);
         mbar_fence_init();
     }
+    if (tid < 256) reinterpret_cast<uint4*>(outt)[tid] = make_uint4(0u, 0u, 0u, 0u);      // 4 KiB of zeros: the operand of the accumulator-clearing MMA
+    tc::fence_async_smem();
     if (warp == NWW) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)G_TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tm = *tmem_slot;
-    const uint32_t D[2] = {tm, tm + 128};
     if (warp == NWW) {
         if (lane == 0) {
             mbar_expect_tx(tile_full, TILE);
@@ -569,23 +580,47 @@ __global__ void __launch_bounds__(THREADS, 2) k_psi_g(AdmmP<float> p, const __gr
         __syncwarp();
     } else if (warp == NWW + 1) {
         if (lane == 0) {
+            constexpr uint32_t id1 = instr_desc_bf16(128, NS, 0), idz = instr_desc_bf16(128, 128, 0);
+            const uint32_t tile_a = smem_u32(tile), slots_a = smem_u32(slots);
             mbar_wait(tile_full, 0);
-            issue_pass1<G_NSLOT>(smem_u32(tile), smem_u32(slots), D, q_full, q_empty, L, L);
+            tc::tc_fence_after();
+            // clear all 128 columns: (any 128 x 16 tile) x (128 x 16 zeros)
+            umma_bf16(tm, tc::smem_desc(tile_a, RS, 128, 0), tc::smem_desc(smem_u32(outt), 2048, 128, 0), idz, 0u);
+            for (int i = 0; i < 2 * L; ++i) {
+                const int slot = i % G_NSLOT, l = i >> 1, hf = i & 1;
+                mbar_wait(&q_full[slot], (i / G_NSLOT) & 1);
+                tc::tc_fence_after();
+                const uint32_t a0 = tile_a + (uint32_t)(L - 1 - l) * 16, b0 = slots_a + slot * QSLOT;
+#pragma unroll
+                for (int j = 0; j < KC / 32; ++j) {
+                    const int ks = hf * (KC / 32) + j;
+                    umma_bf16(tm + 32 * (l & 1), tc::smem_desc(a0 + ks * 2 * RS, RS, 128, 0), tc::smem_desc(b0 + j * QKS, NRG * 128, 128, 0), id1, 1u);
+                }
+                tc::umma_commit(&q_empty[slot]);
+            }
             tc::umma_commit(d1_full);
         }
         __syncwarp();
     } else {
         const int quad = warp % 4, half = warp / 4, m = quad * 32 + lane, n0 = half * 8;
+        const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
         mbar_wait(d1_full, 0);
         tc::tc_fence_after();
-        float gr[8], gi[8];
-        read_pass1(D, (uint32_t)(quad * 32) << 16, n0, L, gr, gi);
+        float gr[8] = {}, gi[8] = {}, a[16];
+        // smallest terms first: lo [64,96), mid [32,64), then the two hi blocks [0,32) and [96,128)
+#pragma unroll
+        for (int blk = 0; blk < 4; ++blk) {
+            const int col = blk == 0 ? 64 : blk == 1 ? 32 : blk == 2 ? 0 : 96;
+            tc::tmem_ld16(tm + lane_base + col + 2 * n0, a);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) { gr[r] += a[2 * r]; gi[r] += a[2 * r + 1]; }
+        }
         tc::tc_fence_before();
         cx<float> g[8];
         double ss = 0.0;
 #pragma unroll
         for (int r = 0; r < 8; ++r) { g[r] = mk<float>(gr[r], gi[r]); ss += (double)gr[r] * gr[r] + (double)gi[r] * gi[r]; }
-        tile_write8(outt, m, half, g);
+        tile_write8(outt, m, half, g);                           // (the zero block has been consumed: d1_full covers the clearing MMA)
         tc::fence_async_smem();
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_down_sync(0xffffffffu, ss, o);
         if (lane == 0) red[warp] = ss;
@@ -600,7 +635,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_psi_g(AdmmP<float> p, const __gr
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == NWW) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"((uint32_t)TMEM_COLS));
+    if (warp == NWW) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"((uint32_t)G_TMEM_COLS));
 }
 
 // ---- the fused iteration kernel ------------------------------------------------------------------------------------------

@@ -22,7 +22,11 @@ extern "C" int jstsp_create(jstsp_handle** out, int device) {
     h->smem_optin = prop.sharedMemPerBlockOptin;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return JSTSP_E_CUDA; }
     h->own_stream = true;
-    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess) { delete h; return JSTSP_E_CUDA; }
+    {   // the eigen-solves on the side stream are short, latency-bound and on the critical path of the next iteration: their CTAs go first
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi) != cudaSuccess) { delete h; return JSTSP_E_CUDA; }
+    }
     if (cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking) != cudaSuccess) { delete h; return JSTSP_E_CUDA; }
     for (int k = 0; k < 2; ++k) { cudaEventCreateWithFlags(&h->ev_in[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_done[k], cudaEventDisableTiming); }
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
