@@ -183,7 +183,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--trials", type=int, default=592, help="trials per GPU per step (4 x 148 SMs)")
-    ap.add_argument("--e2e-trials", type=int, default=1184, help="trials per end-to-end call (the library splits them into passes and overlaps the H2D of pass k+1 with the solve of pass k)")
+    ap.add_argument("--e2e-trials", type=int, default=2368, help="trials per end-to-end call (the library splits them into passes and overlaps the H2D of pass k+1 with the solve of pass k)")
+    ap.add_argument("--e2e-pass", type=int, default=0, help="trials per internal pass of the end-to-end call (0 = the library's choice)")
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--cpu-trials", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
@@ -323,6 +324,8 @@ def main():
                                                    vp(hty), vp(hts), vp(hrho), vp(hS), None, None)
             eng.h.check(rc)
 
+        if args.e2e_pass:
+            eng.h.set_chunk(args.e2e_pass)
         for _ in range(3):
             host_step()
         barrier()

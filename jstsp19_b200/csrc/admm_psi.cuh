@@ -523,20 +523,22 @@ __device__ __forceinline__ void issue_pass1(uint32_t tile_a, uint32_t slots_a, c
 }
 // worker: this thread's 8 rows of column m of the pass-1 result; smallest terms first: lo, mid, hi of both accumulators
 __device__ __forceinline__ void read_pass1(const uint32_t (&D)[2], uint32_t lane_base, int n0, int taps, float (&xr)[8], float (&xi)[8]) {
-    float a[16];
+    float hi[16], mid[16], lo[16];
+    tc::tmem_ld16x3(D[0] + lane_base + 2 * n0, D[0] + lane_base + 32 + 2 * n0, D[0] + lane_base + 64 + 2 * n0, hi, mid, lo);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) { xr[r] = 0.f; xi[r] = 0.f; }
+    for (int r = 0; r < 8; ++r) { xr[r] = lo[2 * r]; xi[r] = lo[2 * r + 1]; }
+    if (taps > 1) {
+        float hi1[16], mid1[16], lo1[16];
+        tc::tmem_ld16x3(D[1] + lane_base + 2 * n0, D[1] + lane_base + 32 + 2 * n0, D[1] + lane_base + 64 + 2 * n0, hi1, mid1, lo1);
 #pragma unroll
-    for (int u = 2; u >= 0; --u) {
-        tc::tmem_ld16(D[0] + lane_base + 32 * u + 2 * n0, a);
+        for (int j = 0; j < 16; ++j) { lo[j] = lo1[j]; mid[j] += mid1[j]; hi[j] += hi1[j]; }
 #pragma unroll
-        for (int r = 0; r < 8; ++r) { xr[r] += a[2 * r]; xi[r] += a[2 * r + 1]; }
-        if (taps > 1) {
-            tc::tmem_ld16(D[1] + lane_base + 32 * u + 2 * n0, a);
-#pragma unroll
-            for (int r = 0; r < 8; ++r) { xr[r] += a[2 * r]; xi[r] += a[2 * r + 1]; }
-        }
+        for (int r = 0; r < 8; ++r) { xr[r] += lo[2 * r]; xi[r] += lo[2 * r + 1]; }
     }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { xr[r] += mid[2 * r]; xi[r] += mid[2 * r + 1]; }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { xr[r] += hi[2 * r]; xi[r] += hi[2 * r + 1]; }
 }
 
 // ---- G = (A Res) B on the chunk, |G|^2 partial ------------------------------------------------------------------------------
@@ -630,7 +632,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_psi_g(AdmmP<float> p, const __gr
             bulk_commit();
             double s = 0; for (int w = 0; w < NWW; ++w) s += red[w];
             in.gg[(size_t)b * p.nmc + chunk] = s;
-            bulk_wait_all();
+            bulk_wait_read();
         }
     }
     tc::tc_fence_before();
@@ -852,13 +854,10 @@ __global__ void __launch_bounds__(THREADS, 2) k_fused_psi(AdmmP<float> p, const 
         for (int l = 0; l < L; ++l) {
             mbar_wait(&d2_full[l & 1], (l >> 1) & 1);
             tc::tc_fence_after();
-            float acc[16] = {}, a[16];
+            float acc[16], a1[16], a2[16];
+            tc::tmem_ld16x3(D[l & 1] + lane_base + 64 + 2 * n0, D[l & 1] + lane_base + 32 + 2 * n0, D[l & 1] + lane_base + 2 * n0, acc, a1, a2);
 #pragma unroll
-            for (int u = 2; u >= 0; --u) {
-                tc::tmem_ld16(D[l & 1] + lane_base + 32 * u + 2 * n0, a);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] += a[j];
-            }
+            for (int j = 0; j < 16; ++j) acc[j] = (acc[j] + a1[j]) + a2[j];          // lo + mid, then hi
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&d2_empty[l & 1]);
@@ -915,7 +914,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_fused_psi(AdmmP<float> p, const 
                 out[2 * t] = re; out[2 * t + 1] = im;
             }
         }
-        if (tid == 0) bulk_wait_all();
+        if (tid == 0) bulk_wait_read();                          // shared memory must outlive the store's reads; the writes complete with the grid
         JSTSP_STAMP(p, 3, cta_id, 4);
         if (p.dbg && p.dbg_kernel == 3 && threadIdx.x == 0) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); p.dbg[(size_t)cta_id * 8 + 7] = sm; }
     }

@@ -96,6 +96,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
 }
+// three 16-column loads in flight, one wait
+__device__ __forceinline__ void tmem_ld16x3(uint32_t t0, uint32_t t1, uint32_t t2, float (&a)[16], float (&b)[16], float (&c)[16]) {
+    uint32_t r[48];
+#define JSTSP_LD16(base, T)                                                                                                                              \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                               \
+                 : "=r"(r[base + 0]), "=r"(r[base + 1]), "=r"(r[base + 2]), "=r"(r[base + 3]), "=r"(r[base + 4]), "=r"(r[base + 5]), "=r"(r[base + 6]),   \
+                   "=r"(r[base + 7]), "=r"(r[base + 8]), "=r"(r[base + 9]), "=r"(r[base + 10]), "=r"(r[base + 11]), "=r"(r[base + 12]), "=r"(r[base + 13]), \
+                   "=r"(r[base + 14]), "=r"(r[base + 15])                                                                                                \
+                 : "r"(T))
+    JSTSP_LD16(0, t0); JSTSP_LD16(16, t1); JSTSP_LD16(32, t2);
+#undef JSTSP_LD16
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { a[j] = __uint_as_float(r[j]); b[j] = __uint_as_float(r[16 + j]); c[j] = __uint_as_float(r[32 + j]); }
+}
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }   // what the tensor core keeps
 __device__ __forceinline__ float tf32_lo(float x) { return x - tf32_hi(x); }                                        // exact in fp32
 
