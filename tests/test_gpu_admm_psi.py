@@ -120,3 +120,39 @@ def test_device_engine_matches_host_call():
     assert eng.h.last_path == 2
     S_dev = np.swapaxes(S_dev.cpu().numpy(), -1, -2)
     assert _rel(S_dev, S_host) < 1e-6
+
+
+@pytest.mark.parametrize("name,shape", [
+    ("odd_taps", fx.Shape(Nt=64, Nr=16, L=3, Mr=4, T=4)),                 # L = 3: the last tap has no partner accumulator
+    ("one_tap", fx.Shape(Nt=64, Nr=16, L=1, Mr=4, T=2)),                  # L = 1, a single 128-column chunk
+    ("coarse_grid", fx.Shape(Nt=64, Nr=16, L=4, Mr=4, T=4, Gt=32)),       # Gt < Nt: Dt is not the unitary DFT -> generic rotations
+    ("eight_taps", fx.Shape(Nt=64, Nr=16, L=8, Mr=6, T=2, Gt=16)),        # L = 8 (the kernel's maximum), tiny grid
+])
+def test_other_structured_shapes(name, shape):
+    """Shapes around the metric one that still qualify for the tensor-core kernel (N = 16, Nt = 64, M % 128 == 0)."""
+    import jstsp19_b200 as jb
+    from jstsp19_b200._lib import default_handle
+    t = fx.make_trial(shape, 3.0, 77)
+    S1, Y1 = jb.proposed_algorithm_psi(t["subY"], t["Omega"], t["A"], t["Dt"], t["Psi_bar"], 60, t["tau_Y"], t["tau_Z"], t["rho"], "approximate",
+                                       precision="f32", nargout=2)
+    assert default_handle().last_path == 2, name
+    S0, Y0 = _oracle(t, Imax=60)
+    assert _rel(S1, S0) < TOL["f32"]["S"] and _rel(Y1, Y0) < TOL["f32"]["S"], (name, _rel(S1, S0), _rel(Y1, Y0))
+
+
+def test_host_passes_ping_pong():
+    """HOST buffers split into several internal passes (staging sets alternate, the structure check runs per pass)."""
+    import jstsp19_b200 as jb
+    from jstsp19_b200._lib import Handle
+    shape = fx.Shape(Nt=64, Nr=16, L=2, Mr=4, T=2)
+    trials = [fx.make_trial(shape, 5.0, 300 + k) for k in range(5)]
+    st = lambda k: np.stack([t[k] for t in trials])
+    h = Handle(0)
+    h.set_chunk(2)                                                        # 3 passes: 2 + 2 + 1 trials
+    S1 = jb.proposed_algorithm_psi(st("subY"), st("Omega"), st("A"), trials[0]["Dt"], st("Psi_bar"), 30, [t["tau_Y"] for t in trials],
+                                   [t["tau_Z"] for t in trials], [t["rho"] for t in trials], "approximate", precision="f32", nargout=1, handle=h)
+    assert h.last_path == 2
+    for k, t in enumerate(trials):
+        S0, _ = _oracle(t, Imax=30)
+        assert _rel(S1[k], S0) < TOL["f32"]["S"], (k, _rel(S1[k], S0))
+    h.close()
