@@ -230,6 +230,14 @@ int jstsp_admm_parameters(jstsp_handle* h, int dtype, int mem, int N, int M, int
                           const void* Y, long long ld_Y, const void* Zbar, long long ld_Z,
                           double* tau_Y, double* tau_Z, double* rho);
 
+/* rate[b] = real(log2(det(eye(n) + scale[b] * X_b * X_b')))  for X n x m complex, n <= 64: the achievable-rate / capacity
+ * metric of the sweep drivers:
+ *   plot_rateVSframelength.m:113,130,135   X = Zbar,     scale = 1 / (Nr * (sigma^2 + NMSE))
+ *   plot_capacity.m:47-66, plot_ee.m:36-87 X = W_c' * Y, scale = 1 / (sigma^2 * Nt)
+ * scale and rate are doubles in `mem` space. */
+int jstsp_log2det_rate(jstsp_handle* h, int dtype, int mem, int n, int m, int batch,
+                       const void* X, long long ld_X, const double* scale, double* rate);
+
 #ifdef __cplusplus
 }
 #endif

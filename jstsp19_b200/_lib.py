@@ -75,6 +75,7 @@ def _load():
     lib.jstsp_measure.argtypes = [vp, C.POINTER(MeasDesc), i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.jstsp_nmse.argtypes = [vp, i, i, i, i, i, vp, ll, vp, ll, vp]
     lib.jstsp_admm_parameters.argtypes = [vp, i, i, i, i, i, i, i, i, vp, ll, vp, ll, vp, vp, vp]
+    lib.jstsp_log2det_rate.argtypes = [vp, i, i, i, i, i, vp, ll, vp, vp]
     lib.jstsp_mc_admm.argtypes = [vp, i, i, i, i, i, i, vp, ll, vp, ll, vp, ll, vp, vp, vp, ll, vp, ll]
     return lib
 
@@ -87,7 +88,7 @@ EXPORTED = [
     "jstsp_synchronize", "jstsp_launch_count", "jstsp_set_chunk", "jstsp_profile", "jstsp_profile_read", "jstsp_debug_buffer",
     "jstsp_proposed_algorithm", "jstsp_proposed_algorithm_angles", "jstsp_proposed_algorithm_psi", "jstsp_last_path",
     "jstsp_svt", "jstsp_mc_svt", "jstsp_mc_admm", "jstsp_omp", "jstsp_sparse_admm", "jstsp_vamp",
-    "jstsp_wideband_mmwave_channel", "jstsp_measure", "jstsp_nmse", "jstsp_admm_parameters",
+    "jstsp_wideband_mmwave_channel", "jstsp_measure", "jstsp_nmse", "jstsp_admm_parameters", "jstsp_log2det_rate",
 ]
 
 

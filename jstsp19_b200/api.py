@@ -379,3 +379,18 @@ def admm_parameters(Y, Zbar, rho_rule="sigma6", *, precision="f64", handle=None)
     h.check(_lib.lib.jstsp_admm_parameters(h.ptr, _DT[precision], _lib.HOST, N, M, G, P, 1, 6 if rho_rule == "sigma6" else 1,
                                            _ptr(Ym), N * M, _ptr(Zm), G * P, _ptr(tY), _ptr(tZ), _ptr(rho)))
     return float(tY[0]), float(tZ[0]), float(rho[0])
+
+
+def log2det_rate(X, scale, *, precision="f64", handle=None):
+    """real(log2(det(eye(n) + scale*X*X'))): the rate metric of plot_rateVSframelength.m:113,130 (X = Zbar,
+    scale = 1/(Nr*(sigma2 + nmse))) and the capacity of plot_capacity.m:47-66 (X = W_c'*Y, scale = 1/(sigma2*Nt))."""
+    h = handle or default_handle()
+    cd = _CD[precision]
+    bs = _batch_of(X, 2)
+    batch = 1 if bs is None else bs
+    Xm = _cm(X, cd)
+    n, m = Xm.shape[-1], Xm.shape[-2]
+    sc = _per_trial(scale, batch)
+    out = np.empty(batch, dtype=np.float64)
+    h.check(_lib.lib.jstsp_log2det_rate(h.ptr, _DT[precision], _lib.HOST, n, m, batch, _ptr(Xm), n * m, _ptr(sc), _ptr(out)))
+    return float(out[0]) if bs is None else out

@@ -410,6 +410,69 @@ extern "C" int jstsp_nmse(jstsp_handle* h, int dtype, int mem, int G, int P, int
     return fail(h, JSTSP_E_ARG, "unknown dtype");
 }
 
+
+namespace jstsp {
+// ---------------------------------------------------------------------------------------------
+// rate metric: log2 det(I + c X X^H)   
+// ---------------------------------------------------------------------------------------------
+// The achievable-rate / capacity sweeps evaluate real(log2(det(eye(n) + c * X * X'))) per trial:
+//   plot_rateVSframelength.m:113,130,135   X = Zbar (Nr x L*Gt),   c = 1/(Nr (sigma^2 + NMSE))
+//   plot_capacity.m:47-66, plot_ee.m        X = W_c' * Y (Mr x T), c = 1/(sigma^2 Nt)
+// Computed through the eigenvalues of the n x n Gram matrix (same fp64 Jacobi solver as the SVT): sum_k log2(1 + c lambda_k).
+template <typename T>
+__global__ void __launch_bounds__(256) k_log2det(const cx<T>* X, long long ld_X, int n, int m, const double* scale, double* out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    JacobiSmem sm; sm.carve(smem, n);
+    const int b = blockIdx.x;
+    gram_rows<T>(sm, X + (long long)b * ld_X, nullptr, n, m);
+    jacobi_hermitian_block(sm, n);
+    if (threadIdx.x == 0) {
+        const double c = scale[b];
+        double acc = 0.0;
+        for (int k = 0; k < n; ++k) acc += log2(1.0 + c * fmax(sm.Are[k + n * k], 0.0));
+        out[b] = acc;
+    }
+}
+
+template <typename T>
+static int run_log2det(Handle* h, int mem, int n, int m, int batch, const void* X, long long ld_X, const double* scale, double* out) {
+    if (n <= 0 || m <= 0 || batch <= 0 || !X || !scale || !out) return fail(h, JSTSP_E_ARG, "bad argument");
+    if (n > 64) return fail(h, JSTSP_E_UNSUPPORTED, "rate kernel covers <= 64 rows");
+    const bool host = mem == JSTSP_HOST;
+    const size_t NM = (size_t)n * m;
+    if (!ld_X) ld_X = NM;
+    const size_t smem = JacobiSmem::bytes(n);
+    int rc = set_smem(h, k_log2det<T>, smem); if (rc) return rc;
+    const cx<T>* dx = (const cx<T>*)X; const double* ds = scale; double* dout = out;
+    if (host) {
+        rc = ensure_workspace(h, NM * batch * sizeof(cx<T>) + 2 * batch * sizeof(double) + 2048); if (rc) return rc;
+        Arena ar(h->ws, h->ws_bytes);
+        cx<T>* a = ar.take<cx<T>>(NM * batch);
+        double* s2 = ar.take<double>(batch); double* o2 = ar.take<double>(batch);
+        JSTSP_CUDA(h, cudaMemcpy2DAsync(a, NM * sizeof(cx<T>), X, (size_t)ld_X * sizeof(cx<T>), NM * sizeof(cx<T>), batch, cudaMemcpyHostToDevice, h->stream));
+        JSTSP_CUDA(h, cudaMemcpyAsync(s2, scale, sizeof(double) * batch, cudaMemcpyHostToDevice, h->stream));
+        dx = a; ld_X = NM; ds = s2; dout = o2;
+    }
+    JSTSP_LAUNCH(h, PK_OTHER, (k_log2det<T><<<batch, 256, smem, h->stream>>>(dx, ld_X, n, m, ds, dout)));
+    JSTSP_CUDA(h, cudaGetLastError());
+    if (host) {
+        JSTSP_CUDA(h, cudaMemcpyAsync(out, dout, sizeof(double) * batch, cudaMemcpyDeviceToHost, h->stream));
+        JSTSP_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    return JSTSP_OK;
+}
+
+}  // namespace jstsp
+using namespace jstsp;
+extern "C" int jstsp_log2det_rate(jstsp_handle* h, int dtype, int mem, int n, int m, int batch,
+                                  const void* X, long long ld_X, const double* scale, double* rate) {
+    if (!h) return JSTSP_E_ARG;
+    JSTSP_CUDA(h, cudaSetDevice(h->device));
+    if (dtype == JSTSP_F32) return run_log2det<float>(h, mem, n, m, batch, X, ld_X, scale, rate);
+    if (dtype == JSTSP_F64) return run_log2det<double>(h, mem, n, m, batch, X, ld_X, scale, rate);
+    return fail(h, JSTSP_E_ARG, "unknown dtype");
+}
+
 template <typename T>
 static int run_params(Handle* h, int mem, int N, int M, int G, int P, int batch, int kth, const void* Y, long long ld_Y, const void* Z, long long ld_Z,
                       double* tauY, double* tauZ, double* rho) {

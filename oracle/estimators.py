@@ -390,3 +390,12 @@ def nmse(S, Zbar):
     (plot_errorVSsnr.m:138-141)."""
     e = _ratio(norm2(S - Zbar) ** 2, norm2(Zbar) ** 2)
     return float(min(e, 1.0)) if not np.isnan(e) else float("nan")
+
+
+def log2det_rate(X, scale):
+    """real(log2(det(eye(n) + scale*X*X'))) exactly as the sweep drivers write it
+    (plot_rateVSframelength.m:113,130,135 with X = Zbar, scale = 1/(Nr*(sigma2+nmse));
+    plot_capacity.m:47-66 with X = W_c'*Y, scale = 1/(sigma2*Nt))."""
+    X = np.asarray(X, dtype=np.complex128)
+    n = X.shape[0]
+    return float(np.real(np.log2(np.linalg.det(np.eye(n) + scale * (X @ X.conj().T)))))

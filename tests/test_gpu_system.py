@@ -133,3 +133,20 @@ def test_nmse_and_parameters():
         a = jb.admm_parameters(t["subY"], t["Zbar"], rule)
         b = est.admm_parameters(t["subY"], t["Zbar"], rule)
         assert a == pytest.approx(b, rel=1e-9)
+
+
+@pytest.mark.parametrize("precision,tol", [("f64", 1e-10), ("f32", 1e-5)])
+def test_log2det_rate_matches_oracle(precision, tol):
+    """ASE of plot_rateVSframelength.m:130 (X = Zbar) and capacity of plot_capacity.m:47 (X = W_c'Y) on seeded trials."""
+    import jstsp19_b200 as jb
+    trials = [fx.make_trial(fx.METRIC, snr, 500 + k) for k, snr in enumerate([-10.0, 0.0, 10.0])]
+    Z = np.stack([t["Zbar"] for t in trials])
+    nm = np.array([0.3, 0.05, 0.002])
+    sc = np.array([1.0 / (fx.METRIC.Nr * (t["sigma2"] + e)) for t, e in zip(trials, nm)])
+    r1 = jb.log2det_rate(Z, sc, precision=precision)
+    r0 = np.array([est.log2det_rate(t["Zbar"], c) for t, c in zip(trials, sc)])
+    np.testing.assert_allclose(r1, r0, rtol=tol)
+    t = trials[1]
+    X = t["W_e"].conj().T @ t["Ynoiseless"]
+    c = 1.0 / (t["sigma2"] * fx.METRIC.Nt)
+    assert abs(jb.log2det_rate(X, c, precision=precision) - est.log2det_rate(X, c)) <= tol * abs(est.log2det_rate(X, c))

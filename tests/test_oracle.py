@@ -153,3 +153,18 @@ def test_golden_fixture_frozen():
     S, Y, c = est.proposed_algorithm_structured(g["subY"], g["Omega"], g["A"], g["B"], int(g["Imax"]), float(g["tau_Y"]),
                                                 float(g["tau_S"]), float(g["rho"]), "approximate")
     assert _rel(S, g["S"]) < 1e-12 and _rel(Y, g["Y"]) < 1e-12
+
+
+def test_log2det_rate_known_answers():
+    """log2 det(I + c X X') against closed forms: orthogonal rows, and the matrix-determinant lemma for a rank-1 X."""
+    rng = np.random.default_rng(3)
+    n, m = 6, 40
+    Q, _ = np.linalg.qr(rng.standard_normal((m, n)) + 1j * rng.standard_normal((m, n)))
+    sig = np.array([3.0, 2.0, 1.5, 1.0, 0.5, 0.1])
+    X = (Q * sig).T                                    # rows orthogonal with norms sig
+    c = 0.7
+    assert abs(est.log2det_rate(X, c) - np.sum(np.log2(1.0 + c * sig ** 2))) < 1e-10
+    u = rng.standard_normal((n, 1)) + 1j * rng.standard_normal((n, 1))
+    v = rng.standard_normal((1, m)) + 1j * rng.standard_normal((1, m))
+    X1 = u @ v
+    assert abs(est.log2det_rate(X1, c) - np.log2(1.0 + c * np.linalg.norm(u) ** 2 * np.linalg.norm(v) ** 2)) < 1e-10
