@@ -166,6 +166,31 @@ int jstsp_omp(jstsp_handle* h, int dtype, int mem, int measures, int size_d, int
               const void* A, long long ld_A, const void* v, long long ld_v,
               void* x_hat, long long ld_x, int* index_set, void* target_matrix, int* ambiguous, double margin_tol);
 
+/* OMP over the Kronecker dictionary Phi = kron(B.', A) without materialising it:
+ *   [x_hat, indexSet] = OMP(kron(B.', A), vec(Y), m)   (benchmark_algorithms/OMP.m:1-32 on the operands the
+ *   drivers build at plot_errorVSdelays.m:77-78 / plot_errorVSframelength.m:78-79; BASELINE config 2 would
+ *   need an 8192 x 262144 Phi).  A N x G, B P x M, Y N x M complex (ld_A / ld_B = 0: shared by all trials).
+ *   index_set: m int32 per trial, 1-based linear index g + G*(p-1) into the G x P unknown, first-maximum
+ *   rule of OMP.m:17.  x_hat (G*P per trial, may be NULL - it is 2 MiB per trial at config 2), x_sel (m per
+ *   trial, may be NULL): coefficient of pick t as OMP.m:29-31 scatters it, residual (N x M, may be NULL):
+ *   v - T x of the last iteration (OMP.m:20-21), ambiguous / margin_tol as in jstsp_omp. */
+int jstsp_omp_kron(jstsp_handle* h, int dtype, int mem, int N, int M, int G, int P, int m, int batch,
+                   const void* A, long long ld_A, const void* B, long long ld_B, const void* Y, long long ld_Y,
+                   void* x_hat, long long ld_x, int* index_set, void* x_sel, void* residual, long long ld_r,
+                   int* ambiguous, double margin_tol);
+
+/* Joint (MMV) OMP - replaces the reference's external sparse-plex call
+ *   spx.pursuit.joint.OrthogonalMatchingPursuit(A, K).solve(Y).Z
+ *   (plot_errorVSsnr.m:116-118, plot_errorVSdelays.m:114-115, plot_time_comparisions.m:101-102).
+ *   sparse-plex is neither vendored nor version-pinned by the reference (README.md:9): this is the textbook
+ *   row-l2 SOMP, a documented replacement rather than a parity target.  A N x D, Y N x S, Z D x S (out);
+ *   support K int32 per trial, 1-based in selection order, 0 = unused (out); n_iters per trial (out, may be
+ *   NULL); residual N x S (out, may be NULL).  Stops after K picks, at min(N, D) atoms, on a repeated pick,
+ *   or when ||R||_F <= res_tol * ||Y||_F. */
+int jstsp_somp(jstsp_handle* h, int dtype, int mem, int N, int D, int S, int K, int batch,
+               const void* A, long long ld_A, const void* Y, long long ld_Y,
+               void* Z, long long ld_Z, int* support, int* n_iters, void* residual, long long ld_R, double res_tol);
+
 /* [S, convergence_error] = sparse_admm(Htrue, OH, Dr, Dt, Imax)
  *   replaces benchmark_algorithms/sparse_admm.m:1-36 (rho = 0.01, tau_s = 1e-4 hard-coded, :12-13).
  *   Like the reference this needs Gr == Mr and Gt == Mt (Dr Mr x Mr, Dt Mt x Mt); Mr, Mt <= 64.

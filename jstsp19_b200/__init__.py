@@ -13,8 +13,9 @@ There is no CPU fallback: without the shared library the import raises, without 
 B200-class GPU every solver call raises.
 """
 from . import _lib  # noqa: F401  (raises if the CUDA library is missing)
-from .api import (OMP, admm_parameters, hbf, log2det_rate, mc_admm, mc_svt, nmse, proposed_algorithm, proposed_algorithm_angles,  # noqa: F401
+from . import api  # noqa: F401
+from .api import (OMP, OMP_kron, somp, admm_parameters, hbf, log2det_rate, mc_admm, mc_svt, nmse, proposed_algorithm, proposed_algorithm_angles,  # noqa: F401
                   proposed_algorithm_psi, proposed_hbf, sparse_admm, svt, vamp, wideband_hybBF_comm_system_training, wideband_mmwave_channel)
 
-__all__ = ["proposed_algorithm", "proposed_algorithm_angles", "proposed_algorithm_psi", "svt", "mc_svt", "mc_admm", "OMP", "sparse_admm", "vamp",
+__all__ = ["proposed_algorithm", "proposed_algorithm_angles", "proposed_algorithm_psi", "svt", "mc_svt", "mc_admm", "OMP", "OMP_kron", "somp", "sparse_admm", "vamp",
            "wideband_mmwave_channel", "proposed_hbf", "hbf", "wideband_hybBF_comm_system_training", "nmse", "admm_parameters", "log2det_rate"]

@@ -69,6 +69,8 @@ def _load():
     lib.jstsp_svt.argtypes = [vp, i, i, i, i, i, vp, ll, vp, vp, ll]
     lib.jstsp_mc_svt.argtypes = [vp, i, i, i, i, i, i, vp, ll, vp, ll, vp, vp, vp, ll]
     lib.jstsp_omp.argtypes = [vp, i, i, i, i, i, i, vp, ll, vp, ll, vp, ll, vp, vp, vp, C.c_double]
+    lib.jstsp_omp_kron.argtypes = [vp, i, i, i, i, i, i, i, i, vp, ll, vp, ll, vp, ll, vp, ll, vp, vp, vp, ll, vp, C.c_double]
+    lib.jstsp_somp.argtypes = [vp, i, i, i, i, i, i, i, vp, ll, vp, ll, vp, ll, vp, vp, vp, ll, C.c_double]
     lib.jstsp_sparse_admm.argtypes = [vp, i, i, i, i, i, i, vp, ll, vp, ll, vp, ll, vp, ll, vp, ll, vp, ll]
     lib.jstsp_vamp.argtypes = [vp, i, i, i, i, i, i, C.c_double, vp, ll, vp, ll, vp, vp, vp, ll, vp, ll, vp, ll]
     lib.jstsp_wideband_mmwave_channel.argtypes = [vp, i, i, i, i, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -87,7 +89,7 @@ EXPORTED = [
     "jstsp_create", "jstsp_destroy", "jstsp_last_error", "jstsp_version", "jstsp_set_stream",
     "jstsp_synchronize", "jstsp_launch_count", "jstsp_set_chunk", "jstsp_profile", "jstsp_profile_read", "jstsp_debug_buffer",
     "jstsp_proposed_algorithm", "jstsp_proposed_algorithm_angles", "jstsp_proposed_algorithm_psi", "jstsp_last_path",
-    "jstsp_svt", "jstsp_mc_svt", "jstsp_mc_admm", "jstsp_omp", "jstsp_sparse_admm", "jstsp_vamp",
+    "jstsp_svt", "jstsp_mc_svt", "jstsp_mc_admm", "jstsp_omp", "jstsp_omp_kron", "jstsp_somp", "jstsp_sparse_admm", "jstsp_vamp",
     "jstsp_wideband_mmwave_channel", "jstsp_measure", "jstsp_nmse", "jstsp_admm_parameters", "jstsp_log2det_rate",
 ]
 

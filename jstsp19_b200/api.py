@@ -234,6 +234,102 @@ def OMP(A, v, m, snr=None, *, precision="f64", handle=None, return_ambiguous=Fal
     return out + (amb,) if return_ambiguous else out
 
 
+def OMP_kron(A, B, Y, m, *, precision="f64", handle=None, want_x_hat=True, return_ambiguous=False):
+    """[x_hat, indexSet, x_sel, residual] = OMP(kron(B.', A), vec(Y), m) without forming the Kronecker
+    dictionary (benchmark_algorithms/OMP.m:1-32 on the operands of plot_errorVSdelays.m:77-78).
+    ``A`` N x G, ``B`` P x M, ``Y`` N x M; a leading batch axis on ``Y`` (and optionally on ``A`` / ``B``)
+    solves independent trials.  ``indexSet`` holds 1-based linear indices into the G x P unknown;
+    ``x_hat`` (G*P, ``None`` when ``want_x_hat`` is false), ``x_sel`` the coefficient of each pick."""
+    h = handle or default_handle()
+    cd = _CD[precision]
+    bs = _batch_of(Y, 2)
+    batch = 1 if bs is None else bs
+    Ym = _cm(Y, cd).reshape(batch, -1)
+    Am, Bm = _cm(A, cd), _cm(B, cd)
+    G, N = Am.shape[-2], Am.shape[-1]
+    M, P = Bm.shape[-2], Bm.shape[-1]
+    if Ym.shape[1] != N * M:
+        raise ValueError("Y must be size(A,1) x size(B,2)")
+    m = int(m)
+    x = np.empty((batch, G * P), dtype=cd) if want_x_hat else None
+    idx = np.empty((batch, m), dtype=np.int32)
+    xs = np.empty((batch, m), dtype=cd)
+    res = np.empty((batch, M, N), dtype=cd)
+    amb = np.zeros(batch, dtype=np.int32)
+    tol = 1e-10 if precision == "f64" else 1e-4
+    h.check(_lib.lib.jstsp_omp_kron(h.ptr, _DT[precision], _lib.HOST, N, M, G, P, m, batch,
+                                    _ptr(Am), N * G if Am.ndim == 3 else 0, _ptr(Bm), P * M if Bm.ndim == 3 else 0,
+                                    _ptr(Ym), N * M, _ptr(x), G * P, _ptr(idx), _ptr(xs), _ptr(res), N * M, _ptr(amb), tol))
+    R = np.swapaxes(res, -1, -2)
+    if bs is None:
+        out = (x[0] if want_x_hat else None, [int(k) for k in idx[0]], xs[0], R[0])
+        return out + (int(amb[0]),) if return_ambiguous else out
+    out = (x, idx, xs, R)
+    return out + (amb,) if return_ambiguous else out
+
+
+def somp(A, Y, K, *, precision="f64", handle=None, res_tol=0.0):
+    """Z, support, residual of the joint (MMV) OMP that stands in for
+    ``spx.pursuit.joint.OrthogonalMatchingPursuit(A, K).solve(Y)`` (plot_errorVSsnr.m:116-118).
+    ``A`` N x D, ``Y`` N x S (leading batch axis allowed); ``support`` is 1-based, in selection order."""
+    h = handle or default_handle()
+    cd = _CD[precision]
+    bs = _batch_of(Y, 2)
+    batch = 1 if bs is None else bs
+    Ym = _cm(Y, cd)
+    Am = _cm(A, cd)
+    D, N = Am.shape[-2], Am.shape[-1]
+    S = Ym.shape[-2]
+    if Ym.shape[-1] != N:
+        raise ValueError("Y must have size(A,1) rows")
+    K = int(K)
+    Z = np.empty((batch, S, D), dtype=cd)
+    sup = np.zeros((batch, K), dtype=np.int32)
+    nit = np.zeros(batch, dtype=np.int32)
+    res = np.empty((batch, S, N), dtype=cd)
+    h.check(_lib.lib.jstsp_somp(h.ptr, _DT[precision], _lib.HOST, N, D, S, K, batch, _ptr(Am), N * D if Am.ndim == 3 else 0,
+                                _ptr(Ym.reshape(batch, -1)), N * S, _ptr(Z), D * S, _ptr(sup), _ptr(nit), _ptr(res), N * S, float(res_tol)))
+    Zo, Ro = np.swapaxes(Z, -1, -2), np.swapaxes(res, -1, -2)
+    if bs is None:
+        return Zo[0], [int(k) for k in sup[0][: nit[0]]], Ro[0]
+    return Zo, [[int(k) for k in sup[b][: nit[b]]] for b in range(batch)], Ro
+
+
+class _SompResult:
+    """Result object of :class:`spx_joint_OrthogonalMatchingPursuit` (fields the drivers read: ``Z``)."""
+
+    def __init__(self, Z, support, R):
+        self.Z, self.support, self.R, self.iterations = Z, support, R, len(support)
+
+
+class spx_joint_OrthogonalMatchingPursuit:
+    """Shim with the call shape of ``spx.pursuit.joint.OrthogonalMatchingPursuit(A, K)`` /
+    ``.solve(Y)`` / ``.Z`` so the drivers' lines (plot_errorVSsnr.m:116-118) translate one to one."""
+
+    def __init__(self, A, K, *, precision="f64", handle=None):
+        self.A, self.K, self._kw = A, int(K), dict(precision=precision, handle=handle)
+
+    def solve(self, Y):
+        return _SompResult(*somp(self.A, Y, self.K, **self._kw))
+
+
+class _OmpResult:
+    def __init__(self, z, support):
+        self.z, self.support, self.iterations = z, support, len(support)
+
+
+class spx_single_OrthogonalMatchingPursuit:
+    """Shim with the call shape of ``spx.pursuit.single.OrthogonalMatchingPursuit(Phi, K)`` / ``.solve(y)`` /
+    ``.z`` (plot_time_comparisions.m:83-85), served by OMP.m's semantics (:func:`OMP`)."""
+
+    def __init__(self, Phi, K, *, precision="f64", handle=None):
+        self.Phi, self.K, self._kw = Phi, int(K), dict(precision=precision, handle=handle)
+
+    def solve(self, y):
+        x, idx, _, _ = OMP(self.Phi, np.asarray(y).reshape(-1), self.K, **self._kw)
+        return _OmpResult(x, idx)
+
+
 def sparse_admm(Htrue, OH, Dr, Dt, Imax, *, precision="f64", handle=None, nargout=2):
     """[S, convergence_error] = sparse_admm(Htrue, OH, Dr, Dt, Imax)  (benchmark_algorithms/sparse_admm.m:1)."""
     h = handle or default_handle()

@@ -220,6 +220,63 @@ def omp_literal(A, v, m, snr=None):
     return x_hat, index_set, v, target
 
 
+def somp_textbook(A, Y, K, res_tol=0.0):
+    """Row-l2 simultaneous OMP standing in for spx.pursuit.joint.OrthogonalMatchingPursuit(A,K).solve(Y)
+    (plot_errorVSsnr.m:116-118).  sparse-plex is external and unpinned (README.md:9): PARITY UNPINNED -
+    this states the algorithm the CUDA replacement implements, not sparse-plex's source.
+    t = 1..K: d = first argmax_d ||A(:,d)' R||_2; Z(support,:) = lstsq(A(:,support), Y); R = Y - A(:,support) Z;
+    stops at min(N, D) atoms, on a repeated pick, or when ||R||_F <= res_tol ||Y||_F."""
+    A = np.asarray(A, dtype=np.complex128); Y = np.asarray(Y, dtype=np.complex128)
+    N, D = A.shape
+    R = Y.copy(); support = []
+    X = np.zeros((0, Y.shape[1]), dtype=np.complex128)
+    ynorm = np.linalg.norm(Y)
+    for _t in range(int(K)):
+        if len(support) >= min(N, D):
+            break
+        c = np.sum(np.abs(A.conj().T @ R) ** 2, axis=1)
+        d = int(np.argmax(c))
+        if d in support:
+            break
+        support.append(d)
+        X = np.linalg.lstsq(A[:, support], Y, rcond=None)[0]
+        R = Y - A[:, support] @ X
+        if np.linalg.norm(R) <= res_tol * ynorm:
+            break
+    Z = np.zeros((D, Y.shape[1]), dtype=np.complex128)
+    Z[support, :] = X
+    return Z, [d + 1 for d in support], R
+
+
+def omp_kron_structured(A, B, Y, m):
+    """OMP(kron(B.', A), vec(Y), m) (OMP.m:1-32 on Phi of plot_errorVSdelays.m:77-78) without forming
+    Phi: Phi' r = vec(A' R B') (:17), column j = g + G p is vec(A(:,g) B(p,:)) (:18); pinv re-solve on the
+    materialised selected atoms (:19).  Returns (x_hat, indexSet 1-based, x per pick, residual N x M).
+    tests/test_oracle.py proves it equal to omp_literal on the materialised Phi."""
+    A = np.asarray(A, dtype=np.complex128); B = np.asarray(B, dtype=np.complex128)
+    Y = np.asarray(Y, dtype=np.complex128)
+    N, G = A.shape; P, M = B.shape
+    v = Y.reshape(-1, order="F")
+    r = v.copy()
+    target = np.zeros((N * M, 0), dtype=np.complex128)
+    index_set = []
+    x = np.zeros(0, dtype=np.complex128)
+    AH, BH = A.conj().T, B.conj().T
+    for _t in range(int(m)):
+        corr = np.abs((AH @ r.reshape(N, M, order="F") @ BH).reshape(-1, order="F"))   # :17
+        idx = int(np.argmax(corr))
+        index_set.append(idx + 1)
+        g, p = idx % G, idx // G
+        atom = np.outer(A[:, g], B[p, :]).reshape(-1, order="F")                          # :18
+        target = np.concatenate([target, atom[:, None]], axis=1)
+        x = mpinv(target) @ v                                                             # :19
+        r = v - target @ x                                                                # :20-21
+    x_hat = np.zeros(G * P, dtype=np.complex128)                                          # :27
+    for t, idx1 in enumerate(index_set):                                                  # :29-31
+        x_hat[idx1 - 1] = x[t]
+    return x_hat, index_set, x, r.reshape(N, M, order="F")
+
+
 # ----------------------------------------------------------------------------
 # proposed_algorithm.m / proposed_algorithm_angles.m
 # ----------------------------------------------------------------------------

@@ -1,0 +1,109 @@
+"""GPU parity: Kronecker-dictionary OMP (BASELINE config 2 operands, plot_errorVSdelays.m:77-78) and the joint SOMP that
+stands in for sparse-plex, through the C ABI, against the oracle."""
+import numpy as np
+import pytest
+
+from oracle import estimators as est
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def _problem(rng, N, M, G, P, nnz, noise):
+    A = (rng.standard_normal((N, G)) + 1j * rng.standard_normal((N, G))) / np.sqrt(N)
+    B = (rng.standard_normal((P, M)) + 1j * rng.standard_normal((P, M))) / np.sqrt(M)
+    S = np.zeros((G, P), complex)
+    S.flat[rng.choice(G * P, nnz, replace=False)] = rng.standard_normal(nnz) + 1j * rng.standard_normal(nnz) + 2
+    Y = A @ S @ B + noise * (rng.standard_normal((N, M)) + 1j * rng.standard_normal((N, M)))
+    return A, B, Y
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+@pytest.mark.parametrize("shape", [(6, 9, 8, 10), (32, 40, 32, 32), (33, 70, 65, 47)])
+def test_kron_omp_equals_materialised_omp(shape, precision):
+    """Small and ragged shapes: literal OMP on kron(B.', A) is the ground truth (OMP.m:1-32)."""
+    import jstsp19_b200 as jb
+    rng = np.random.default_rng(sum(shape))
+    N, M, G, P = shape
+    A, B, Y = _problem(rng, N, M, G, P, 6, 0.01)
+    m = 10
+    x0, i0, _, _ = est.omp_literal(np.kron(B.T, A), Y.reshape(-1, order="F"), m)
+    x1, i1, xs, R, amb = jb.OMP_kron(A, B, Y, m, precision=precision, return_ambiguous=True)
+    assert amb == 0 and i1 == i0                      # support and order bit-exact
+    tol = 1e-9 if precision == "f64" else 3e-4
+    assert _rel(x1, x0) < tol
+    assert _rel(xs, np.array([x0[k - 1] for k in i0])) < tol
+    assert _rel(R, Y - A @ x0.reshape(G, P, order="F") @ B) < (1e-8 if precision == "f64" else 1e-3) * max(1.0, np.linalg.norm(Y) / max(np.linalg.norm(R), 1e-30))
+
+
+def test_kron_omp_config2_shape():
+    """BASELINE config 2: Nt = Nr = 64, 4x oversampled grids - A 64 x 256, B 1024 x 128, Phi would be 8192 x 262144."""
+    import jstsp19_b200 as jb
+    rng = np.random.default_rng(64)
+    N, M, G, P = 64, 128, 256, 1024
+    A = np.exp(-2j * np.pi * np.outer(np.arange(N), np.arange(G)) / G) / np.sqrt(N)          # oversampled DFT grid (wideband_mmwave_channel.m:9)
+    B = (rng.choice([-1, 1], (P, M)) + 1j * rng.choice([-1, 1], (P, M))) / np.sqrt(2 * M)
+    S = np.zeros((G, P), complex)
+    S.flat[rng.choice(G * P, 12, replace=False)] = (rng.standard_normal(12) + 1j * rng.standard_normal(12)) + 3
+    Ys = np.stack([A @ S @ B + 0.02 * (rng.standard_normal((N, M)) + 1j * rng.standard_normal((N, M))) for _ in range(3)])
+    m = 16
+    X, I, XS, R, amb = jb.OMP_kron(A, B, Ys, m, precision="f32", want_x_hat=False, return_ambiguous=True)
+    X64, I64, XS64, R64 = jb.OMP_kron(A, B, Ys[:1], m, precision="f64")
+    for k in range(3):
+        x0, i0, xs0, r0 = est.omp_kron_structured(A, B, Ys[k], m)
+        if amb[k] == 0:
+            assert list(I[k]) == i0
+            assert _rel(XS[k], xs0) < 5e-4
+        if k == 0:
+            assert list(I64[0]) == i0 and _rel(XS64[0], xs0) < 1e-9 and _rel(X64[0], x0) < 1e-9
+    assert (amb == 0).sum() >= 2
+
+
+def test_kron_omp_device_batch_per_trial_dictionaries():
+    """Per-trial B (a fresh pilot matrix per trial, plot_errorVSsnr.m:63-67) and shared A."""
+    import jstsp19_b200 as jb
+    rng = np.random.default_rng(11)
+    N, M, G, P = 16, 48, 32, 40
+    probs = [_problem(rng, N, M, G, P, 4, 0.01) for _ in range(4)]
+    A = probs[0][0]
+    Bs = np.stack([p[1] for p in probs])
+    Ys = np.stack([A @ np.linalg.lstsq(p[0], p[2], rcond=None)[0] for p in probs])
+    X, I, XS, R = jb.OMP_kron(A, Bs, Ys, 6, precision="f64")
+    for k in range(4):
+        x0, i0, _, _ = est.omp_kron_structured(A, Bs[k], Ys[k], 6)
+        assert list(I[k]) == i0 and _rel(X[k], x0) < 1e-9
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_somp_matches_textbook_oracle(precision):
+    import jstsp19_b200 as jb
+    rng = np.random.default_rng(9)
+    N, D, S = 32, 32, 16                              # plot_errorVSsnr.m defaults: A 32 x 32, Y*pinv(B) 32 x 16, K = 100
+    A = (rng.standard_normal((N, D)) + 1j * rng.standard_normal((N, D))) / np.sqrt(N)
+    Z0 = np.zeros((D, S), complex); Z0[[3, 9, 20]] = rng.standard_normal((3, S)) + 1j * rng.standard_normal((3, S)) + 1
+    Y = A @ Z0 + 0.05 * (rng.standard_normal((N, S)) + 1j * rng.standard_normal((N, S)))
+    for K in (5, 100):
+        Z, sup, R = est.somp_textbook(A, Y, K)
+        Z1, sup1, R1 = jb.somp(A, Y, K, precision=precision)
+        n = min(len(sup), 12)                          # fp32: late picks sit at rounding level once the residual is ~0
+        assert sup1[:n] == sup[:n]
+        if K == 5:
+            assert sup1 == sup and _rel(Z1, Z) < (1e-9 if precision == "f64" else 2e-4)
+            assert _rel(R1, R) < (1e-8 if precision == "f64" else 1e-3)
+    sh = jb.api.spx_joint_OrthogonalMatchingPursuit(A, 5, precision=precision).solve(Y)
+    assert _rel(sh.Z, est.somp_textbook(A, Y, 5)[0]) < (1e-9 if precision == "f64" else 2e-4)
+
+
+def test_somp_batched_wide():
+    import jstsp19_b200 as jb
+    rng = np.random.default_rng(10)
+    N, D, S = 16, 64, 256                             # metric-shape right-hand sides (S = L*Gt = 256)
+    A = (rng.standard_normal((N, D)) + 1j * rng.standard_normal((N, D))) / np.sqrt(N)
+    Ys = rng.standard_normal((3, N, S)) + 1j * rng.standard_normal((3, N, S))
+    Z, sup, R = jb.somp(A, Ys, 6)
+    for k in range(3):
+        Z0, s0, R0 = est.somp_textbook(A, Ys[k], 6)
+        assert sup[k] == s0 and _rel(Z[k], Z0) < 1e-9 and _rel(R[k], R0) < 1e-9

@@ -168,3 +168,34 @@ def test_log2det_rate_known_answers():
     v = rng.standard_normal((1, m)) + 1j * rng.standard_normal((1, m))
     X1 = u @ v
     assert abs(est.log2det_rate(X1, c) - np.log2(1.0 + c * np.linalg.norm(u) ** 2 * np.linalg.norm(v) ** 2)) < 1e-10
+
+
+def test_omp_kron_structured_equals_literal():
+    """OMP on the materialised kron(B.', A) (plot_errorVSdelays.m:77-78) == the factor form the GPU path implements."""
+    rng = np.random.default_rng(21)
+    N, M, G, P = 6, 9, 8, 10
+    A = rng.standard_normal((N, G)) + 1j * rng.standard_normal((N, G))
+    B = rng.standard_normal((P, M)) + 1j * rng.standard_normal((P, M))
+    S = np.zeros((G, P), complex)
+    S.flat[rng.choice(G * P, 5, replace=False)] = rng.standard_normal(5) + 1j * rng.standard_normal(5) + 2
+    Y = A @ S @ B + 0.01 * (rng.standard_normal((N, M)) + 1j * rng.standard_normal((N, M)))
+    Phi = np.kron(B.T, A)
+    x0, i0, _, _ = est.omp_literal(Phi, Y.reshape(-1, order="F"), 8)
+    x1, i1, xs, R = est.omp_kron_structured(A, B, Y, 8)
+    assert i1 == i0
+    assert np.allclose(x1, x0, rtol=1e-10, atol=1e-12)
+    assert np.allclose(R.reshape(-1, order="F"), Y.reshape(-1, order="F") - Phi @ x0, atol=1e-10)
+
+
+def test_somp_textbook_properties():
+    """The sparse-plex stand-in (parity unpinned): exact recovery of a row-sparse matrix, support growth, LS optimality."""
+    rng = np.random.default_rng(3)
+    N, D, S = 24, 40, 7
+    A = (rng.standard_normal((N, D)) + 1j * rng.standard_normal((N, D))) / np.sqrt(N)
+    Z0 = np.zeros((D, S), complex); rows = sorted(rng.choice(D, 4, replace=False)); Z0[rows] = rng.standard_normal((4, S)) + 1j * rng.standard_normal((4, S)) + 1
+    Y = A @ Z0
+    Z, sup, R = est.somp_textbook(A, Y, 10, res_tol=1e-10)
+    assert sorted(sup) == [r + 1 for r in rows] and np.allclose(Z, Z0, atol=1e-10) and np.linalg.norm(R) < 1e-9
+    Zf, supf, Rf = est.somp_textbook(A, Y + 0.1 * rng.standard_normal((N, S)), 100)
+    assert len(supf) == min(N, D) and len(set(supf)) == len(supf)          # K = 100 on a small dictionary stops at min(N, D) atoms
+    assert np.allclose(A[:, [s - 1 for s in supf]].conj().T @ Rf, 0, atol=1e-8)
