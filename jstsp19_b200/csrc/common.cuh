@@ -49,7 +49,7 @@ __host__ __device__ __forceinline__ long long ceil_div_ll(long long a, long long
 // ---------------------------------------------------------------------------
 // Optional per-kernel-class device timing (CUDA events on the launching stream), switched on
 // by jstsp_profile(); bench.py reads it for the live roofline numbers.
-enum { PK_XUPD_T1 = 0, PK_RES, PK_Q, PK_VUPD, PK_XS, PK_EIG, PK_SETUP, PK_SVT_STEP, PK_OMP, PK_OTHER, PK_FUSED_TC, PK_EXPAND, PK_FUSED_PSI, PK_PSI_AUX, PK_PSI_G, PK_PSI_STEP, PK_OMP_CORR, PK_SOMP, PK_COUNT };
+enum { PK_XUPD_T1 = 0, PK_RES, PK_Q, PK_VUPD, PK_XS, PK_EIG, PK_SETUP, PK_SVT_STEP, PK_OMP, PK_OTHER, PK_FUSED_TC, PK_EXPAND, PK_FUSED_PSI, PK_PSI_AUX, PK_PSI_G, PK_PSI_STEP, PK_OMP_CORR, PK_SOMP, PK_OMP_CORR_TC, PK_COUNT };
 struct Prof {
     bool on = false;
     struct Rec { int slot; cudaEvent_t a, b; };
@@ -72,6 +72,7 @@ struct Handle {
     cudaStream_t copy = nullptr;        // H2D stream of the HOST-buffer path (next pass's inputs travel while this pass computes)
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     std::string err;
+    std::string bad_launch;             // first kernel launch the runtime rejected (slot and source line), reported with the next error
     long long launches = 0;
     int max_chunk = 0;
     int last_path = 0;                  // structured entry: 1 = dense kernels on the materialised B, 2 = Psi-domain tcgen05 kernel (last pass)
@@ -89,7 +90,10 @@ struct jstsp_handle : public jstsp::Handle {};
 namespace jstsp {
 
 inline int fail(Handle* h, int code, const std::string& msg) {
-    if (h) h->err = msg;
+    if (h) {
+        h->err = msg;
+        if (!h->bad_launch.empty()) { h->err += " [first rejected launch: " + h->bad_launch + "]"; h->bad_launch.clear(); }
+    }
     return code;
 }
 
@@ -133,6 +137,8 @@ inline void prof_collect(Handle* h) {
     do {                                    \
         ::jstsp::prof_begin((h), (slot));   \
         __VA_ARGS__;                        \
+        if (cudaPeekAtLastError() != cudaSuccess && (h)->bad_launch.empty())                             \
+            (h)->bad_launch = std::string(#slot) + " at " + __FILE__ + ":" + std::to_string(__LINE__);   \
         ::jstsp::prof_end((h));             \
         (h)->launches++;                    \
     } while (0)
@@ -164,13 +170,15 @@ inline int ensure_workspace(Handle* h, size_t bytes) {
 }
 
 template <typename K>
-inline int set_smem(Handle* h, K kernel, size_t bytes) {
-    if (bytes > h->smem_optin) return fail(h, JSTSP_E_UNSUPPORTED, "kernel needs more shared memory than the device offers");
-    if (bytes > 48 * 1024) {
+inline int set_smem_named(Handle* h, const char* what, K kernel, size_t bytes) {
+    if (bytes > h->smem_optin)
+        return fail(h, JSTSP_E_UNSUPPORTED, std::string("kernel needs more shared memory than the device offers: ") + what + " wants " + std::to_string(bytes) + " bytes");
+    if (bytes > 32 * 1024) {                 // dynamic + static shared memory may cross the 48 KiB default together
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return fail(h, JSTSP_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     }
     return JSTSP_OK;
 }
+#define set_smem(h, ...) set_smem_named((h), #__VA_ARGS__, __VA_ARGS__)   // variadic: kernel template-ids contain commas
 
 }  // namespace jstsp

@@ -107,3 +107,30 @@ def test_somp_batched_wide():
     for k in range(3):
         Z0, s0, R0 = est.somp_textbook(A, Ys[k], 6)
         assert sup[k] == s0 and _rel(Z[k], Z0) < 1e-9 and _rel(R[k], R0) < 1e-9
+
+
+def test_kron_omp_tensor_core_screen_equals_fp32_kernel(monkeypatch):
+    """Config 2 shape: the tcgen05 tf32 screen + fp64 re-evaluation of the in-band candidates must give the oracle's
+    supports, and the same result as the plain fp32 kernel (JSTSP_OMP_TC=0)."""
+    import jstsp19_b200 as jb
+    rng = np.random.default_rng(65)
+    N, M, G, P = 64, 128, 256, 1024
+    A = np.exp(-2j * np.pi * np.outer(np.arange(N), np.arange(G)) / G) / np.sqrt(N)
+    Bs = (rng.choice([-1, 1], (4, P, M)) + 1j * rng.choice([-1, 1], (4, P, M))) / np.sqrt(2 * M)
+    Ys = []
+    for k in range(4):
+        S = np.zeros((G, P), complex)
+        S.flat[rng.choice(G * P, 10, replace=False)] = (rng.standard_normal(10) + 1j * rng.standard_normal(10)) + 3
+        Ys.append(A @ S @ Bs[k] + 0.02 * (rng.standard_normal((N, M)) + 1j * rng.standard_normal((N, M))))
+    Ys = np.stack(Ys)
+    m = 14
+    monkeypatch.setenv("JSTSP_OMP_TC", "1")
+    X1, I1, XS1, R1, amb1 = jb.OMP_kron(A, Bs, Ys, m, precision="f32", want_x_hat=False, return_ambiguous=True)
+    monkeypatch.setenv("JSTSP_OMP_TC", "0")
+    X0, I0, XS0, R0, amb0 = jb.OMP_kron(A, Bs, Ys, m, precision="f32", want_x_hat=False, return_ambiguous=True)
+    for k in range(4):
+        x, i, xs, r = est.omp_kron_structured(A, Bs[k], Ys[k], m)
+        assert list(I1[k]) == i, (k, list(I1[k]), i)          # the screen path re-evaluates in fp64: supports equal the fp64 oracle's
+        assert _rel(XS1[k], xs) < 5e-4
+        if amb0[k] == 0:
+            assert list(I0[k]) == i

@@ -208,6 +208,24 @@ def test_omp_gateway_cell_output_and_support():
 
 
 @pytest.mark.gpu
+def test_omp_kron_and_somp_gateways():
+    rng = np.random.default_rng(6)
+    N, M, G, P = 8, 12, 10, 9
+    A = rng.standard_normal((N, G)) + 1j * rng.standard_normal((N, G))
+    B = rng.standard_normal((P, M)) + 1j * rng.standard_normal((P, M))
+    S = np.zeros((G, P), complex); S[2, 3] = 2 - 1j; S[7, 0] = 1.5j; S[4, 8] = -2
+    Y = A @ S @ B
+    xh, idx, xs, res = mh.Gateway("OMP_kron")(4, A, B, Y, 3)
+    x0, i0, _, _ = est.omp_literal(np.kron(B.T, A), Y.reshape(-1, order="F"), 3)
+    assert [int(c[0, 0]) for c in idx] == i0 and _rel(xh.reshape(-1), x0) < 1e-9
+    assert _rel(xs.reshape(-1), np.array([x0[k - 1] for k in i0])) < 1e-9 and np.linalg.norm(res) < 1e-9 * np.linalg.norm(Y)
+    Ys = Y @ np.linalg.pinv(B)                               # the drivers' Y*pinv(B) (plot_errorVSsnr.m:117)
+    Z, sup, R = mh.Gateway("jstsp_somp")(3, A, Ys, 3)
+    Z0, s0, R0 = est.somp_textbook(A, Ys, 3)
+    assert [int(v) for v in np.asarray(sup).reshape(-1)] == s0 and _rel(Z, Z0) < 1e-9 and _rel(R, R0) < 1e-6 + 1e-9
+
+
+@pytest.mark.gpu
 def test_vamp_gateway_uses_matlab_svd():
     rng = np.random.default_rng(8)
     m, n = 24, 48

@@ -16,6 +16,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=296)
 ap.add_argument("--m", type=int, default=50)
 ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--dbg", action="store_true")
 ap.add_argument("--shape", type=int, nargs=4, default=[64, 128, 256, 1024])
 a = ap.parse_args()
 N, M, G, P = a.shape
@@ -25,7 +26,8 @@ A = (torch.exp(-2j * torch.pi * torch.outer(torch.arange(G, device=dev), torch.a
 B = ((torch.randint(0, 2, (a.batch, M, P), generator=g, device=dev) * 2 - 1) + 1j * (torch.randint(0, 2, (a.batch, M, P), generator=g, device=dev) * 2 - 1)).to(torch.complex64) / (2 * M) ** 0.5
 S = torch.zeros(a.batch, P, G, dtype=torch.complex64, device=dev)
 idx = torch.randint(0, G * P, (a.batch, 12), generator=g, device=dev)
-S.view(a.batch, -1).scatter_(1, idx, torch.full((a.batch, 12), 3 + 1j, dtype=torch.complex64, device=dev))
+gains = (torch.randn(a.batch, 12, generator=g, device=dev) + 1j * torch.randn(a.batch, 12, generator=g, device=dev)).to(torch.complex64) * 2   # CN(0,.) path gains (wideband_mmwave_channel.m:19)
+S.view(a.batch, -1).scatter_(1, idx, gains)
 # Y' (M,N) = B' S' A'  in the stored (transposed) layout
 Y = torch.matmul(torch.matmul(B, S), A.unsqueeze(0).expand(a.batch, -1, -1)).contiguous()
 Y += 0.02 * torch.randn(Y.shape, generator=g, device=dev, dtype=torch.float32).to(torch.complex64)
@@ -43,6 +45,15 @@ def run():
 
 
 run(); torch.cuda.synchronize()
+if a.dbg:
+    dbg = torch.zeros(2048, dtype=torch.int64, device=dev)
+    _lib.lib.jstsp_debug_buffer(h.ptr, C.c_void_p(dbg.data_ptr()))
+    run(); torch.cuda.synchronize()
+    _lib.lib.jstsp_debug_buffer(h.ptr, None)
+    d = dbg[:1184].view(148, 8).double().mean(0).tolist()
+    print(json.dumps(dict(screen_updates=int(dbg[1200]), failed=int(dbg[1201]), candidates=int(dbg[1202]), whole_rows=int(dbg[1203]))), file=sys.stderr)
+    print(json.dumps(dict(dbg_last_launch=dict(mma_total_cyc=d[0], mma_wait_full=d[1], mma_wait_tready=d[2], mma_wait_d2empty=d[3], items=d[4],
+                                               prod_wait_empty=d[5], prod_total_cyc=d[6]))), file=sys.stderr)
 _lib.lib.jstsp_profile(h.ptr, 2)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
@@ -61,7 +72,7 @@ while True:
     slot += 1
 _lib.lib.jstsp_profile(h.ptr, 0)
 cmac = N * M * P + G * N * P                      # per iteration per trial: R B^H then A^H T
-corr = kern.get("omp_kron_corr", {}).get("avg_ms")
+corr = (kern.get("omp_kron_corr_tc") or kern.get("omp_kron_corr", {})).get("avg_ms")
 print(json.dumps(dict(shape=a.shape, batch=a.batch, m=a.m, ms_per_call=ms, trials_per_s=a.batch / ms * 1e3,
                       corr_tflops=(8 * cmac * a.batch / (corr * 1e-3) / 1e12) if corr else None,
                       ambiguous_trials=int((amb > 0).sum()), kernels=kern)))
