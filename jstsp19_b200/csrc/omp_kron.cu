@@ -449,13 +449,15 @@ __global__ void __launch_bounds__(kt::THREADS, 1) k_kron_corr_tc(KronP<float> p,
     if (warp == 4) tmem_dealloc(tm, 512);
 }
 
+constexpr int KU_T = 512, KU_W = KU_T / 32;      // threads / warps of k_kron_update (latency-bound: more loads in flight per trial)
+
 template <typename T>
-__global__ void __launch_bounds__(256) k_kron_update(KronP<T> p) {
+__global__ void __launch_bounds__(KU_T) k_kron_update(KronP<T> p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = p.N, G = p.G, P = p.P, m = p.m, t = p.t;
     const size_t NM = (size_t)N * p.M;
-    __shared__ double s_red[8][2];
+    __shared__ double s_red[KU_W][2];
     __shared__ int s_pick, s_dup;
     cx<T>* r = p.res + (size_t)b * NM;
     int* st = p.state + (size_t)b * (2 + 3 * m);
@@ -473,15 +475,15 @@ __global__ void __launch_bounds__(256) k_kron_update(KronP<T> p) {
         __shared__ float s_vmax;
         const float* rv1 = p.row_v1 + (size_t)b * P; const int* rg1 = p.row_g1 + (size_t)b * P; const float* rv2 = p.row_v2 + (size_t)b * P;
         float vm = -1.f;
-        for (int q = tid; q < P; q += 256) vm = fmaxf(vm, rv1[q]);
+        for (int q = tid; q < P; q += KU_T) vm = fmaxf(vm, rv1[q]);
         for (int o = 16; o > 0; o >>= 1) vm = fmaxf(vm, __shfl_xor_sync(0xffffffffu, vm, o));
         if (lane == 0) s_red[warp][0] = vm;
         if (tid == 0) { s_nc = 0; s_nrow = 0; }
         __syncthreads();
-        if (tid == 0) { float a = -1.f; for (int w = 0; w < 8; ++w) a = fmaxf(a, (float)s_red[w][0]); s_vmax = a; }
+        if (tid == 0) { float a = -1.f; for (int w = 0; w < KU_W; ++w) a = fmaxf(a, (float)s_red[w][0]); s_vmax = a; }
         __syncthreads();
         const float vmax = s_vmax, lim = vmax * (1.f - p.band);
-        for (int q = tid; q < P; q += 256) {
+        for (int q = tid; q < P; q += KU_T) {
             const bool whole = rv2[q] >= lim && rv2[q] >= 0.f;
             if (whole) { const int k = atomicAdd(&s_nrow, 1); if (k < MAXR) s_rows[k] = q; }
             else if (rv1[q] >= lim) { const int k = atomicAdd(&s_nc, 1); if (k < MAXC) s_cand[k] = rg1[q] + G * q; }
@@ -504,7 +506,7 @@ __global__ void __launch_bounds__(256) k_kron_update(KronP<T> p) {
                 const cx<T>* a = p.A + (long long)b * p.ld_A + (size_t)N * g;
                 const cx<T>* bq = p.B + (long long)b * p.ld_B + pq;
                 double re = 0.0, im = 0.0;
-                for (size_t i = tid; i < NM; i += 256) {
+                for (size_t i = tid; i < NM; i += KU_T) {
                     const int n = (int)(i % N), mm = (int)(i / N);
                     const cx<T> av = a[n], bv = bq[(size_t)P * mm], rv = r[i];
                     const double wr = (double)av.re * bv.re - (double)av.im * bv.im, wi = (double)av.re * bv.im + (double)av.im * bv.re;   // a b
@@ -513,7 +515,7 @@ __global__ void __launch_bounds__(256) k_kron_update(KronP<T> p) {
                 for (int o = 16; o > 0; o >>= 1) { re += __shfl_xor_sync(0xffffffffu, re, o); im += __shfl_xor_sync(0xffffffffu, im, o); }
                 if (lane == 0) { s_red[warp][0] = re; s_red[warp][1] = im; }
                 __syncthreads();
-                if (tid == 0) { double cr = 0, ci = 0; for (int w = 0; w < 8; ++w) { cr += s_red[w][0]; ci += s_red[w][1]; } s_cmag[c] = cr * cr + ci * ci; }
+                if (tid == 0) { double cr = 0, ci = 0; for (int w = 0; w < KU_W; ++w) { cr += s_red[w][0]; ci += s_red[w][1]; } s_cmag[c] = cr * cr + ci * ci; }
                 __syncthreads();
             }
             // whole rows: u = R b_p' (N values), c_g = a_g' u for every g; entries inside a slightly wider band join the list with exact values
@@ -522,16 +524,16 @@ __global__ void __launch_bounds__(256) k_kron_update(KronP<T> p) {
             for (int rr = 0; rr < nrow; ++rr) {
                 const int pq = s_rows[rr];
                 const cx<T>* bq = p.B + (long long)b * p.ld_B + pq;
-                for (int n = tid; n < 2 * N; n += 256) u[n] = 0.0;
+                for (int n = tid; n < 2 * N; n += KU_T) u[n] = 0.0;
                 __syncthreads();
-                for (size_t i = tid; i < NM; i += 256) {
+                for (size_t i = tid; i < NM; i += KU_T) {
                     const int n = (int)(i % N), mm = (int)(i / N);
                     const cx<T> bv = bq[(size_t)P * mm], x = r[i];
                     atomicAdd(&u[2 * n], (double)x.re * bv.re + (double)x.im * bv.im);
                     atomicAdd(&u[2 * n + 1], (double)x.im * bv.re - (double)x.re * bv.im);
                 }
                 __syncthreads();
-                for (int g = tid; g < G; g += 256) {
+                for (int g = tid; g < G; g += KU_T) {
                     const cx<T>* a = p.A + (long long)b * p.ld_A + (size_t)N * g;
                     double re = 0.0, im = 0.0;
                     for (int n = 0; n < N; ++n) { const cx<T> av = a[n]; re += (double)av.re * u[2 * n] + (double)av.im * u[2 * n + 1]; im += (double)av.re * u[2 * n + 1] - (double)av.im * u[2 * n]; }
@@ -584,7 +586,7 @@ __global__ void __launch_bounds__(256) k_kron_update(KronP<T> p) {
     cx<double>* gcol = reinterpret_cast<cx<double>*>(smem);                   // Gram column -> w = L^-1 g
     cx<double>* xtmp = gcol + (m + 1);
     double* dg = reinterpret_cast<double*>(xtmp + (m + 1));                   // diagonal of L
-    cx<T>* a_s = reinterpret_cast<cx<T>*>(dg + (m + 2));
+    cx<T>* a_s = reinterpret_cast<cx<T>*>(dg + ((m + 3) & ~1));             // keeps cx<double> 16-byte aligned for odd m
     cx<T>* b_s = a_s + N;
     cx<T>* As = b_s + M;
     cx<T>* Bs = As + J * N;
@@ -596,12 +598,12 @@ __global__ void __launch_bounds__(256) k_kron_update(KronP<T> p) {
     const cx<T>* Bg = p.B + (long long)b * p.ld_B + pp;
     const cx<T>* Y = p.Y + (long long)b * p.ld_Y;
     __shared__ cx<double> s_rhs;
-    for (int i = tid; i < N; i += 256) { const cx<T> a = Ag[i]; a_s[i] = a; Asel[(size_t)nu * N + i] = a; }               // atom = A(:,g) B(p,:)  (OMP.m:18)
-    for (int i = tid; i < M; i += 256) { const cx<T> v = Bg[(size_t)P * i]; b_s[i] = v; Bsel[(size_t)nu * M + i] = v; }
+    for (int i = tid; i < N; i += KU_T) { const cx<T> a = Ag[i]; a_s[i] = a; Asel[(size_t)nu * N + i] = a; }               // atom = A(:,g) B(p,:)  (OMP.m:18)
+    for (int i = tid; i < M; i += KU_T) { const cx<T> v = Bg[(size_t)P * i]; b_s[i] = v; Bsel[(size_t)nu * M + i] = v; }
     __syncthreads();
     {   // rhs_t = atom' v
         double re = 0.0, im = 0.0;
-        for (size_t i = tid; i < NM; i += 256) {
+        for (size_t i = tid; i < NM; i += KU_T) {
             const int n = (int)(i % N), mm = (int)(i / N);
             const cx<T> av = a_s[n], bv = b_s[mm], y = Y[i];
             const double wr = (double)av.re * bv.re - (double)av.im * bv.im, wi = (double)av.re * bv.im + (double)av.im * bv.re;
@@ -610,7 +612,7 @@ __global__ void __launch_bounds__(256) k_kron_update(KronP<T> p) {
         for (int o = 16; o > 0; o >>= 1) { re += __shfl_xor_sync(0xffffffffu, re, o); im += __shfl_xor_sync(0xffffffffu, im, o); }
         if (lane == 0) { s_red[warp][0] = re; s_red[warp][1] = im; }
     }
-    for (int j = warp; j <= nu; j += 8) {                                     // Gram column g_j = <atom_j, atom_t>, j = nu is the new atom itself
+    for (int j = warp; j <= nu; j += KU_W) {                                     // Gram column g_j = <atom_j, atom_t>, j = nu is the new atom itself
         const cx<T>* aj = j == nu ? a_s : Asel + (size_t)j * N;
         const cx<T>* bj = j == nu ? b_s : Bsel + (size_t)j * M;
         double ar = 0.0, ai = 0.0, br = 0.0, bi = 0.0;
@@ -623,14 +625,14 @@ __global__ void __launch_bounds__(256) k_kron_update(KronP<T> p) {
         if (lane == 0) gcol[j] = mk<double>(ar * br - ai * bi, ar * bi + ai * br);
     }
     __syncthreads();
-    if (tid == 0) { double cr = 0, ci = 0; for (int w = 0; w < 8; ++w) { cr += s_red[w][0]; ci += s_red[w][1]; } s_rhs = mk<double>(cr, ci); }
+    if (tid == 0) { double cr = 0, ci = 0; for (int w = 0; w < KU_W; ++w) { cr += s_red[w][0]; ci += s_red[w][1]; } s_rhs = mk<double>(cr, ci); }
     __syncthreads();
     // K = L^-1 (row-major, lower) is kept instead of L: the new row is -(w' K)/l_tt with w = K g, so every step below is a
     // parallel matrix-vector product (one memory round trip) instead of a latency chain of triangular-solve steps.
     __shared__ double s_ltt;
     __shared__ int s_dep;
     __shared__ cx<double> s_yt;
-    for (int j = warp; j < nu; j += 8) {                                      // w = K g
+    for (int j = warp; j < nu; j += KU_W) {                                      // w = K g
         const cx<double>* kr = K + (size_t)j * m;
         cx<double> acc = mk<double>(0.0, 0.0);
         for (int i = lane; i <= j; i += 32) acc = acc + kr[i] * gcol[i];
@@ -651,7 +653,7 @@ __global__ void __launch_bounds__(256) k_kron_update(KronP<T> p) {
     cx<double>* rhsv = p.rhsv + (size_t)b * m;
     {
         cx<double> part = mk<double>(0.0, 0.0);
-        for (int i = tid; i < nu; i += 256) {                                 // K(t, i) = -(1/l_tt) sum_{j >= i} conj(w_j) K(j, i)
+        for (int i = tid; i < nu; i += KU_T) {                                 // K(t, i) = -(1/l_tt) sum_{j >= i} conj(w_j) K(j, i)
             cx<double> acc = mk<double>(0.0, 0.0);
             for (int j = i; j < nu; ++j) acc = acc + conj(xtmp[j]) * K[(size_t)j * m + i];
             const cx<double> kt = mk<double>(-iltt * acc.re, -iltt * acc.im);
@@ -663,7 +665,7 @@ __global__ void __launch_bounds__(256) k_kron_update(KronP<T> p) {
     }
     __syncthreads();
     if (tid == 0) {
-        double cr = 0, ci = 0; for (int w = 0; w < 8; ++w) { cr += s_red[w][0]; ci += s_red[w][1]; }
+        double cr = 0, ci = 0; for (int w = 0; w < KU_W; ++w) { cr += s_red[w][0]; ci += s_red[w][1]; }
         const cx<double> yt = mk<double>(cr + iltt * s_rhs.re, ci + iltt * s_rhs.im);                                   // y_t = K(t,:) rhs
         K[(size_t)nu * m + nu] = mk<double>(iltt, 0.0);
         rhsv[nu] = s_rhs; yv[nu] = yt; s_yt = yt;
@@ -671,7 +673,7 @@ __global__ void __launch_bounds__(256) k_kron_update(KronP<T> p) {
     __syncthreads();
     {
         cx<double>* xv = p.xv + (size_t)b * m;
-        for (int i = tid; i <= nu; i += 256) {                                // x = K' y
+        for (int i = tid; i <= nu; i += KU_T) {                                // x = K' y
             cx<double> acc = mk<double>(0.0, 0.0);
             for (int j = i; j <= nu; ++j) acc = acc + conj(K[(size_t)j * m + i]) * (j == nu ? s_yt : yv[j]);
             xtmp[i] = acc; xv[i] = acc;
@@ -681,15 +683,15 @@ __global__ void __launch_bounds__(256) k_kron_update(KronP<T> p) {
     for (int j0 = 0; j0 <= nu; j0 += J) {
         const int jn = (nu + 1 - j0) < J ? (nu + 1 - j0) : J;
         __syncthreads();
-        for (int e = tid; e < jn * N; e += 256) { const int j = e / N, n = e % N; As[e] = (j0 + j == nu) ? a_s[n] : Asel[(size_t)(j0 + j) * N + n]; }
-        for (int e = tid; e < jn * M; e += 256) {
+        for (int e = tid; e < jn * N; e += KU_T) { const int j = e / N, n = e % N; As[e] = (j0 + j == nu) ? a_s[n] : Asel[(size_t)(j0 + j) * N + n]; }
+        for (int e = tid; e < jn * M; e += KU_T) {
             const int j = e / M, mm = e % M;
             const cx<double> x = xtmp[j0 + j];
             const cx<T> v = (j0 + j == nu) ? b_s[mm] : Bsel[(size_t)(j0 + j) * M + mm];
             Bs[e] = mk<T>((T)(x.re * v.re - x.im * v.im), (T)(x.re * v.im + x.im * v.re));
         }
         __syncthreads();
-        for (size_t i = tid; i < NM; i += 256) {
+        for (size_t i = tid; i < NM; i += KU_T) {
             const int n = (int)(i % N), mm = (int)(i / N);
             T ar = 0, ai = 0;
             for (int j = 0; j < jn; ++j) { const cx<T> a = As[j * N + n], bb = Bs[j * M + mm]; cmac<T>(ar, ai, a.re, a.im, bb.re, bb.im); }
@@ -738,7 +740,7 @@ static int run_omp_kron(Handle* h, int mem, int N, int M, int G, int P, int m, i
     const size_t smem_corr = esz * ((size_t)Npad * KC_PC + KC_KT * KC_RB + KC_KT * KC_PC);
     int rc = set_smem(h, k_kron_corr<T>, smem_corr);
     if (rc) return rc;
-    const size_t smem_upd = 2 * sizeof(cx<double>) * (size_t)(m + 1) + sizeof(double) * (size_t)(m + 2) + esz * (size_t)(33 * (N + M));
+    const size_t smem_upd = 2 * sizeof(cx<double>) * (size_t)(m + 1) + sizeof(double) * (size_t)((m + 3) & ~1) + esz * (size_t)(33 * (N + M));
     rc = set_smem(h, k_kron_update<T>, smem_upd);
     if (rc) return rc;
     const int nchunk = ceil_div(P, KC_PC);
@@ -837,7 +839,7 @@ static int run_omp_kron(Handle* h, int mem, int N, int M, int G, int P, int m, i
                     q.screen = 1;
                     const int items = ntile * nb;
                     JSTSP_LAUNCH(h, PK_OMP_CORR_TC, (k_kron_corr_tc<<<items < h->sm_count ? items : h->sm_count, kt::THREADS, kt::SMEM, st>>>(q, mapBt, mapR, mapA, sharedB ? 1 : 0, sharedA ? 1 : 0, nb)));
-                    JSTSP_LAUNCH(h, PK_OMP, (k_kron_update<T><<<nb, 256, smem_upd, st>>>(q)));
+                    JSTSP_LAUNCH(h, PK_OMP, (k_kron_update<T><<<nb, KU_T, smem_upd, st>>>(q)));
                     q.screen = 0;                                             // trials the screen left undecided (rare) redo the iteration in fp32
                 }
             }
@@ -845,7 +847,7 @@ static int run_omp_kron(Handle* h, int mem, int N, int M, int G, int P, int m, i
                 const int items = nchunk * nb, cap = 4 * h->sm_count;
                 JSTSP_LAUNCH(h, PK_OMP_CORR, (k_kron_corr<T><<<(use_tc && items > cap) ? cap : items, 256, smem_corr, st>>>(q, nb)));
             }
-            JSTSP_LAUNCH(h, use_tc ? PK_OTHER : PK_OMP, (k_kron_update<T><<<nb, 256, smem_upd, st>>>(q)));
+            JSTSP_LAUNCH(h, use_tc ? PK_OTHER : PK_OMP, (k_kron_update<T><<<nb, KU_T, smem_upd, st>>>(q)));
             if (use_tc && t + 1 < m) JSTSP_LAUNCH(h, PK_SETUP, (k_kron_pack_r<T><<<dim3(ceil_div(M, 32), nb), 256, 0, st>>>(q)));
         }
         JSTSP_LAUNCH(h, PK_OMP, (k_kron_finish<T><<<nb, 256, 0, st>>>(q)));

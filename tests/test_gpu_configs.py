@@ -68,11 +68,12 @@ def test_delay_sweep(L):
     assert _rel(S1, S0a) < 2e-5
 
 
-@pytest.mark.parametrize("precision,tol", [("f64", 1e-9), ("f32", 3e-5)])
-def test_large_array_rows(precision, tol):
-    """Config 4 geometry at reduced length: Nr = 64 receive rows (N = G = 64), L = 8 taps, Nt = 16."""
+@pytest.mark.parametrize("Nr,precision,tol", [(64, "f32", 3e-5), (48, "f64", 1e-9), (48, "f32", 3e-5)])
+def test_large_array_rows(Nr, precision, tol):
+    """Config 4 geometry at reduced length: Nr = 64 receive rows (N = G = 64), L = 8 taps, Nt = 16.  The fp64 kernels stop at
+    48 rows (shared memory of the exact-LS / residual kernel); 64 rows in fp64 is refused loudly (next test)."""
     import jstsp19_b200 as jb
-    shape = fx.Shape(Nt=16, Nr=64, L=8, Mr=8, T=8)
+    shape = fx.Shape(Nt=16, Nr=Nr, L=8, Mr=8, T=8)
     t = fx.make_trial(shape, 5.0, 640)
     args = (t["subY"], t["Omega"], t["A"], t["B"], 40, t["tau_Y"], t["tau_Z"], t["rho"], "approximate")
     S0, Y0, _ = est.proposed_algorithm_structured(*args)
@@ -80,3 +81,12 @@ def test_large_array_rows(precision, tol):
     assert _rel(S1, S0) < tol and _rel(Y1, Y0) < tol, (_rel(S1, S0), _rel(Y1, Y0))
     S2 = jb.proposed_algorithm_psi(t["subY"], t["Omega"], t["A"], t["Dt"], t["Psi_bar"], 40, t["tau_Y"], t["tau_Z"], t["rho"], "approximate", precision=precision, nargout=1)
     assert _rel(S2, S0) < tol
+
+
+def test_fp64_at_64_rows_is_refused_by_name():
+    import jstsp19_b200 as jb
+    from jstsp19_b200._lib import JstspError
+    t = fx.make_trial(fx.Shape(Nt=16, Nr=64, L=8, Mr=8, T=8), 5.0, 641)
+    with pytest.raises(JstspError) as e:
+        jb.proposed_algorithm(t["subY"], t["Omega"], t["A"], t["B"], 5, t["tau_Y"], t["tau_Z"], t["rho"], "approximate", precision="f64")
+    assert e.value.code == -3 and "shared memory" in str(e.value) and "k_res" in str(e.value)

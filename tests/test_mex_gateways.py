@@ -222,7 +222,8 @@ def test_omp_kron_and_somp_gateways():
     Ys = Y @ np.linalg.pinv(B)                               # the drivers' Y*pinv(B) (plot_errorVSsnr.m:117)
     Z, sup, R = mh.Gateway("jstsp_somp")(3, A, Ys, 3)
     Z0, s0, R0 = est.somp_textbook(A, Ys, 3)
-    assert [int(v) for v in np.asarray(sup).reshape(-1)] == s0 and _rel(Z, Z0) < 1e-9 and _rel(R, R0) < 1e-6 + 1e-9
+    assert [int(v) for v in np.asarray(sup).reshape(-1)] == s0 and _rel(Z, Z0) < 1e-9
+    assert np.linalg.norm(R - R0) < 1e-9 * np.linalg.norm(Ys)        # three atoms recover Ys exactly: both residuals are rounding-level
 
 
 @pytest.mark.gpu
