@@ -107,7 +107,8 @@ __device__ inline int jacobi_hermitian_block(JacobiSmem& sm, int n, int max_swee
             __syncthreads();
             // phase 1: every 2x2 block (k1,k2) <- J1^H * block * J2 ; U(:, {p,q}) <- U(:, {p,q}) * J
             for (int t = tid; t < h * h; t += nt) {
-                int k1 = t / h, k2 = t % h;
+                int k1 = t % h, k2 = t / h;          // row pairs vary fastest across a warp: the column-major accesses below hit distinct banks
+                                                       // (with k2 fastest all lanes share a row and the stride-n columns collide 16-way at n = 32)
                 int p1 = sm.pp[k1], q1 = sm.qq[k1], p2 = sm.pp[k2], q2 = sm.qq[k2];
                 bool v1 = q1 < n, v2 = q2 < n;
                 double c1 = sm.c[k1], s1 = sm.s[k1], e1r = sm.er[k1], e1i = sm.ei[k1];

@@ -26,13 +26,16 @@ struct SvtP {
     const double *tau, *rho;                 // per trial; threshold = tau / rho (rho == nullptr -> 1)
     cx<T> *Ys, *Zs;                          // state (N x M per trial)
     cx<T>* W; double* gram;                  // weights, partial Grams [b][nmc][2NN]
+    double* Uprev;                           // eigenvectors of the previous iteration [b][2NN] (warm start of the Jacobi solve)
     double* cgram;                           // conv: [b][2][nmc][2NN]  (X - Htrue, Htrue)
     double* convd;                           // conv: [b][imax] ; slot [b][imax] holds sigma_max(Htrue)^2
     cx<T>* out; long long ld_out;
 };
 
+constexpr int kEigThreads = 256;    // one 2 x 2 block of a 32 x 32 problem per thread and rotation step
+
 template <typename T>
-__global__ void __launch_bounds__(128) k_weights(SvtP<T> p) {
+__global__ void __launch_bounds__(kEigThreads) k_weights(SvtP<T> p) {
     extern __shared__ __align__(16) unsigned char smem[];
     JacobiSmem sm; sm.carve(smem, p.N);
     const int b = blockIdx.x, n = p.N, nn = n * n;
@@ -43,7 +46,18 @@ __global__ void __launch_bounds__(128) k_weights(SvtP<T> p) {
         sm.Are[t] = re; sm.Aim[t] = im;
     }
     __syncthreads();
-    jacobi_hermitian_block(sm, n);
+    // Warm start from the previous iteration's eigenvectors (the mc_svt / mc_admm iterates move slowly, so Q^H G Q is nearly
+    // diagonal and one or two sweeps suffice); every 16th iteration restarts cold to shed drift.  Same scheme as k_svt_weights.
+    double* Up = p.Uprev ? p.Uprev + (size_t)b * 2 * nn : nullptr;
+    const bool warm = Up && p.iter > 0 && (p.iter % 16) != 0;
+    if (warm) {
+        for (int t = threadIdx.x; t < nn; t += blockDim.x) { sm.Ure[t] = Up[t]; sm.Uim[t] = Up[nn + t]; }
+        __syncthreads();
+        jacobi_similarity_block(sm, n, reinterpret_cast<double*>(smem + JacobiSmem::bytes(n)));
+    }
+    // fp32 solves: W is rounded to fp32 (6e-8), so a sweep that starts at a relative off-diagonal norm of 1e-5 (and ends near 1e-10) is the last
+    jacobi_hermitian_block(sm, n, 24, warm, sizeof(T) == 4 ? 1e-10 : 1e-20);
+    if (Up) for (int t = threadIdx.x; t < nn; t += blockDim.x) { Up[t] = sm.Ure[t]; Up[nn + t] = sm.Uim[t]; }
     const double tau = p.rho ? p.tau[b] / p.rho[b] : p.tau[b];
     cx<T>* W = p.W + (size_t)b * nn;
     svt_weights_block(sm, n, tau, [&](int i, int j, double re, double im) { W[i + n * j] = mk<T>((T)re, (T)im); });
@@ -181,7 +195,7 @@ static int run_svt_family(Handle* h, int mode, int mem, int N, int M, int batch,
     auto layout = [&](Arena& a, int nb, SvtP<T>& q) {
         q.W = a.take<cx<T>>((size_t)N * N * nb);
         q.gram = a.take<double>((size_t)nb * q.nmc * NN2);
-        if (mode != MODE_SVT) q.Ys = a.take<cx<T>>(NM * nb);
+        if (mode != MODE_SVT) { q.Ys = a.take<cx<T>>(NM * nb); q.Uprev = a.take<double>((size_t)nb * NN2); }
         if (mode == MODE_MCADMM) q.Zs = a.take<cx<T>>(NM * nb);
         if (want_conv) { q.cgram = a.take<double>((size_t)nb * 2 * q.nmc * NN2); q.convd = a.take<double>((size_t)nb * (imax + 1)); }
         if (host) {
@@ -201,13 +215,13 @@ static int run_svt_family(Handle* h, int mode, int mem, int N, int M, int batch,
         if (probe.off <= budget || chunk_trials == 1) { int rc = ensure_workspace(h, probe.off); if (rc) return rc; break; }
         chunk_trials = (chunk_trials + 1) / 2;
     }
-    const size_t sm_step = smem_of(MC), sm_gram = 2 * (size_t)p.RP * MC * sizeof(T), sm_j = JacobiSmem::bytes(N);
+    const size_t sm_step = smem_of(MC), sm_gram = 2 * (size_t)p.RP * MC * sizeof(T), sm_j = JacobiSmem::bytes(N), sm_w = JacobiSmem::bytes(N) + 2 * sizeof(double) * (size_t)N * N + 16;
     int rc;
     if ((rc = set_smem(h, k_svt_step<T, MODE_SVT>, sm_step))) return rc;
     if ((rc = set_smem(h, k_svt_step<T, MODE_MCSVT>, sm_step))) return rc;
     if ((rc = set_smem(h, k_svt_step<T, MODE_MCADMM>, sm_step))) return rc;
     if ((rc = set_smem(h, k_gram_of<T>, sm_gram))) return rc;
-    if ((rc = set_smem(h, k_weights<T>, sm_j))) return rc;
+    if ((rc = set_smem(h, k_weights<T>, sm_w))) return rc;
     if ((rc = set_smem(h, k_mc_conv<T>, sm_j))) return rc;
     JSTSP_CUDA(h, cudaMemsetAsync(h->d_flag, 0, sizeof(int), st));
     const size_t esz = sizeof(cx<T>);
@@ -241,7 +255,7 @@ static int run_svt_family(Handle* h, int mode, int mem, int N, int M, int batch,
         if (mode == MODE_SVT) {
             q.rho = nullptr;
             JSTSP_LAUNCH(h, PK_OTHER, (k_gram_of<T><<<grid, kThreads, sm_gram, st>>>(q, q.in, q.ld_in, q.gram, 1, 0)));
-            JSTSP_LAUNCH(h, PK_EIG, (k_weights<T><<<nb, 128, sm_j, st>>>(q)));
+            JSTSP_LAUNCH(h, PK_EIG, (k_weights<T><<<nb, kEigThreads, sm_w, st>>>(q)));
             q.iter = 0;
             JSTSP_LAUNCH(h, PK_SVT_STEP, (k_svt_step<T, MODE_SVT><<<grid, kThreads, sm_step, st>>>(q)));
         } else {
@@ -255,7 +269,7 @@ static int run_svt_family(Handle* h, int mode, int mem, int N, int M, int batch,
             }
             for (int it = 0; it < imax; ++it) {
                 q.iter = it;
-                JSTSP_LAUNCH(h, PK_EIG, (k_weights<T><<<nb, 128, sm_j, st>>>(q)));
+                JSTSP_LAUNCH(h, PK_EIG, (k_weights<T><<<nb, kEigThreads, sm_w, st>>>(q)));
                 if (mode == MODE_MCSVT) JSTSP_LAUNCH(h, PK_SVT_STEP, (k_svt_step<T, MODE_MCSVT><<<grid, kThreads, sm_step, st>>>(q)));
                 else JSTSP_LAUNCH(h, PK_SVT_STEP, (k_svt_step<T, MODE_MCADMM><<<grid, kThreads, sm_step, st>>>(q)));
                 if (want_conv) { JSTSP_LAUNCH(h, PK_OTHER, (k_mc_conv<T><<<nb, 128, sm_j, st>>>(q, 0))); }
