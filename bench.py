@@ -189,6 +189,9 @@ def main():
     ap.add_argument("--cpu-trials", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-entry", default="pilots", choices=["pilots", "psi"],
+                    help="HOST-buffer entry of the end-to-end leg: pilots = jstsp_proposed_algorithm_pilots (the sequences s_k travel), "
+                         "psi = jstsp_proposed_algorithm_psi (Psi_bar travels); the other one is measured alongside")
     ap.add_argument("--entry", default="psi", choices=["psi", "dense"],
                     help="psi: jstsp_proposed_algorithm_psi (dictionary given by its factors Dt, Psi_bar as the reference's drivers hold them); "
                          "dense: jstsp_proposed_algorithm (dense B, the reference function's own argument list)")
@@ -303,6 +306,7 @@ def main():
             edata = data
         pin = lambda t: t[:ne].cpu().contiguous().pin_memory()
         hsubY, hOm, hB = pin(edata["subY"]), pin(edata["Omega"]), pin(edata["Psi" if use_psi else "B"])
+        hPil = pin(edata["pilots"]) if use_psi else None
         hA = edata["A"].cpu().contiguous().pin_memory()
         hDt = edata["Dt"].cpu().contiguous().pin_memory()
         hty, hts, hrho = (edata[k][:ne].cpu().contiguous().pin_memory() for k in ("tau_Y", "tau_Z", "rho"))
@@ -314,7 +318,14 @@ def main():
         dt = _lib.F32 if args.precision == "f32" else _lib.F64
         vp = lambda t: C.c_void_p(t.data_ptr())
 
+        e2e_entry = [args.e2e_entry if use_psi else "dense"]
+
         def host_step():
+            if use_psi and e2e_entry[0] == "pilots":
+                rc = _lib.lib.jstsp_proposed_algorithm_pilots(eng.h.ptr, C.byref(d), dt, _lib.HOST, vp(hsubY), vp(hOm), None, vp(hA), vp(hDt), 0,
+                                                              vp(hPil), s.Nt * M, s.Nt, s.L, vp(hty), vp(hts), vp(hrho), vp(hS), None, None)
+                eng.h.check(rc)
+                return
             if use_psi:
                 rc = _lib.lib.jstsp_proposed_algorithm_psi(eng.h.ptr, C.byref(d), dt, _lib.HOST, vp(hsubY), vp(hOm), None, vp(hA), vp(hDt), 0,
                                                            vp(hB), s.Nt * M * s.L, s.Nt, s.L, vp(hty), vp(hts), vp(hrho), vp(hS), None, None)
@@ -326,22 +337,32 @@ def main():
 
         if args.e2e_pass:
             eng.h.set_chunk(args.e2e_pass)
-        for _ in range(3):
-            host_step()
-        barrier()
-        t0 = time.perf_counter()
         ksteps = max(3, args.steps // 2 + 1)
-        for _ in range(ksteps):
-            host_step()
-        torch.cuda.synchronize()
-        dt_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt_s, op=dist.ReduceOp.MAX)
         esz = 8 if args.precision == "f32" else 16
-        h2d = ne * (N * M * esz + N * M * esz // 2 + P * M * esz + 24) + N * G * esz
-        d2h = ne * G * P * esz
-        e2e = dict(value=ne * world * ksteps / float(dt_s.item()), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                   trials_per_step=ne, timing="host wall clock around the synchronous C-ABI call, max over ranks")
+
+        def e2e_run(entry):
+            e2e_entry[0] = entry
+            for _ in range(3):
+                host_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(ksteps):
+                host_step()
+            torch.cuda.synchronize()
+            dt_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dt_s, op=dist.ReduceOp.MAX)
+            dict_bytes = {"pilots": s.Nt * M * esz, "psi": s.Nt * M * s.L * esz, "dense": P * M * esz}[entry]
+            h2d = ne * (N * M * esz + N * M * esz // 2 + dict_bytes + 24) + N * G * esz + (s.Nt * s.Nt * esz if entry != "dense" else 0)
+            return dict(value=ne * world * ksteps / float(dt_s.item()), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=ne * G * P * esz,
+                        trials_per_step=ne, timing="host wall clock around the synchronous C-ABI call, max over ranks",
+                        entry={"pilots": "jstsp_proposed_algorithm_pilots (pilot sequences s_k, Nt x M per trial)",
+                               "psi": "jstsp_proposed_algorithm_psi (Psi_bar, Nt x M x L per trial)", "dense": "jstsp_proposed_algorithm (dense B)"}[entry])
+
+        e2e = e2e_run(e2e_entry[0])
+        if use_psi:      # the other structured entry on the same trials, for the record
+            alt = e2e_run("psi" if args.e2e_entry == "pilots" else "pilots")
+            e2e["other_entry"] = dict(entry=alt["entry"], value=alt["value"], h2d_bytes_per_step=alt["h2d_bytes_per_step"])
 
     if rank != 0:
         if world > 1:

@@ -131,6 +131,16 @@ int jstsp_proposed_algorithm_psi(jstsp_handle* h, const jstsp_admm_desc* d, int 
                                  const void* Dt, long long ld_Dt, const void* Psi_bar, long long ld_Psi, int Nt, int L,
                                  const double* tau_Y, const double* tau_S, const double* rho,
                                  void* S, void* Y, void* conv);
+/* Same estimator, fed the pilot SEQUENCES instead of Psi_bar: pilots is Nt x M per trial, row k = s_k, the vector the drivers
+ * pass to toeplitz() at plot_errorVSsnr.m:63-67 (= Psi_i(1,:,k)).  Psi_bar(k,:,l) = row l of toeplitz(s_k) (proposed_hbf.m:15-18,
+ * MATLAB's Hermitian rule below the diagonal) is expanded on the device, so a HOST call moves L times fewer dictionary bytes.
+ * Results are identical to jstsp_proposed_algorithm_psi on the expanded Psi_bar (same kernels from there on). */
+int jstsp_proposed_algorithm_pilots(jstsp_handle* h, const jstsp_admm_desc* d, int dtype, int mem,
+                                    const void* subY, const void* omega, const int* indx_S, const void* A,
+                                    const void* Dt, long long ld_Dt, const void* pilots, long long ld_pilots, int Nt, int L,
+                                    const double* tau_Y, const double* tau_S, const double* rho,
+                                    void* S, void* Y, void* conv);
+
 /* Path taken by the last jstsp_proposed_algorithm_psi call on this handle: 1 = dense kernels on the materialised
  * dictionary, 2 = Psi-domain tcgen05 kernel (0 = no call yet). */
 int jstsp_last_path(const jstsp_handle* h);

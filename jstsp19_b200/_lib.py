@@ -65,6 +65,7 @@ def _load():
     lib.jstsp_proposed_algorithm.argtypes = [vp, C.POINTER(AdmmDesc), i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.jstsp_proposed_algorithm_angles.argtypes = [vp, C.POINTER(AdmmDesc), i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.jstsp_proposed_algorithm_psi.argtypes = [vp, C.POINTER(AdmmDesc), i, i, vp, vp, vp, vp, vp, ll, vp, ll, i, i, vp, vp, vp, vp, vp, vp]
+    lib.jstsp_proposed_algorithm_pilots.argtypes = [vp, C.POINTER(AdmmDesc), i, i, vp, vp, vp, vp, vp, ll, vp, ll, i, i, vp, vp, vp, vp, vp, vp]
     lib.jstsp_last_path.argtypes = [vp]
     lib.jstsp_svt.argtypes = [vp, i, i, i, i, i, vp, ll, vp, vp, ll]
     lib.jstsp_mc_svt.argtypes = [vp, i, i, i, i, i, i, vp, ll, vp, ll, vp, vp, vp, ll]
@@ -88,7 +89,7 @@ lib = _load()
 EXPORTED = [
     "jstsp_create", "jstsp_destroy", "jstsp_last_error", "jstsp_version", "jstsp_set_stream",
     "jstsp_synchronize", "jstsp_launch_count", "jstsp_set_chunk", "jstsp_profile", "jstsp_profile_read", "jstsp_debug_buffer",
-    "jstsp_proposed_algorithm", "jstsp_proposed_algorithm_angles", "jstsp_proposed_algorithm_psi", "jstsp_last_path",
+    "jstsp_proposed_algorithm", "jstsp_proposed_algorithm_angles", "jstsp_proposed_algorithm_psi", "jstsp_proposed_algorithm_pilots", "jstsp_last_path",
     "jstsp_svt", "jstsp_mc_svt", "jstsp_mc_admm", "jstsp_omp", "jstsp_omp_kron", "jstsp_somp", "jstsp_sparse_admm", "jstsp_vamp",
     "jstsp_wideband_mmwave_channel", "jstsp_measure", "jstsp_nmse", "jstsp_admm_parameters", "jstsp_log2det_rate",
 ]

@@ -57,7 +57,7 @@ def _type_code(type_):
     return _lib.APPROXIMATE if type_ == "approximate" else _lib.STD
 
 
-def _admm(subY, Omega, indx_S, A, B, Imax, tau_Y, tau_S, rho, type_, precision, handle, nargout, psi=None):
+def _admm(subY, Omega, indx_S, A, B, Imax, tau_Y, tau_S, rho, type_, precision, handle, nargout, psi=None, pilots_L=None):
     h = handle or default_handle()
     cd, rd = _CD[precision], _RD[precision]
     bs = _batch_of(subY, 2)
@@ -75,8 +75,12 @@ def _admm(subY, Omega, indx_S, A, B, Imax, tau_Y, tau_S, rho, type_, precision, 
         # Dt (Nt, Gt) [or (b, Nt, Gt)], Psi_bar (Nt, M, L) [or (b, Nt, M, L)] in MATLAB indexing -> column-major storage
         Dt, Psi_bar = np.asarray(psi[0]), np.asarray(psi[1])
         Dm = _cm(Dt, cd)
-        Pm = np.ascontiguousarray(np.moveaxis(Psi_bar, (-3, -2, -1), (-1, -2, -3)), dtype=cd)      # (..., L, M, Nt)
-        Nt, Gt, L = Dm.shape[-1], Dm.shape[-2], Pm.shape[-3]
+        if pilots_L is None:
+            Pm = np.ascontiguousarray(np.moveaxis(Psi_bar, (-3, -2, -1), (-1, -2, -3)), dtype=cd)  # (..., L, M, Nt)
+            Nt, Gt, L = Dm.shape[-1], Dm.shape[-2], Pm.shape[-3]
+        else:
+            Pm = _cm(Psi_bar, cd)                                                                  # pilot sequences (..., M, Nt)
+            Nt, Gt, L = Dm.shape[-1], Dm.shape[-2], int(pilots_L)
         G, P = Am.shape[-2], L * Gt
         Bm = None
         bad = Pm.shape[-1] != Nt or Pm.shape[-2] != M
@@ -100,7 +104,11 @@ def _admm(subY, Omega, indx_S, A, B, Imax, tau_Y, tau_S, rho, type_, precision, 
                                   else np.asarray(indx_S).reshape(1, -1), dtype=np.int32)
         d.n_indx = ix.shape[1]
         d.ld_indx = ix.shape[1] if ix.shape[0] == batch and batch > 1 else 0
-    if psi is not None:
+    if psi is not None and pilots_L is not None:
+        rc = _lib.lib.jstsp_proposed_algorithm_pilots(h.ptr, C.byref(d), _DT[precision], _lib.HOST, _ptr(sY), _ptr(om), _ptr(ix), _ptr(Am),
+                                                      _ptr(Dm), Nt * Gt if Dm.ndim == 3 else 0, _ptr(Pm), Nt * M if Pm.ndim == 3 else 0, Nt, L,
+                                                      dp(tY), dp(tS), dp(rh), _ptr(S), _ptr(Y), _ptr(conv))
+    elif psi is not None:
         rc = _lib.lib.jstsp_proposed_algorithm_psi(h.ptr, C.byref(d), _DT[precision], _lib.HOST, _ptr(sY), _ptr(om), _ptr(ix), _ptr(Am),
                                                    _ptr(Dm), Nt * Gt if Dm.ndim == 3 else 0, _ptr(Pm), Nt * M * L if Pm.ndim == 4 else 0, Nt, L,
                                                    dp(tY), dp(tS), dp(rh), _ptr(S), _ptr(Y), _ptr(conv))
@@ -142,6 +150,14 @@ def proposed_algorithm_psi(subY, Omega, A, Dt, Psi_bar, Imax, tau_Y, tau_S, rho,
     wideband_mmwave_channel.m:1 and ``Psi_bar`` (Nt x M x L) from proposed_hbf.m:1.  Same outputs as
     ``proposed_algorithm(subY, Omega, A, B, ...)`` with that ``B``; Toeplitz 4-QAM pilots take the tensor-core path."""
     return _admm(subY, Omega, indx_S, A, None, Imax, tau_Y, tau_S, rho, type, precision, handle, nargout, psi=(Dt, Psi_bar))
+
+
+def proposed_algorithm_pilots(subY, Omega, A, Dt, pilots, L, Imax, tau_Y, tau_S, rho, type, indx_S=None, *,
+                              precision="f64", handle=None, nargout=3):
+    """:func:`proposed_algorithm_psi` fed the pilot sequences themselves: ``pilots`` is Nt x M with row k = ``s_k``, the vector the
+    drivers hand to ``toeplitz`` (plot_errorVSsnr.m:63-67); ``Psi_bar(k,:,l)`` = row l of ``toeplitz(s_k)`` (proposed_hbf.m:15-18) is
+    formed on the device, so the call moves L times fewer dictionary bytes.  Same outputs."""
+    return _admm(subY, Omega, indx_S, A, None, Imax, tau_Y, tau_S, rho, type, precision, handle, nargout, psi=(Dt, pilots), pilots_L=L)
 
 
 def svt(Y, tau, *, precision="f64", handle=None):

@@ -637,7 +637,19 @@ static bool tc_enabled() {
     return e ? atoi(e) != 0 : false;
 }
 // structured dictionary B = (I (x) Dt') Psi_bar of jstsp_proposed_algorithm_psi (host-level description)
-struct PsiArgs { const void* Dt; long long ld_Dt; const void* Psi; long long ld_Psi; int Nt, Gt, L; };
+struct PsiArgs { const void* Dt; long long ld_Dt; const void* Psi; long long ld_Psi; int Nt, Gt, L; int pilots; };   // pilots: Psi holds the sequences s_k (Nt x M), Psi_bar is expanded on the device
+// Psi_bar(k, j, l) = row l of toeplitz(s_k) at column j (proposed_hbf.m:15-18, plot_errorVSsnr.m:63-67): s_k(j - l) for j >= l, conj(s_k(l - j)) below the diagonal
+template <typename T>
+__global__ void __launch_bounds__(256) k_expand_pilots(const cx<T>* __restrict__ pil, long long ld_pil, cx<T>* __restrict__ psi, long long ld_psi, int Nt, int M, int L) {
+    const int b = blockIdx.y;
+    const cx<T>* s = pil + (long long)b * ld_pil;
+    cx<T>* o = psi + (long long)b * ld_psi;
+    const size_t n = (size_t)Nt * M * L;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % Nt), j = (int)((i / Nt) % M), l = (int)(i / ((size_t)Nt * M)), t = j - l;
+        o[i] = t >= 0 ? s[k + (size_t)Nt * t] : conj(s[k + (size_t)Nt * (-t)]);
+    }
+}
 static bool psi_fast_enabled() {
     const char* e = getenv("JSTSP_PSI_DENSE");      // developer switch: force the materialised-B kernels
     return !(e && atoi(e) != 0);
@@ -719,7 +731,8 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
     cx<T>* bt_ws = nullptr;
     cx<T>* b_ws = nullptr;               // structured entry: the materialised dictionary
     psi::In pin{};                       // structured entry: device-side description (fp32 fast path)
-    const cx<T> *psi_dev = nullptr, *dt_dev = nullptr;
+    const cx<T> *psi_dev = nullptr, *dt_dev = nullptr, *pil_dev = nullptr;
+    cx<T>* psi_exp = nullptr;            // pilots entry with DEVICE buffers: the expanded Psi_bar
     float* asop_ws = nullptr;            // tensor-core path: A S expanded into the pass-1 operand image (hi | lo)
     const int Wn = cta_width(p.NG);
     const long long Mpad = (long long)ceil_div(M, Wn) * Wn;      // B^T is stored in Wn-wide column tiles
@@ -744,6 +757,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
         if (fast_xs && !use_tc) bt_ws = a.take<cx<T>>((size_t)P * Mpad * (sharedB ? 1 : nb));    // (unused once the structured path is confirmed)
         if (ps) {
             b_ws = a.take<cx<T>>((size_t)P * M * (sharedB ? 1 : nb));
+            if (ps->pilots && !host) psi_exp = a.take<cx<T>>((size_t)ps->Nt * M * ps->L * (ps->ld_Psi ? nb : 1));
             if (psi_shape) {
                 const int nE = ps->ld_Psi ? nb : 1;
                 pin.E = a.take<unsigned short>((size_t)nE * psi::NKG * (M + 8) * 8);
@@ -776,9 +790,10 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
                 const cx<T>* s_B = ps ? nullptr : a.take<cx<T>>((size_t)P * M * (d->ld_B ? nb : 1));
                 const cx<T>* s_Psi = ps ? a.take<cx<T>>((size_t)ps->Nt * M * ps->L * (ps->ld_Psi ? nb : 1)) : nullptr;
                 const cx<T>* s_Dt = ps ? a.take<cx<T>>((size_t)ps->Nt * ps->Gt * (ps->ld_Dt ? nb : 1)) : nullptr;
+                const cx<T>* s_Pil = (ps && ps->pilots) ? a.take<cx<T>>((size_t)ps->Nt * M * (ps->ld_Psi ? nb : 1)) : nullptr;
                 const double *s_rho = a.take<double>(nb), *s_tauY = a.take<double>(nb), *s_tauS = a.take<double>(nb);
                 const int* s_indx = angles ? a.take<int>((size_t)d->n_indx * (d->ld_indx ? nb : 1)) : nullptr;
-                if (use) { psi_dev = s_Psi; dt_dev = s_Dt; }
+                if (use) { psi_dev = s_Psi; dt_dev = s_Dt; pil_dev = s_Pil; }
                 if (use) { q.subY = s_subY; q.omega = s_omega; q.A = s_A; q.B = s_B; q.rho = s_rho; q.tauY = s_tauY; q.tauS = s_tauS; q.indx = s_indx; }
             }
             if (Y_) q.Yout = a.take<cx<T>>(NM * nb);
@@ -856,6 +871,12 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
             JSTSP_CUDA(h, up(q.A, A_, (size_t)N * G, d->ld_A, esz));
             if (!ps) JSTSP_CUDA(h, up(q.B, B_, (size_t)P * M, d->ld_B, esz));
             else {
+                if (ps->pilots) {   // the sequences travel (Nt x M per trial, L times fewer bytes); Psi_bar is expanded on the device, on the copy stream
+                    JSTSP_CUDA(h, up(pil_dev, ps->Psi, (size_t)ps->Nt * M, ps->ld_Psi, esz));
+                    dim3 g(4 * h->sm_count, ps->ld_Psi ? nb : 1);
+                    k_expand_pilots<T><<<g, 256, 0, cs>>>(pil_dev, ps->ld_Psi ? (long long)ps->Nt * M : 0, const_cast<cx<T>*>(psi_dev), ps->ld_Psi ? (long long)ps->Nt * M * ps->L : 0, ps->Nt, M, ps->L);
+                    h->launches++;
+                } else
                 JSTSP_CUDA(h, up(psi_dev, ps->Psi, (size_t)ps->Nt * M * ps->L, ps->ld_Psi, esz));
                 JSTSP_CUDA(h, up(dt_dev, ps->Dt, (size_t)ps->Nt * ps->Gt, ps->ld_Dt, esz));
             }
@@ -883,8 +904,12 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
         bool use_psi = false;
         psi::Maps pmaps;
         if (ps) {
-            const long long ldP = ps->ld_Psi ? (host ? (long long)ps->Nt * M * ps->L : ps->ld_Psi) : 0, ldD = ps->ld_Dt ? (host ? (long long)ps->Nt * ps->Gt : ps->ld_Dt) : 0;
-            const cx<T>* Pd = host ? psi_dev : (const cx<T>*)ps->Psi + (long long)b0 * ps->ld_Psi;
+            const long long ldP = ps->ld_Psi ? ((host || ps->pilots) ? (long long)ps->Nt * M * ps->L : ps->ld_Psi) : 0, ldD = ps->ld_Dt ? (host ? (long long)ps->Nt * ps->Gt : ps->ld_Dt) : 0;
+            if (ps->pilots && !host) {
+                dim3 g(4 * h->sm_count, ps->ld_Psi ? nb : 1);
+                JSTSP_LAUNCH(h, PK_SETUP, (k_expand_pilots<T><<<g, 256, 0, st>>>((const cx<T>*)ps->Psi + (long long)b0 * ps->ld_Psi, ps->ld_Psi, psi_exp, ldP, ps->Nt, M, ps->L)));
+            }
+            const cx<T>* Pd = host ? psi_dev : (ps->pilots ? psi_exp : (const cx<T>*)ps->Psi + (long long)b0 * ps->ld_Psi);
             const cx<T>* Dd = host ? dt_dev : (const cx<T>*)ps->Dt + (long long)b0 * ps->ld_Dt;
             if constexpr (std::is_same<T, float>::value) {
                 if (psi_shape) {
@@ -1107,7 +1132,25 @@ extern "C" int jstsp_proposed_algorithm_psi(jstsp_handle* h, const jstsp_admm_de
     if (!d) return fail(h, JSTSP_E_ARG, "NULL descriptor");
     if (L <= 0 || Nt <= 0 || d->P % L != 0) return fail(h, JSTSP_E_ARG, "structured dictionary: P must be a multiple of L");
     JSTSP_CUDA(h, cudaSetDevice(h->device));
-    PsiArgs ps{Dt, ld_Dt, Psi_bar, ld_Psi, Nt, d->P / L, L};
+    PsiArgs ps{Dt, ld_Dt, Psi_bar, ld_Psi, Nt, d->P / L, L, 0};
+    h->last_path = 1;
+    const bool angles = indx_S != nullptr;
+    if (dtype == JSTSP_F32) return run_admm<float>(h, d, mem, subY, omega, indx_S, A, nullptr, tau_Y, tau_S, rho, S, Y, conv, angles, &ps);
+    if (dtype == JSTSP_F64) return run_admm<double>(h, d, mem, subY, omega, indx_S, A, nullptr, tau_Y, tau_S, rho, S, Y, conv, angles, &ps);
+    return fail(h, JSTSP_E_ARG, "unknown dtype");
+}
+
+extern "C" int jstsp_proposed_algorithm_pilots(jstsp_handle* h, const jstsp_admm_desc* d, int dtype, int mem,
+                                               const void* subY, const void* omega, const int* indx_S, const void* A,
+                                               const void* Dt, long long ld_Dt, const void* pilots, long long ld_pilots, int Nt, int L,
+                                               const double* tau_Y, const double* tau_S, const double* rho,
+                                               void* S, void* Y, void* conv) {
+    if (!h) return JSTSP_E_ARG;
+    if (!d) return fail(h, JSTSP_E_ARG, "NULL descriptor");
+    if (L <= 0 || Nt <= 0 || d->P % L != 0) return fail(h, JSTSP_E_ARG, "structured dictionary: P must be a multiple of L");
+    if (L > d->M) return fail(h, JSTSP_E_ARG, "more delay taps than training columns");
+    JSTSP_CUDA(h, cudaSetDevice(h->device));
+    PsiArgs ps{Dt, ld_Dt, pilots, ld_pilots, Nt, d->P / L, L, 1};
     h->last_path = 1;
     const bool angles = indx_S != nullptr;
     if (dtype == JSTSP_F32) return run_admm<float>(h, d, mem, subY, omega, indx_S, A, nullptr, tau_Y, tau_S, rho, S, Y, conv, angles, &ps);

@@ -119,7 +119,9 @@ def build_from_draws(s: Shape, coef, u_r, u_t, noise_unit, sym_idx, mask_rank, s
                 B=cm(B), Zbar=cm(Zbar), tau_Y=tau_Y.double().contiguous(), tau_Z=tau_Z.double().contiguous(),
                 rho=rho.double().contiguous(), H=H,
                 # factors of B as the drivers hold them: Dt (1,Gt,Nt) and Psi_bar (b,L,M,Nt), per-trial column-major
-                Dt=Dt.T.contiguous().to(cdtype)[None], Psi=Psi.transpose(2, 3).contiguous().to(cdtype))
+                Dt=Dt.T.contiguous().to(cdtype)[None], Psi=Psi.transpose(2, 3).contiguous().to(cdtype),
+                # the pilot sequences themselves (b,M,Nt): row k of the Nt x M matrix is s_k (plot_errorVSsnr.m:63-67)
+                pilots=sk.transpose(1, 2).contiguous().to(cdtype))
 
 
 def make_batch(s: Shape, batch, snr_db, seed, first_trial=0, device="cuda", cdtype=torch.complex64):

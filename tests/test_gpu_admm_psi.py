@@ -156,3 +156,34 @@ def test_host_passes_ping_pong():
         S0, _ = _oracle(t, Imax=30)
         assert _rel(S1[k], S0) < TOL["f32"]["S"], (k, _rel(S1[k], S0))
     h.close()
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_pilots_entry_equals_psi_entry(precision):
+    """jstsp_proposed_algorithm_pilots expands Psi_bar(k,:,l) = row l of toeplitz(s_k) (proposed_hbf.m:15-18) on the device:
+    same result as handing over Psi_bar, at the metric shape (tensor-core path for f32) and at the default shape."""
+    import jstsp19_b200 as jb
+    from jstsp19_b200._lib import default_handle
+    for shape, imax in ((fx.METRIC, 40), (fx.CONFIG0, 60)):
+        t = fx.make_trial(shape, 5.0, 91)
+        a = (t["subY"], t["Omega"], t["A"], t["Dt"])
+        b = (imax, t["tau_Y"], t["tau_Z"], t["rho"], "approximate")
+        S0, Y0 = jb.proposed_algorithm_psi(*a, t["Psi_bar"], *b, precision=precision, nargout=2)
+        path0 = default_handle().last_path
+        S1, Y1 = jb.proposed_algorithm_pilots(*a, t["pilots"], shape.L, *b, precision=precision, nargout=2)
+        assert default_handle().last_path == path0
+        assert np.array_equal(S1, S0) and np.array_equal(Y1, Y0)            # identical kernels on identical device inputs
+    Sa = jb.proposed_algorithm_pilots(*a, t["pilots"], shape.L, *b, t["indx_S"], precision=precision, nargout=1)
+    Sb = jb.proposed_algorithm_psi(*a, t["Psi_bar"], *b, t["indx_S"], precision=precision, nargout=1)
+    assert np.array_equal(Sa, Sb)
+
+
+def test_pilots_entry_batched_host_passes():
+    import jstsp19_b200 as jb
+    trials = [fx.make_trial(fx.METRIC, 5.0, 200 + k) for k in range(3)]
+    st = lambda k: np.stack([t[k] for t in trials])
+    args = (st("subY"), st("Omega"), trials[0]["A"], trials[0]["Dt"])
+    par = (30, [t["tau_Y"] for t in trials], [t["tau_Z"] for t in trials], [t["rho"] for t in trials], "approximate")
+    S0 = jb.proposed_algorithm_psi(*args, st("Psi_bar"), *par, precision="f32", nargout=1)
+    S1 = jb.proposed_algorithm_pilots(*args, st("pilots"), 4, *par, precision="f32", nargout=1)
+    assert np.array_equal(S1, S0)

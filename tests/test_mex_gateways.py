@@ -208,6 +208,16 @@ def test_omp_gateway_cell_output_and_support():
 
 
 @pytest.mark.gpu
+def test_proposed_algorithm_pilots_gateway():
+    """The pilot sequences s_k (rows of an Nt x M matrix) instead of Psi_bar: same numbers as the oracle on the dense B."""
+    t = fx.make_trial(fx.CONFIG0, 5.0, 14)
+    g = mh.Gateway("proposed_algorithm_pilots")
+    S1, Y1 = g(2, t["subY"], t["Omega"], t["A"], t["Dt"], t["pilots"], float(fx.CONFIG0.L), 40, t["tau_Y"], t["tau_Z"], t["rho"], "approximate")
+    S0, Y0, _ = est.proposed_algorithm_structured(t["subY"], t["Omega"], t["A"], t["B"], 40, t["tau_Y"], t["tau_Z"], t["rho"], "approximate", want_conv=False)
+    assert _rel(S1, S0) < 1e-8 and _rel(Y1, Y0) < 1e-8
+
+
+@pytest.mark.gpu
 def test_omp_kron_and_somp_gateways():
     rng = np.random.default_rng(6)
     N, M, G, P = 8, 12, 10, 9
