@@ -189,6 +189,7 @@ def main():
     ap.add_argument("--cpu-trials", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the full trial-loop leg (channel + measurement + parameters + estimator + NMSE on the device)")
     ap.add_argument("--e2e-entry", default="pilots", choices=["pilots", "psi"],
                     help="HOST-buffer entry of the end-to-end leg: pilots = jstsp_proposed_algorithm_pilots (the sequences s_k travel), "
                          "psi = jstsp_proposed_algorithm_psi (Psi_bar travels); the other one is measured alongside")
@@ -293,6 +294,30 @@ def main():
     mc = MonteCarlo(dev)
     mc.add(synth.nmse_spectral(S, data["Zbar"]))
     stats = mc.reduce()
+
+    # ---- the whole trial loop body on the device through the library (SURVEY 8d metric ii): channel + measurement synthesis +
+    #      parameters + estimator + NMSE, draws included; device-timed, max over ranks ----
+    pipeline = None
+    if use_psi and not args.no_pipeline:
+        from jstsp19_b200.engine import TrialPipeline
+        pipe = TrialPipeline(s, local, args.precision, engine=eng)
+        psnr = torch.tensor([SNR_SWEEP[(first + k) % len(SNR_SWEEP)] for k in range(nb)], dtype=torch.float64)
+        pmc = MonteCarlo(dev)
+        pipe.run(nb, psnr, seed=20190913, first_trial=first)
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for k in range(2):
+            pmc.add(pipe.run(nb, psnr, seed=20190913 + 1 + k, first_trial=first))
+        p1.record()
+        barrier()
+        pms = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(pms, op=dist.ReduceOp.MAX)
+        pst = pmc.reduce()
+        pipeline = dict(value=nb * world * 2 / (float(pms.item()) * 1e-3), unit="trials/s", ms_per_step=float(pms.item()) / 2,
+                        stages="draws (torch) -> jstsp_wideband_mmwave_channel -> jstsp_measure -> jstsp_admm_parameters -> jstsp_proposed_algorithm_pilots -> jstsp_nmse",
+                        mean_nmse=pst["mean_nmse"], trials=pst["trials"], flagged=pst["flagged"])
 
     # ---- end-to-end through the HOST-buffer C ABI (pinned host memory) ----
     e2e = None
@@ -422,7 +447,7 @@ def main():
                             parallelism=f"trials sharded over {world} GPU(s), one NCCL all-reduce of NMSE sums"),
                 clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu,
                 algorithmic_gflop_per_estimate=F_est / 1e9, achieved_tflops_whole_step=F_est * value / 1e12,
-                nmse=stats, other_entry=other)
+                nmse=stats, other_entry=other, pipeline=pipeline)
     emit(line)
     if world > 1:
         dist.destroy_process_group()

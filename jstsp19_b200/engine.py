@@ -16,7 +16,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import AdmmDesc, Handle
+from ._lib import AdmmDesc, Handle, MeasDesc
 
 _CD = {"f32": torch.complex64, "f64": torch.complex128}
 _RD = {"f32": torch.float32, "f64": torch.float64}
@@ -111,9 +111,100 @@ class AdmmEngine:
         self.h.check(rc)
         return S_out
 
+    def proposed_algorithm_pilots(self, subY, Omega, A, Dt, pilots, L, imax, tau_Y, tau_S, rho, type="approximate", indx_S=None, S_out=None, Y_out=None):
+        """:meth:`proposed_algorithm_psi` fed the pilot sequences (jstsp_proposed_algorithm_pilots): ``pilots`` (b|1, M, Nt) = per-trial
+        column-major Nt x M with row k = s_k; Psi_bar is expanded inside the library."""
+        cd, rdt = _CD[self.precision], _RD[self.precision]
+        b, M, N = subY.shape
+        G = A.shape[-2]
+        Gt, Nt = Dt.shape[-2], Dt.shape[-1]
+        P = int(L) * Gt
+        for t, dt in ((subY, cd), (A, cd), (Dt, cd), (pilots, cd), (Omega, rdt), (tau_Y, torch.float64), (tau_S, torch.float64), (rho, torch.float64)):
+            if t.dtype != dt or not t.is_contiguous() or t.device != self.device:
+                raise ValueError("engine tensors must be contiguous, on the engine's device, and of the engine's precision")
+        if pilots.shape[-1] != Nt or pilots.shape[-2] != M:
+            raise ValueError("pilots must be (b|1, M, Nt)")
+        if S_out is None:
+            S_out = torch.empty(b, P, G, dtype=cd, device=self.device)
+        d = AdmmDesc()
+        d.N, d.M, d.G, d.P, d.imax, d.batch = N, M, G, P, int(imax), b
+        d.type = _lib.APPROXIMATE if type == "approximate" else _lib.STD
+        d.ld_subY = N * M
+        d.ld_omega = N * M if Omega.shape[0] == b else 0
+        d.ld_A = N * G if A.shape[0] == b else 0
+        d.ld_S, d.ld_Y, d.ld_conv = G * P, N * M, 0
+        if indx_S is not None:
+            d.n_indx = indx_S.shape[-1]
+            d.ld_indx = indx_S.shape[-1] if indx_S.dim() == 2 and indx_S.shape[0] == b else 0
+        self._bind_stream()
+        rc = _lib.lib.jstsp_proposed_algorithm_pilots(self.h.ptr, C.byref(d), _DT[self.precision], _lib.DEVICE, _p(subY), _p(Omega), _p(indx_S), _p(A),
+                                                      _p(Dt), Nt * Gt if (Dt.dim() == 3 and Dt.shape[0] == b and b > 1) else 0,
+                                                      _p(pilots), Nt * M if (pilots.dim() == 3 and pilots.shape[0] == b and b > 1) else 0, Nt, int(L),
+                                                      _p(tau_Y), _p(tau_S), _p(rho), _p(S_out), _p(Y_out), None)
+        self.h.check(rc)
+        return S_out
+
     @property
     def launches(self):
         return self.h.launches
+
+
+class TrialPipeline:
+    """The body of the reference's Monte-Carlo loop (plot_errorVSsnr.m:56-67,124-141) for a batch of trials, device-resident and
+    entirely through the library's C ABI: wideband_mmwave_channel -> proposed_hbf (pilots, noise, ZC combiner, sampling mask) ->
+    tau_Y / tau_Z / rho -> proposed_algorithm -> NMSE.  torch only draws the random numbers and holds the buffers."""
+
+    def __init__(self, shape, device=0, precision="f32", engine=None):
+        self.s = shape
+        self.eng = engine or AdmmEngine(device, precision)
+        self.device, self.precision = self.eng.device, self.eng.precision
+        from . import synth
+        cd = _CD[self.precision]
+        s = shape
+        W = synth._zc(s.Nr, self.device, torch.complex128)                                   # createBeamformer(Nr,'ZC') (plot_errorVSsnr.m:124)
+        Dr = synth._dft(s.Nr, s.Nr, self.device, torch.complex128)
+        self.W = W.T.contiguous().to(cd)[None]                                                # (1, Nr, Nr) column-major
+        self.A = (W.conj().T @ Dr).T.contiguous().to(cd)[None]                                # A = W_e' Dr (:132), W_e = W (Mr_e = Nr)
+        self.Dt = synth._dft(s.Nt, s.Nt, self.device, torch.complex128).T.contiguous().to(cd)[None]
+
+    def run_from_draws(self, coef, u_r, u_t, noise_unit, sym_idx, mask_rank, sigma2, imax=100, keep=False):
+        s, dev, h = self.s, self.device, self.eng.h
+        cd, rd, dt = _CD[self.precision], _RD[self.precision], _DT[self.precision]
+        b = coef.shape[0]
+        Nr, Nt, L, M, P = s.Nr, s.Nt, s.L, s.M, s.P
+        self.eng._bind_stream()
+        lib = _lib.lib
+        # draws in the reference's order (wideband_mmwave_channel.m:19-22): (randn, randn) and (rand, rand) per (tap, ray)
+        normals = (torch.view_as_real(coef.to(torch.complex128)) * (2.0 ** 0.5)).contiguous()           # (b, L, Np, 2)
+        uniforms = torch.stack([u_r.double(), u_t.double()], dim=-1).contiguous()
+        H = torch.empty(b, L, Nt, Nr, dtype=cd, device=dev)
+        Zbar = torch.empty(b, P, Nr, dtype=cd, device=dev)
+        h.check(lib.jstsp_wideband_mmwave_channel(h.ptr, dt, _lib.DEVICE, L, Nr, Nt, s.ncl, s.nray, Nr, Nt, b, _p(normals), _p(uniforms),
+                                                  _p(H), _p(Zbar), None, None, None, None))
+        qam = torch.tensor([1 + 1j, -1 + 1j, 1 - 1j, -1 - 1j], dtype=torch.complex128, device=dev) / (2.0 ** 0.5)   # qam4mod.m:7-8
+        pilots = qam[sym_idx].transpose(1, 2).contiguous().to(cd)                                        # (b, M, Nt): row k = s_k
+        noise = (noise_unit.to(torch.complex128) * torch.sqrt(sigma2.double())[:, None, None]).transpose(1, 2).contiguous().to(cd)   # :60
+        perm = (mask_rank.argsort(dim=1).transpose(1, 2) + 1).to(torch.int32).contiguous()               # (b, M, Nr): rows in sampling order
+        md = MeasDesc()
+        md.Nr, md.Nt, md.L, md.T, md.Wc, md.Lr, md.psi_mode, md.Tp, md.batch = Nr, Nt, L, M, Nr, s.Mr, 1, M, b
+        md.ld_H, md.ld_N, md.ld_Psi, md.ld_W = Nr * Nt * L, Nr * M, Nt * M, 0
+        subY = torch.empty(b, M, Nr, dtype=cd, device=dev)
+        Omega = torch.empty(b, M, Nr, dtype=rd, device=dev)
+        h.check(lib.jstsp_measure(h.ptr, C.byref(md), dt, _lib.DEVICE, _p(H), _p(noise), _p(pilots), _p(self.W), _p(perm),
+                                  _p(subY), None, None, _p(Omega), None))                               # proposed_hbf.m:14-42
+        tau_Y, tau_Z, rho = (torch.empty(b, dtype=torch.float64, device=dev) for _ in range(3))
+        h.check(lib.jstsp_admm_parameters(h.ptr, dt, _lib.DEVICE, Nr, M, Nr, P, b, 6, _p(subY), Nr * M, _p(Zbar), Nr * P, _p(tau_Y), _p(tau_Z), _p(rho)))
+        S = self.eng.proposed_algorithm_pilots(subY, Omega, self.A, self.Dt, pilots, L, imax, tau_Y, tau_Z, rho, "approximate")   # :137
+        nm = torch.empty(b, dtype=torch.float64, device=dev)
+        self.eng._bind_stream()
+        h.check(lib.jstsp_nmse(h.ptr, dt, _lib.DEVICE, Nr, P, b, _p(S), Nr * P, _p(Zbar), Nr * P, _p(nm)))    # :138-141
+        if keep:
+            return dict(nmse=nm, S=S, Zbar=Zbar, subY=subY, Omega=Omega, H=H, tau_Y=tau_Y, tau_Z=tau_Z, rho=rho, pilots=pilots)
+        return nm
+
+    def run(self, batch, snr_db, seed, first_trial=0, imax=100, keep=False):
+        from . import synth
+        return self.run_from_draws(*synth.draw(self.s, batch, snr_db, seed, first_trial, self.device), imax=imax, keep=keep)
 
 
 def shard_range(n_trials, rank, world):

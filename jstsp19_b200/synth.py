@@ -124,9 +124,9 @@ def build_from_draws(s: Shape, coef, u_r, u_t, noise_unit, sym_idx, mask_rank, s
                 pilots=sk.transpose(1, 2).contiguous().to(cdtype))
 
 
-def make_batch(s: Shape, batch, snr_db, seed, first_trial=0, device="cuda", cdtype=torch.complex64):
-    """Draws for trials [first_trial, first_trial+batch): the generator is keyed by
-    (seed, first_trial) so a rank's shard does not depend on the number of ranks as long as
+def draw(s: Shape, batch, snr_db, seed, first_trial=0, device="cuda"):
+    """Raw draws of trials [first_trial, first_trial+batch): coefficient, angle uniforms, unit noise, 4-QAM symbol indices, mask ranks and
+    the noise variance.  The generator is keyed by (seed, first_trial) so a rank's shard does not depend on the number of ranks as long as
     shards start at the same trial indices."""
     g = torch.Generator(device=device)
     g.manual_seed(int(seed) * 1000003 + int(first_trial))
@@ -139,7 +139,12 @@ def make_batch(s: Shape, batch, snr_db, seed, first_trial=0, device="cuda", cdty
     rank = torch.rand(batch, s.Nr, s.M, **f).argsort(dim=1).argsort(dim=1)
     snr = torch.as_tensor(snr_db, device=device, dtype=torch.float64).expand(batch) if not torch.is_tensor(snr_db) else snr_db.to(device).double()
     sigma2 = 10.0 ** (-snr / 10.0)
-    return build_from_draws(s, coef, u_r, u_t, noise, sym, rank, sigma2, cdtype=cdtype)
+    return coef, u_r, u_t, noise, sym, rank, sigma2
+
+
+def make_batch(s: Shape, batch, snr_db, seed, first_trial=0, device="cuda", cdtype=torch.complex64):
+    """:func:`draw` + :func:`build_from_draws` (torch fp64 arithmetic: the bench's input generator and the pipeline's cross-check)."""
+    return build_from_draws(s, *draw(s, batch, snr_db, seed, first_trial, device), cdtype=cdtype)
 
 
 def nmse_spectral(S, Zbar):
