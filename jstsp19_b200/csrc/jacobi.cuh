@@ -30,14 +30,15 @@ struct JacobiSmem {
 // Fast fp64 reciprocal square root / reciprocal: fp32 hardware seed + Newton steps in fp64 (full
 // double accuracy after two/three steps).  The argument is range-reduced through its exponent so
 // the fp32 seed never over/underflows.  x > 0 and finite.
+__device__ __forceinline__ double pow2i(int k) { return __hiloint2double((1023 + k) << 20, 0); }   // exact 2^k, -1022 <= k <= 1023
 __device__ __forceinline__ double fast_rsqrt(double x) {
     const int ex = ((__double2hiint(x) >> 20) & 0x7ff) - 1023;
     const int hshift = ex >> 1;
-    const double xs = scalbn(x, -2 * hshift);                 // in [1, 4)
+    const double xs = x * pow2i(-2 * hshift);                 // in [1, 4); one exact multiply instead of scalbn's library path
     double r = (double)rsqrtf((float)xs);                     // relative error <= 2^-22: two Newton steps (e <- 1.5 e^2) reach 1e-26
     r = r * (1.5 - 0.5 * xs * r * r);
     r = r * (1.5 - 0.5 * xs * r * r);
-    return scalbn(r, -hshift);
+    return r * pow2i(-hshift);
 }
 __device__ __forceinline__ double fast_rcp_ge1(double d) {     // d >= 1 ; huge d (> fp32 range) returns 0
     double r = (double)__frcp_rn((float)d);                   // relative error <= 2^-24: two Newton steps (e <- e^2) reach 1e-29
@@ -49,8 +50,9 @@ __device__ __forceinline__ double fast_rcp_ge1(double d) {     // d >= 1 ; huge 
 // Round-robin ("circle method") pairing: npad players, step s in [0, npad-1).
 __device__ __forceinline__ void rr_pair(int npad, int s, int k, int& p, int& q) {
     int a, b;
-    if (k == 0) { a = npad - 1; b = s; }
-    else { a = (s + k) % (npad - 1); b = (s - k + npad - 1) % (npad - 1); }
+    const int r = npad - 1;
+    if (k == 0) { a = r; b = s; }
+    else { a = s + k; if (a >= r) a -= r; b = s - k + r; if (b >= r) b -= r; }      // (s +- k) mod (npad - 1) without a division
     p = a < b ? a : b; q = a < b ? b : a;
 }
 
@@ -79,6 +81,21 @@ __device__ inline int jacobi_hermitian_block(JacobiSmem& sm, int n, int max_swee
     if (n < 2 || sm.red[0] == 0.0) return 0;
     int sweep = 0;
     for (; sweep < max_sweeps; ++sweep) {
+        if (keep_U || sweep > 0) {
+            // Is another sweep worth it?  Off-diagonal mass now (one block reduction) against stop_rel2^1.5 |A|_F^2: a warm-started or
+            // already-swept matrix whose relative off-diagonal NORM is below stop_rel2^0.75 (3e-8 for the fp32 solves, 1e-15 for fp64) has
+            // eigenvectors good to that level, and the sweep that would confirm it costs as much as the ones that did the work.
+            double o2 = 0.0;
+            for (int i = tid; i < n * n; i += nt) if (i % n != i / n) o2 += sm.Are[i] * sm.Are[i] + sm.Aim[i] * sm.Aim[i];
+            for (int o = 16; o > 0; o >>= 1) o2 += __shfl_down_sync(0xffffffffu, o2, o);
+            if (tid == 0) sm.red[1] = 0.0;
+            __syncthreads();
+            for (int w = 0; w < (nt + 31) / 32; ++w) {
+                if (tid == w * 32) sm.red[1] += o2;
+                __syncthreads();
+            }
+            if (sm.red[1] <= stop_rel2 * sqrt(stop_rel2) * sm.red[0]) break;
+        }
         if (tid < h) sm.offacc[tid] = 0.0;
         for (int step = 0; step < npad - 1; ++step) {
             // phase 0: rotation parameters, one thread per pair
