@@ -65,6 +65,7 @@ __device__ __forceinline__ void rr_pair(int npad, int s, int k, int& p, int& q) 
 __device__ inline int jacobi_hermitian_block(JacobiSmem& sm, int n, int max_sweeps = 24, bool keep_U = false, double stop_rel2 = 1e-20) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int npad = n + (n & 1), h = npad / 2;
+    const bool fast_t = stop_rel2 > 1e-15;          // the fp32 callers' tolerance
     if (!keep_U) for (int i = tid; i < n * n; i += nt) { sm.Ure[i] = (i % n == i / n) ? 1.0 : 0.0; sm.Uim[i] = 0.0; }
     {   // Frobenius norm^2 (block reduction; deterministic order)
         double f = 0.0;
@@ -112,9 +113,17 @@ __device__ inline int jacobi_hermitian_block(JacobiSmem& sm, int n, int max_swee
                         const double rm = fast_rsqrt(m2);              // 1/|a_pq|
                         er = ar * rm; ei = ai * rm;
                         const double tau = (aqq - app) * 0.5 * rm;
-                        const double s1 = 1.0 + tau * tau;
-                        const double w = s1 < 1e300 ? s1 * fast_rsqrt(s1) : fabs(tau);     // sqrt(1 + tau^2)
-                        const double t = (tau >= 0.0 ? 1.0 : -1.0) * fast_rcp_ge1(fabs(tau) + w);
+                        double t;
+                        if (fast_t) {
+                            // fp32 solves: the tangent to single precision (|tau| beyond the float range gives t = 0, its limit).  (c, s, e) below still
+                            // form an exactly unitary rotation in fp64; it merely leaves ~1e-7 |a_pq| behind, far under what the next sweep removes.
+                            const float tf = (float)tau;
+                            t = (double)(copysignf(1.f, tf) / (fabsf(tf) + sqrtf(fmaf(tf, tf, 1.f))));
+                        } else {
+                            const double s1 = 1.0 + tau * tau;
+                            const double w = s1 < 1e300 ? s1 * fast_rsqrt(s1) : fabs(tau);     // sqrt(1 + tau^2)
+                            t = (tau >= 0.0 ? 1.0 : -1.0) * fast_rcp_ge1(fabs(tau) + w);
+                        }
                         c = fast_rsqrt(1.0 + t * t);
                         s = t * c;
                     }
@@ -157,8 +166,10 @@ __device__ inline int jacobi_hermitian_block(JacobiSmem& sm, int n, int max_swee
                         br[rr][1] = s2 * xr + c2 * eyr; bi[rr][1] = s2 * xi + c2 * eyi;
                     }
                 }
-                if (k1 == k2) {   // the annihilated pair: exact zeros off-diagonal, real diagonal
-                    br[0][1] = bi[0][1] = br[1][0] = bi[1][0] = 0.0; bi[0][0] = 0.0; bi[1][1] = 0.0;
+                if (k1 == k2) {   // the annihilated pair: exact zeros off-diagonal (what is left of them with fp32 angles stays), real diagonal
+                    if (!fast_t) { br[0][1] = bi[0][1] = br[1][0] = bi[1][0] = 0.0; }
+                    else { br[1][0] = br[0][1]; bi[1][0] = -bi[0][1]; }
+                    bi[0][0] = 0.0; bi[1][1] = 0.0;
                 }
                 sm.Are[p1 + n * p2] = br[0][0]; sm.Aim[p1 + n * p2] = bi[0][0];
                 if (v2) { sm.Are[p1 + n * q2] = br[0][1]; sm.Aim[p1 + n * q2] = bi[0][1]; }
@@ -208,7 +219,8 @@ __device__ inline void jacobi_similarity_block(JacobiSmem& sm, int n, double* tm
     for (int t = tid; t < n * n; t += nt) {          // A = Q^H T
         const int i = t % n, j = t / n;
         double re = 0.0, im = 0.0;
-        for (int k = 0; k < n; ++k) {
+        for (int kk = 0; kk < n; ++kk) {
+            int k = kk + i; if (k >= n) k -= n;      // skewed start: lanes read Q(k, i) for consecutive i - with a common k that is a stride-n (same bank) access
             const double qr = sm.Ure[k + n * i], qi = -sm.Uim[k + n * i], tr = Tre[k + n * j], ti = Tim[k + n * j];
             re += qr * tr - qi * ti; im += qr * ti + qi * tr;
         }
