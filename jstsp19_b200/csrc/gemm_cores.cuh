@@ -172,19 +172,33 @@ __device__ __forceinline__ void expand_cols(void* smem_raw, int RP, int NG, int 
 template <typename T>
 __device__ __forceinline__ void gram_partial(const T* __restrict__ zre, const T* __restrict__ zim, int RP, int n, int ncols,
                                              double* __restrict__ out) {
-    for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
-        int i = t % n, j = t / n;
-        double dre = 0.0, dim = 0.0;
+    // 2 x 2 outputs per thread (rows beyond n inside the RP-padded tile are zero); per output the summation order is unchanged:
+    // 16-column partial sums in T, accumulated in double
+    const int h = (n + 1) / 2;
+    for (int t = threadIdx.x; t < h * h; t += blockDim.x) {
+        const int i0 = 2 * (t % h), j0 = 2 * (t / h);
+        const int i1 = i0 + 1 < n ? i0 + 1 : i0, j1 = j0 + 1 < n ? j0 + 1 : j0;
+        double dre[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, dim[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
         for (int c0 = 0; c0 < ncols; c0 += 16) {
-            T re = 0, im = 0;
+            T re[2][2] = {{0, 0}, {0, 0}}, im[2][2] = {{0, 0}, {0, 0}};
             int ce = c0 + 16 < ncols ? c0 + 16 : ncols;
             for (int c = c0; c < ce; ++c) {
-                T xr = zre[c * RP + i], xi = zim[c * RP + i], yr = zre[c * RP + j], yi = zim[c * RP + j];
-                cmac<T>(re, im, xr, xi, yr, -yi);
+                const T x0r = zre[c * RP + i0], x0i = zim[c * RP + i0], x1r = zre[c * RP + i1], x1i = zim[c * RP + i1];
+                const T y0r = zre[c * RP + j0], y0i = zim[c * RP + j0], y1r = zre[c * RP + j1], y1i = zim[c * RP + j1];
+                cmac<T>(re[0][0], im[0][0], x0r, x0i, y0r, -y0i); cmac<T>(re[1][0], im[1][0], x1r, x1i, y0r, -y0i);
+                cmac<T>(re[0][1], im[0][1], x0r, x0i, y1r, -y1i); cmac<T>(re[1][1], im[1][1], x1r, x1i, y1r, -y1i);
             }
-            dre += (double)re; dim += (double)im;
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int bq = 0; bq < 2; ++bq) { dre[a][bq] += (double)re[a][bq]; dim[a][bq] += (double)im[a][bq]; }
         }
-        out[2 * t] = dre; out[2 * t + 1] = dim;
+        out[2 * (i0 + n * j0)] = dre[0][0]; out[2 * (i0 + n * j0) + 1] = dim[0][0];
+        if (i1 != i0) { out[2 * (i1 + n * j0)] = dre[1][0]; out[2 * (i1 + n * j0) + 1] = dim[1][0]; }
+        if (j1 != j0) {
+            out[2 * (i0 + n * j1)] = dre[0][1]; out[2 * (i0 + n * j1) + 1] = dim[0][1];
+            if (i1 != i0) { out[2 * (i1 + n * j1)] = dre[1][1]; out[2 * (i1 + n * j1) + 1] = dim[1][1]; }
+        }
     }
 }
 

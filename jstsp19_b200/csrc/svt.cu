@@ -139,12 +139,10 @@ __global__ void __launch_bounds__(kThreads) k_svt_step(SvtP<T> p) {
     }
     __syncthreads();
     const bool last = p.iter == p.imax - 1;
-    for (int t = threadIdx.x; t < N * ncols; t += kThreads) {
-        int r = t % N, c = t / N;
-        T xr = 0, xi = 0;
-        for (int k = 0; k < N; ++k) { cx<T> w = Ws[r + N * k]; cmac<T>(xr, xi, w.re, w.im, Zre[c * RP + k], Zim[c * RP + k]); }
+    // X = W Z, 2 rows x 2 columns per thread (two 8-byte reads of W and four of Z per 8 complex MACs), then the element-wise updates
+    auto elem = [&](int r, int c, T xr, T xi) {
         size_t gi = (size_t)c * N + r;
-        if (MODE == MODE_SVT) { p.out[(long long)b * p.ld_out + (size_t)(c0 + c) * N + r] = mk<T>(xr, xi); continue; }
+        if (MODE == MODE_SVT) { p.out[(long long)b * p.ld_out + (size_t)(c0 + c) * N + r] = mk<T>(xr, xi); return; }
         const T om = p.omega[(long long)b * p.ld_omega + (size_t)(c0 + c) * N + r];
         cx<T> oh = in[gi];
         if (MODE == MODE_MCSVT) {
@@ -162,6 +160,21 @@ __global__ void __launch_bounds__(kThreads) k_svt_step(SvtP<T> p) {
             if (conv) { cx<T> ht = p.Htrue[(long long)b * p.ld_H + (size_t)(c0 + c) * N + r]; Ere[c * RP + r] = xr - ht.re; Eim[c * RP + r] = xi - ht.im; }
         }
         if (last) p.out[(long long)b * p.ld_out + (size_t)(c0 + c) * N + r] = mk<T>(xr, xi);
+    };
+    const int hN = (N + 1) / 2, hC = (ncols + 1) / 2;
+    for (int t = threadIdx.x; t < hN * hC; t += kThreads) {
+        const int r0 = 2 * (t % hN), ca = 2 * (t / hN);
+        const int r1 = r0 + 1 < N ? r0 + 1 : r0, cb = ca + 1 < ncols ? ca + 1 : ca;
+        T ar[2][2] = {{0, 0}, {0, 0}}, ai[2][2] = {{0, 0}, {0, 0}};                           // [row][column]
+        for (int k = 0; k < N; ++k) {
+            const cx<T> w0 = Ws[r0 + N * k], w1 = Ws[r1 + N * k];
+            const T zar = Zre[ca * RP + k], zai = Zim[ca * RP + k], zbr = Zre[cb * RP + k], zbi = Zim[cb * RP + k];
+            cmac<T>(ar[0][0], ai[0][0], w0.re, w0.im, zar, zai); cmac<T>(ar[1][0], ai[1][0], w1.re, w1.im, zar, zai);
+            cmac<T>(ar[0][1], ai[0][1], w0.re, w0.im, zbr, zbi); cmac<T>(ar[1][1], ai[1][1], w1.re, w1.im, zbr, zbi);
+        }
+        elem(r0, ca, ar[0][0], ai[0][0]);
+        if (r1 != r0) elem(r1, ca, ar[1][0], ai[1][0]);
+        if (cb != ca) { elem(r0, cb, ar[0][1], ai[0][1]); if (r1 != r0) elem(r1, cb, ar[1][1], ai[1][1]); }
     }
     if (MODE == MODE_SVT) return;
     __syncthreads();
