@@ -684,6 +684,9 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
     const size_t esz0 = sizeof(cx<T>);
     const bool no_fast = getenv("JSTSP_DISABLE_FAST") != nullptr;
     const bool overlap_eig = getenv("JSTSP_NO_OVERLAP") == nullptr;
+    // side-stream eigen-solve: one warp per trial at N <= 16 (a quarter of the registers and thread slots next to k_psi_res / k_psi_g, which it shares the SMs
+    // with; measured 0.649 -> 0.638 ms of main-stream kernel time per iteration), 128 threads for taller problems
+    const int eig_threads = getenv("JSTSP_EIG_THREADS") ? atoi(getenv("JSTSP_EIG_THREADS")) : (N <= 16 ? 32 : 128);
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     const bool segP = (P * esz0) % 16 == 0, segM = (M * esz0) % 16 == 0;
     const bool b_ok = host || ps || (al16(B_) && ((size_t)d->ld_B * esz0) % 16 == 0);
@@ -1013,7 +1016,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
                 if (overlap_eig) {
                     JSTSP_CUDA(h, cudaEventRecord(h->ev_fork, st));
                     JSTSP_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-                    k_svt_weights<T><<<nb, 128, sm_j, h->side>>>(qe); h->launches++;
+                    k_svt_weights<T><<<nb, eig_threads, sm_j, h->side>>>(qe); h->launches++;
                     JSTSP_CUDA(h, cudaEventRecord(h->ev_join, h->side));
                 } else {
                     JSTSP_LAUNCH(h, PK_EIG, (k_svt_weights<T><<<nb, 128, sm_j, st>>>(qe)));
