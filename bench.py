@@ -182,8 +182,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--trials", type=int, default=592, help="trials per GPU per step (4 x 148 SMs)")
-    ap.add_argument("--e2e-trials", type=int, default=2368, help="trials per end-to-end call (the library splits them into passes and overlaps the H2D of pass k+1 with the solve of pass k)")
+    ap.add_argument("--trials", type=int, default=888, help="trials per GPU per step (6 x 148 SMs: every kernel of the iteration then runs whole waves)")
+    ap.add_argument("--e2e-trials", type=int, default=3552, help="trials per end-to-end call (the library splits them into passes and overlaps the H2D of pass k+1 with the solve of pass k)")
     ap.add_argument("--e2e-pass", type=int, default=0, help="trials per internal pass of the end-to-end call (0 = the library's choice)")
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--cpu-trials", type=int, default=12)

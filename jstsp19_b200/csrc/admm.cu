@@ -728,7 +728,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
     if (h->max_chunk > 0 && chunk_trials > h->max_chunk) chunk_trials = h->max_chunk;
     // HOST buffers: passes of ~4 trials per SM (measured: 592-trial passes beat 296-trial ones end to end, 7.6k vs 7.0k estimates/s), so that the H2D copy of pass k+1 (copy stream, second staging
     // set) overlaps the solve of pass k.  Smaller passes would leave SMs idle in the one-CTA-per-trial kernels.
-    const int pass_min = 4 * h->sm_count;
+    const int pass_min = 6 * h->sm_count;      // 6 trials per SM: the grids of all four kernels of an iteration are whole waves (8.9k -> 9.3k estimates/s against 4 per SM)
     if (host && h->max_chunk == 0 && batch >= 2 * pass_min) chunk_trials = ceil_div(batch, batch / pass_min);
     bool pingpong = host && chunk_trials < batch;
     cx<T>* bt_ws = nullptr;
