@@ -330,7 +330,11 @@ def main():
         else:
             edata = data
         pin = lambda t: t[:ne].cpu().contiguous().pin_memory()
-        hsubY, hOm, hB = pin(edata["subY"]), pin(edata["Omega"]), pin(edata["Psi" if use_psi else "B"])
+        # the bulky dictionary operand (Psi_bar / dense B, 2 MB per trial) is pinned for all `ne` trials only when it is the measured entry;
+        # as the accompanying "other entry" it runs on the first two passes' worth of trials (keeps 8 ranks' pinned memory small)
+        ne_alt = ne if (not use_psi or args.e2e_entry == "psi") else min(ne, 2 * nb)
+        hsubY, hOm = pin(edata["subY"]), pin(edata["Omega"])
+        hB = edata["Psi" if use_psi else "B"][:ne_alt].cpu().contiguous().pin_memory()
         hPil = pin(edata["pilots"]) if use_psi else None
         hA = edata["A"].cpu().contiguous().pin_memory()
         hDt = edata["Dt"].cpu().contiguous().pin_memory()
@@ -365,8 +369,9 @@ def main():
         ksteps = max(3, args.steps // 2 + 1)
         esz = 8 if args.precision == "f32" else 16
 
-        def e2e_run(entry):
+        def e2e_run(entry, ne=ne):
             e2e_entry[0] = entry
+            d.batch = ne
             for _ in range(3):
                 host_step()
             barrier()
@@ -386,8 +391,8 @@ def main():
 
         e2e = e2e_run(e2e_entry[0])
         if use_psi:      # the other structured entry on the same trials, for the record
-            alt = e2e_run("psi" if args.e2e_entry == "pilots" else "pilots")
-            e2e["other_entry"] = dict(entry=alt["entry"], value=alt["value"], h2d_bytes_per_step=alt["h2d_bytes_per_step"])
+            alt = e2e_run("psi" if args.e2e_entry == "pilots" else "pilots", ne_alt if args.e2e_entry == "pilots" else ne)
+            e2e["other_entry"] = dict(entry=alt["entry"], value=alt["value"], h2d_bytes_per_step=alt["h2d_bytes_per_step"], trials_per_step=alt["trials_per_step"])
 
     if rank != 0:
         if world > 1:
