@@ -254,6 +254,17 @@ int jstsp_measure(jstsp_handle* h, const jstsp_meas_desc* d, int dtype, int mem,
                   const void* H, const void* N, const void* Psi, const void* W, const int* perm,
                   void* Y_out, void* W_e, void* Psi_bar, void* Omega, void* Y_noiseless);
 
+/* ---- combiner codebooks and pilot symbols -------------------------------------- */
+enum { JSTSP_BF_FFT = 0, JSTSP_BF_RAND = 1, JSTSP_BF_RAND_PS = 2, JSTSP_BF_PS = 3, JSTSP_BF_ZC = 4, JSTSP_BF_QUANTIZED_4 = 5, JSTSP_BF_QUANTIZED = 6 };
+/* B = createBeamformer(N, beamformer_type)   replaces basic_system_functions/createBeamformer.m:1-35; B is N x N (out).
+ *   draws (random codebooks only, in `mem` space): 'rand' N*N int32 in 0..3 = index of each randsrc(N,N,[1 -1 1j -1j]) entry
+ *   into that alphabet, column-major (:8); 'rand_ps' N int32 in 1..32 = randi(32,1,N) (:10-11).  NULL otherwise. */
+int jstsp_create_beamformer(jstsp_handle* h, int dtype, int mem, int N, int type, const int* draws, void* B);
+/* symbols = qam4mod(input, mode, N)   replaces basic_system_functions/qam4mod.m:1-33.
+ *   mode 0 ('mod'): draws = n int32 in 0..3, the index of each randsrc draw into the alphabet of qam4mod.m:7; input unused.
+ *   mode 1 ('demod'): hard decision of the n soft symbols in `input` (qam4mod.m:12-31); draws unused. */
+int jstsp_qam4mod(jstsp_handle* h, int dtype, int mem, int mode, long long n, const int* draws, const void* input, void* symbols);
+
 /* ---- driver-side metric and parameters ("next" rows) ---------------------- */
 /* nmse[b] = min(1, norm(S-Zbar)^2/norm(Zbar)^2) with matrix 2-norms (plot_errorVSsnr.m:138-141). */
 int jstsp_nmse(jstsp_handle* h, int dtype, int mem, int G, int P, int batch,

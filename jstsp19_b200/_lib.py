@@ -76,6 +76,8 @@ def _load():
     lib.jstsp_vamp.argtypes = [vp, i, i, i, i, i, i, C.c_double, vp, ll, vp, ll, vp, vp, vp, ll, vp, ll, vp, ll]
     lib.jstsp_wideband_mmwave_channel.argtypes = [vp, i, i, i, i, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.jstsp_measure.argtypes = [vp, C.POINTER(MeasDesc), i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.jstsp_create_beamformer.argtypes = [vp, i, i, i, i, vp, vp]
+    lib.jstsp_qam4mod.argtypes = [vp, i, i, i, ll, vp, vp, vp]
     lib.jstsp_nmse.argtypes = [vp, i, i, i, i, i, vp, ll, vp, ll, vp]
     lib.jstsp_admm_parameters.argtypes = [vp, i, i, i, i, i, i, i, i, vp, ll, vp, ll, vp, vp, vp]
     lib.jstsp_log2det_rate.argtypes = [vp, i, i, i, i, i, vp, ll, vp, vp]
@@ -91,7 +93,7 @@ EXPORTED = [
     "jstsp_synchronize", "jstsp_launch_count", "jstsp_set_chunk", "jstsp_profile", "jstsp_profile_read", "jstsp_debug_buffer",
     "jstsp_proposed_algorithm", "jstsp_proposed_algorithm_angles", "jstsp_proposed_algorithm_psi", "jstsp_proposed_algorithm_pilots", "jstsp_last_path",
     "jstsp_svt", "jstsp_mc_svt", "jstsp_mc_admm", "jstsp_omp", "jstsp_omp_kron", "jstsp_somp", "jstsp_sparse_admm", "jstsp_vamp",
-    "jstsp_wideband_mmwave_channel", "jstsp_measure", "jstsp_nmse", "jstsp_admm_parameters", "jstsp_log2det_rate",
+    "jstsp_wideband_mmwave_channel", "jstsp_measure", "jstsp_create_beamformer", "jstsp_qam4mod", "jstsp_nmse", "jstsp_admm_parameters", "jstsp_log2det_rate",
 ]
 
 

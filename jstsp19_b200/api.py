@@ -392,6 +392,51 @@ def vamp(y, A, sigma, L, *, precision="f64", handle=None, nit=100, damp=0.85):
     return x[0]
 
 
+_BF_TYPES = {"fft": 0, "rand": 1, "rand_ps": 2, "ps": 3, "ZC": 4, "quantized_4": 5, "quantized": 6}
+_QAM4 = np.array([1 + 1j, -1 + 1j, 1 - 1j, -1 - 1j]) / np.sqrt(2.0)
+
+
+def createBeamformer(N, beamformer_type, *, draws=None, precision="f64", handle=None):
+    """B = createBeamformer(N, beamformer_type)  (basic_system_functions/createBeamformer.m:1).  The random codebooks take their draws
+    as an input: ``'rand'`` the N x N matrix ``randsrc(N,N,[1 -1 1j -1j])`` itself, ``'rand_ps'`` the row ``randi(32,1,N)``."""
+    h = handle or default_handle()
+    cd = _CD[precision]
+    if beamformer_type not in _BF_TYPES:
+        raise ValueError(f"unknown beamformer_type {beamformer_type!r}")
+    t = _BF_TYPES[beamformer_type]
+    N = int(N)
+    d = None
+    if t == 1:
+        a = np.asarray(draws).reshape(N, N)
+        alphabet = np.array([1, -1, 1j, -1j])
+        d = np.ascontiguousarray(np.argmin(np.abs(a.T[..., None] - alphabet), axis=-1), dtype=np.int32)      # column-major indices
+    elif t == 2:
+        d = np.ascontiguousarray(np.asarray(draws).reshape(N), dtype=np.int32)
+    B = np.empty((N, N), dtype=cd)
+    h.check(_lib.lib.jstsp_create_beamformer(h.ptr, _DT[precision], _lib.HOST, N, t, _ptr(d), _ptr(B)))
+    return B.T
+
+
+def qam4mod(input, mode, N=None, *, draws=None, precision="f64", handle=None):
+    """symbols = qam4mod(input, mode, N)  (basic_system_functions/qam4mod.m:1).  ``'mod'``: ``draws`` is the N x 1 ``randsrc`` result
+    (alphabet symbols) or their indices 0..3; ``'demod'``: hard decision of ``input``."""
+    h = handle or default_handle()
+    cd = _CD[precision]
+    if mode == "mod":
+        a = np.asarray(draws).reshape(-1)
+        idx = a.astype(np.int32) if np.issubdtype(a.dtype, np.integer) else np.argmin(np.abs(a[:, None] - _QAM4), axis=-1).astype(np.int32)
+        out = np.empty(idx.size, dtype=cd)
+        h.check(_lib.lib.jstsp_qam4mod(h.ptr, _DT[precision], _lib.HOST, 0, idx.size, _ptr(np.ascontiguousarray(idx)), None, _ptr(out)))
+        return out
+    if mode == "demod":
+        x = np.asarray(input)
+        xm = np.ascontiguousarray(x.T if x.ndim == 2 else x, dtype=cd)
+        out = np.empty(xm.shape, dtype=cd)
+        h.check(_lib.lib.jstsp_qam4mod(h.ptr, _DT[precision], _lib.HOST, 1, xm.size, None, _ptr(xm), _ptr(out)))
+        return out.T if x.ndim == 2 else out
+    raise ValueError("mode must be 'mod' or 'demod'")
+
+
 def wideband_mmwave_channel(L, Mr, Mt, total_num_of_clusters, total_num_of_rays, Gr, Gt, *, normals, uniforms,
                             precision="f64", handle=None):
     """[H, Zbar, Ar, At, Dr, Dt] = wideband_mmwave_channel(L, Mr, Mt, Ncl, Nray, Gr, Gt)

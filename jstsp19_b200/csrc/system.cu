@@ -366,6 +366,95 @@ static int run_measure(Handle* h, int mem, const jstsp_meas_desc* d, const void*
     return JSTSP_OK;
 }
 
+// ---- combiner codebooks and the 4-QAM alphabet (the inputs the drivers prepare around the estimator) -----------
+namespace jstsp {
+template <typename T>
+__global__ void k_beamformer(int N, int type, const int* __restrict__ draws, cx<T>* __restrict__ B) {
+    const double rs = 1.0 / sqrt((double)N);
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < N * N; t += gridDim.x * blockDim.x) {
+        const int i = t % N, j = t / N;                        // B(i, j), column-major
+        double ph = 0.0;                                       // B = rs * exp(-1j * ph) except for 'rand'
+        switch (type) {
+            case JSTSP_BF_FFT: ph = 2.0 * M_PI * (double)((long long)i * j % N) / N; break;                       // fft(eye(N)), createBeamformer.m:6
+            case JSTSP_BF_RAND: {                                                                                 // randsrc(N,N,[1 -1 1j -1j]), :8
+                const int d = draws[t];
+                B[t] = mk<T>((T)(d == 0 ? rs : d == 1 ? -rs : 0.0), (T)(d == 2 ? rs : d == 3 ? -rs : 0.0));
+                continue;
+            }
+            case JSTSP_BF_RAND_PS: ph = (double)i * 2.0 * M_PI * (double)draws[j] / 32.0; break;                  // randi(32,1,N), :10-11
+            case JSTSP_BF_PS: ph = (double)i * 2.0 * M_PI * (double)j / N; break;                                 // :13-14
+            case JSTSP_BF_ZC: ph = 11.0 * (double)i * M_PI * (double)(j + 1) / N; break;                          // :16-17
+            default: {                                                                                            // quantized_4 (:19-24) / quantized (:26-31)
+                const int nq = type == JSTSP_BF_QUANTIZED_4 ? 4 : 6, levels = 1 << nq;
+                ph = (double)i * (2.0 * M_PI / levels) * (double)(j % levels);                                    // A(1:N) of the tiled 0..2^nq-1
+            }
+        }
+        double sn, cs; sincos(-ph, &sn, &cs);
+        B[t] = mk<T>((T)(rs * cs), (T)(rs * sn));
+    }
+}
+// mode 0: symbols = alphabet(draw) with alphabet = [1+1j, -1+1j, 1-1j, -1-1j]/sqrt(2) (qam4mod.m:7-8);
+// mode 1: hard decision of soft symbols (qam4mod.m:12-31; MATLAB orders complex numbers by their real parts, so the tests are on re / im >= 0, <= 0,
+//         applied in the reference's order s2, s3, s4 - later rules win on the axes)
+template <typename T>
+__global__ void k_qam4(int mode, size_t n, const int* __restrict__ draws, const cx<T>* __restrict__ in, cx<T>* __restrict__ out) {
+    const T a = (T)(1.0 / sqrt(2.0));                        // as the reference forms it, (1+1j)/sqrt(2): one ulp below the correctly rounded sqrt(1/2) in fp64
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+        if (mode == 0) { const int d = draws[t]; out[t] = mk<T>((d & 1) ? -a : a, (d & 2) ? -a : a); continue; }
+        const cx<T> v = in[t];
+        cx<T> s = mk<T>(a, a);
+        if (v.re >= 0 && v.im <= 0) s = mk<T>(a, -a);
+        if (v.re <= 0 && v.im >= 0) s = mk<T>(-a, a);
+        if (v.re <= 0 && v.im <= 0) s = mk<T>(-a, -a);
+        out[t] = s;
+    }
+}
+template <typename T>
+static int run_small(Handle* h, int mem, size_t n_out, const int* draws, size_t n_draws, const void* in, void* out, int kind, int a0, int a1) {
+    const bool host = mem == JSTSP_HOST;
+    Arena probe(nullptr, 0);
+    probe.take<cx<T>>(n_out); probe.take<cx<T>>(n_out); probe.take<int>(n_draws ? n_draws : 1);
+    int rc = ensure_workspace(h, probe.off); if (rc) return rc;
+    Arena ar(h->ws, h->ws_bytes);
+    cx<T>* d_out = host ? ar.take<cx<T>>(n_out) : (cx<T>*)out;
+    const cx<T>* d_in = (const cx<T>*)in;
+    const int* d_draws = draws;
+    if (host) {
+        if (in) { cx<T>* t = ar.take<cx<T>>(n_out); JSTSP_CUDA(h, cudaMemcpyAsync(t, in, n_out * sizeof(cx<T>), cudaMemcpyHostToDevice, h->stream)); d_in = t; }
+        if (draws) { int* t = ar.take<int>(n_draws); JSTSP_CUDA(h, cudaMemcpyAsync(t, draws, n_draws * sizeof(int), cudaMemcpyHostToDevice, h->stream)); d_draws = t; }
+    }
+    const int grid = (int)((n_out + 255) / 256 < 1184 ? (n_out + 255) / 256 : 1184);
+    if (kind == 0) JSTSP_LAUNCH(h, PK_OTHER, (k_beamformer<T><<<grid, 256, 0, h->stream>>>(a0, a1, d_draws, d_out)));
+    else JSTSP_LAUNCH(h, PK_OTHER, (k_qam4<T><<<grid, 256, 0, h->stream>>>(a0, n_out, d_draws, d_in, d_out)));
+    JSTSP_CUDA(h, cudaGetLastError());
+    if (host) {
+        JSTSP_CUDA(h, cudaMemcpyAsync(out, d_out, n_out * sizeof(cx<T>), cudaMemcpyDeviceToHost, h->stream));
+        JSTSP_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    return JSTSP_OK;
+}
+}  // namespace jstsp
+
+extern "C" int jstsp_create_beamformer(jstsp_handle* h, int dtype, int mem, int N, int type, const int* draws, void* B) {
+    if (!h) return JSTSP_E_ARG;
+    if (N <= 0 || !B || type < JSTSP_BF_FFT || type > JSTSP_BF_QUANTIZED) return fail(h, JSTSP_E_ARG, "createBeamformer: bad size or unknown beamformer_type");
+    if ((type == JSTSP_BF_RAND || type == JSTSP_BF_RAND_PS) && !draws) return fail(h, JSTSP_E_ARG, "createBeamformer: this codebook needs its random draws");
+    JSTSP_CUDA(h, cudaSetDevice(h->device));
+    const size_t nd = type == JSTSP_BF_RAND ? (size_t)N * N : type == JSTSP_BF_RAND_PS ? (size_t)N : 0;
+    if (dtype == JSTSP_F32) return run_small<float>(h, mem, (size_t)N * N, nd ? draws : nullptr, nd, nullptr, B, 0, N, type);
+    if (dtype == JSTSP_F64) return run_small<double>(h, mem, (size_t)N * N, nd ? draws : nullptr, nd, nullptr, B, 0, N, type);
+    return fail(h, JSTSP_E_ARG, "unknown dtype");
+}
+
+extern "C" int jstsp_qam4mod(jstsp_handle* h, int dtype, int mem, int mode, long long n, const int* draws, const void* input, void* symbols) {
+    if (!h) return JSTSP_E_ARG;
+    if (n <= 0 || !symbols || (mode == 0 && !draws) || (mode == 1 && !input) || mode < 0 || mode > 1) return fail(h, JSTSP_E_ARG, "qam4mod: bad argument");
+    JSTSP_CUDA(h, cudaSetDevice(h->device));
+    if (dtype == JSTSP_F32) return run_small<float>(h, mem, (size_t)n, mode == 0 ? draws : nullptr, mode == 0 ? (size_t)n : 0, mode == 1 ? input : nullptr, symbols, 1, mode, 0);
+    if (dtype == JSTSP_F64) return run_small<double>(h, mem, (size_t)n, mode == 0 ? draws : nullptr, mode == 0 ? (size_t)n : 0, mode == 1 ? input : nullptr, symbols, 1, mode, 0);
+    return fail(h, JSTSP_E_ARG, "unknown dtype");
+}
+
 extern "C" int jstsp_measure(jstsp_handle* h, const jstsp_meas_desc* d, int dtype, int mem,
                              const void* H, const void* N, const void* Psi, const void* W, const int* perm,
                              void* Y_out, void* W_e, void* Psi_bar, void* Omega, void* Y_noiseless) {

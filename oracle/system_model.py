@@ -116,6 +116,19 @@ def qam4mod(N, rng: RefRandom):
     return rng.randsrc(N, 1, QAM4).reshape(-1)
 
 
+def qam4demod(soft):
+    """qam4mod(input, 'demod') (qam4mod.m:12-31).  MATLAB's relational operators on complex numbers compare REAL parts only, so
+    ``softDecision >= 0 & conjSymbols <= 0`` with ``conjSymbols = -1j*softDecision`` reads re >= 0 & im <= 0; rules apply in order."""
+    x = np.asarray(soft, dtype=np.complex128)
+    a = 1.0 / math.sqrt(2.0)
+    out = np.full(x.shape, a + 1j * a)
+    re, im = x.real, x.imag                                        # real(-1j*x) = imag(x)
+    out[(re >= 0) & (im <= 0)] = a - 1j * a                        # :21,27
+    out[(re <= 0) & (im >= 0)] = -a + 1j * a                       # :22,28
+    out[(re <= 0) & (im <= 0)] = -a - 1j * a                       # :23,29
+    return out
+
+
 # ----------------------------------------------------------------------------
 # proposed_hbf.m / hbf.m / wideband_hybBF_comm_system_training.m
 # ----------------------------------------------------------------------------

@@ -150,3 +150,23 @@ def test_log2det_rate_matches_oracle(precision, tol):
     X = t["W_e"].conj().T @ t["Ynoiseless"]
     c = 1.0 / (t["sigma2"] * fx.METRIC.Nt)
     assert abs(jb.log2det_rate(X, c, precision=precision) - est.log2det_rate(X, c)) <= tol * abs(est.log2det_rate(X, c))
+
+
+@pytest.mark.parametrize("precision,tol", [("f64", 1e-13), ("f32", 2e-6)])
+def test_beamformer_codebooks_and_qam(precision, tol):
+    """createBeamformer.m:4-32 (all seven codebooks) and qam4mod.m:6-31 through the C ABI."""
+    import jstsp19_b200 as jb
+    from oracle.matlab_compat import RefRandom
+    for kind in ("fft", "ps", "ZC", "quantized_4", "quantized"):
+        for N in (4, 32, 33, 100):
+            assert _rel(jb.createBeamformer(N, kind, precision=precision), sm.create_beamformer(N, kind)) < tol, (kind, N)
+    B0 = sm.create_beamformer(16, "rand", RefRandom(3))
+    assert _rel(jb.createBeamformer(16, "rand", draws=B0 * 4.0, precision=precision), B0) < tol
+    d = RefRandom(4).randi(32, 1, 16)
+    assert _rel(jb.createBeamformer(16, "rand_ps", draws=d, precision=precision), sm.create_beamformer(16, "rand_ps", RefRandom(4))) < tol
+    s0 = sm.qam4mod(257, RefRandom(5))
+    assert _rel(jb.qam4mod(None, "mod", 257, draws=s0, precision=precision), s0) < tol
+    soft = np.random.default_rng(6).standard_normal((9, 7)) + 1j * np.random.default_rng(7).standard_normal((9, 7))
+    soft[0, :3] = [0.0, 2.0, -3j]
+    assert _rel(jb.qam4mod(soft, "demod", precision=precision), sm.qam4demod(soft)) < tol
+    assert np.array_equal(np.sign(jb.qam4mod(soft, "demod", precision=precision).real), np.sign(sm.qam4demod(soft).real))

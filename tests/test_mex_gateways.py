@@ -70,6 +70,11 @@ class Script:
             return [np.asarray(self.rng.rand())]
         if name == "randperm":
             return [np.asarray(self.rng.randperm(int(args[0].reshape(-1)[0])), dtype=np.float64).reshape(1, -1)]
+        if name == "randsrc":
+            r, c = int(args[0].reshape(-1)[0]), int(args[1].reshape(-1)[0])
+            return [np.asarray(self.rng.randsrc(r, c, np.asarray(args[2]).reshape(-1)))]
+        if name == "randi":
+            return [np.asarray(self.rng.randi(int(args[0].reshape(-1)[0]), int(args[1].reshape(-1)[0]), int(args[2].reshape(-1)[0])), dtype=np.float64)]
         if name == "svd":
             U, s, Vh = np.linalg.svd(args[0], full_matrices=True)
             S = np.zeros(args[0].shape)
@@ -215,6 +220,30 @@ def test_proposed_algorithm_pilots_gateway():
     S1, Y1 = g(2, t["subY"], t["Omega"], t["A"], t["Dt"], t["pilots"], float(fx.CONFIG0.L), 40, t["tau_Y"], t["tau_Z"], t["rho"], "approximate")
     S0, Y0, _ = est.proposed_algorithm_structured(t["subY"], t["Omega"], t["A"], t["B"], 40, t["tau_Y"], t["tau_Z"], t["rho"], "approximate", want_conv=False)
     assert _rel(S1, S0) < 1e-8 and _rel(Y1, Y0) < 1e-8
+
+
+@pytest.mark.gpu
+def test_beamformer_and_qam_gateways():
+    """createBeamformer / qam4mod by name, random codebooks and pilots drawn through MATLAB's own randsrc / randi."""
+    g = mh.Gateway("createBeamformer")
+    for kind in ("fft", "ps", "ZC", "quantized_4", "quantized"):
+        for N in (5, 16, 70):
+            (B,) = g(1, float(N), kind)
+            assert _rel(B, sm.create_beamformer(N, kind)) < 1e-12, (kind, N)
+    for kind in ("rand", "rand_ps"):
+        g.set_matlab(Script(31))
+        (B,) = g(1, 12.0, kind)
+        assert _rel(B, sm.create_beamformer(12, kind, mc.RefRandom(31))) < 1e-12, kind
+    q = mh.Gateway("qam4mod")
+    q.set_matlab(Script(32))
+    (s1,) = q(1, np.zeros((0, 0)), "mod", 40.0)
+    assert np.array_equal(s1.reshape(-1), sm.qam4mod(40, mc.RefRandom(32)))
+    soft = np.random.default_rng(3).standard_normal((6, 5)) + 1j * np.random.default_rng(4).standard_normal((6, 5))
+    soft[0, 0] = 0.0; soft[1, 1] = 1.0; soft[2, 2] = -1j                  # points on the axes: the later rule of qam4mod.m:27-29 wins
+    (s2,) = q(1, soft, "demod")
+    assert np.array_equal(s2, sm.qam4demod(soft))
+    with pytest.raises(mh.MexError):
+        g(1, 8.0, "no_such_codebook")
 
 
 @pytest.mark.gpu

@@ -199,3 +199,14 @@ def test_somp_textbook_properties():
     Zf, supf, Rf = est.somp_textbook(A, Y + 0.1 * rng.standard_normal((N, S)), 100)
     assert len(supf) == min(N, D) and len(set(supf)) == len(supf)          # K = 100 on a small dictionary stops at min(N, D) atoms
     assert np.allclose(A[:, [s - 1 for s in supf]].conj().T @ Rf, 0, atol=1e-8)
+
+
+def test_qam4_demod_follows_matlab_complex_ordering():
+    """qam4mod.m:21-29: relational operators on complex numbers compare real parts; rules are applied in order (later wins on the axes)."""
+    from oracle import system_model as sm_
+    a = 1 / np.sqrt(2)
+    x = np.array([1 + 1j, 1 - 1j, -1 + 1j, -1 - 1j, 0, 1, -1, 1j, -1j])
+    want = np.array([a + 1j * a, a - 1j * a, -a + 1j * a, -a - 1j * a, -a - 1j * a, a - 1j * a, -a - 1j * a, -a + 1j * a, -a - 1j * a])
+    assert np.allclose(sm_.qam4demod(x), want)
+    s = sm_.qam4mod(64, __import__("oracle.matlab_compat", fromlist=["RefRandom"]).RefRandom(1))
+    assert np.allclose(sm_.qam4demod(s), s)                                  # demod(mod) is the identity on the alphabet
