@@ -14,14 +14,20 @@ from jstsp19_b200 import _lib  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=296)
-ap.add_argument("--m", type=int, default=50)
+ap.add_argument("--m", "--picks", dest="m", type=int, default=50, help="OMP iterations (--picks avoids the clash with torchrun's own --m* options)")
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--dbg", action="store_true")
 ap.add_argument("--shape", type=int, nargs=4, default=[64, 128, 256, 1024])
 a = ap.parse_args()
 N, M, G, P = a.shape
-dev = torch.device("cuda", 0)
-g = torch.Generator(device=dev); g.manual_seed(1)
+# under torchrun every rank solves its own a.batch trials (weak scaling; trials are independent, one all-reduce at the end)
+rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
+g = torch.Generator(device=dev); g.manual_seed(1 + rank)
 A = (torch.exp(-2j * torch.pi * torch.outer(torch.arange(G, device=dev), torch.arange(N, device=dev)) / G) / N ** 0.5).to(torch.complex64).contiguous()   # (G,N) = col-major N x G
 B = ((torch.randint(0, 2, (a.batch, M, P), generator=g, device=dev) * 2 - 1) + 1j * (torch.randint(0, 2, (a.batch, M, P), generator=g, device=dev) * 2 - 1)).to(torch.complex64) / (2 * M) ** 0.5
 S = torch.zeros(a.batch, P, G, dtype=torch.complex64, device=dev)
@@ -31,7 +37,7 @@ S.view(a.batch, -1).scatter_(1, idx, gains)
 # Y' (M,N) = B' S' A'  in the stored (transposed) layout
 Y = torch.matmul(torch.matmul(B, S), A.unsqueeze(0).expand(a.batch, -1, -1)).contiguous()
 Y += 0.02 * torch.randn(Y.shape, generator=g, device=dev, dtype=torch.float32).to(torch.complex64)
-h = _lib.Handle(0)
+h = _lib.Handle(local)
 h.set_stream(torch.cuda.current_stream(dev).cuda_stream)
 index_set = torch.zeros(a.batch, a.m, dtype=torch.int32, device=dev)
 xsel = torch.zeros(a.batch, a.m, dtype=torch.complex64, device=dev)
@@ -55,12 +61,18 @@ if a.dbg:
     print(json.dumps(dict(dbg_last_launch=dict(mma_total_cyc=d[0], mma_wait_full=d[1], mma_wait_tready=d[2], mma_wait_d2empty=d[3], items=d[4],
                                                prod_wait_empty=d[5], prod_total_cyc=d[6]))), file=sys.stderr)
 _lib.lib.jstsp_profile(h.ptr, 2)
+if world > 1:
+    dist.barrier()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(a.steps):
     run()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.steps
+if world > 1:
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)                  # device time, max over ranks
+    ms = float(t.item())
 kern = {}
 slot = 0
 while True:
@@ -73,6 +85,9 @@ while True:
 _lib.lib.jstsp_profile(h.ptr, 0)
 cmac = N * M * P + G * N * P                      # per iteration per trial: R B^H then A^H T
 corr = (kern.get("omp_kron_corr_tc") or kern.get("omp_kron_corr", {})).get("avg_ms")
-print(json.dumps(dict(shape=a.shape, batch=a.batch, m=a.m, ms_per_call=ms, trials_per_s=a.batch / ms * 1e3,
+if rank == 0:
+  print(json.dumps(dict(shape=a.shape, n_gpus=world, batch_per_gpu=a.batch, m=a.m, ms_per_call=ms, trials_per_s=world * a.batch / ms * 1e3,
                       corr_tflops=(8 * cmac * a.batch / (corr * 1e-3) / 1e12) if corr else None,
-                      ambiguous_trials=int((amb > 0).sum()), kernels=kern)))
+                        ambiguous_trials=int((amb > 0).sum()), kernels=kern)))
+if world > 1:
+    dist.destroy_process_group()

@@ -21,9 +21,15 @@ ap.add_argument("--batch", type=int, default=1184)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--no-cpu", action="store_true")
 a = ap.parse_args()
-dev = torch.device("cuda", 0)
-g = torch.Generator(device=dev); g.manual_seed(7)
-h = _lib.Handle(0)
+# under torchrun every rank runs its own batch (weak scaling over independent trials); times are the max over ranks
+rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
+g = torch.Generator(device=dev); g.manual_seed(7 + rank)
+h = _lib.Handle(local)
 h.set_stream(torch.cuda.current_stream(dev).cuda_stream)
 L = _lib.lib
 F32, DEV = _lib.F32, _lib.DEVICE
@@ -41,12 +47,18 @@ LAST_KERNELS = {}
 
 def timed(fn):
     fn(); torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
         fn()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
     L.jstsp_profile(h.ptr, 2)                       # one more call with per-kernel-class CUDA events (not part of the timing above)
     fn(); torch.cuda.synchronize()
     LAST_KERNELS.clear()
@@ -63,7 +75,7 @@ def timed(fn):
 
 
 def cpu_rate(fn, n):
-    if a.no_cpu:
+    if a.no_cpu or rank != 0 or world > 1:
         return None
     t0 = time.perf_counter()
     for _ in range(n):
@@ -72,9 +84,11 @@ def cpu_rate(fn, n):
 
 
 def emit(name, shape, batch, ms, bytes_per_unit, cpu, note, flops_per_unit=None):
-    rate = batch / ms * 1e3
-    gbs = bytes_per_unit * rate / 1e9
-    line = dict(solver=name, shape=shape, batch=batch, ms_per_call=ms, units_per_s=rate, algorithmic_bytes_per_unit=bytes_per_unit,
+    rate = world * batch / ms * 1e3
+    gbs = bytes_per_unit * rate / 1e9 / world                 # per-GPU bandwidth for the roofline
+    if rank != 0:
+        return
+    line = dict(solver=name, shape=shape, n_gpus=world, batch=batch, ms_per_call=ms, units_per_s=rate, algorithmic_bytes_per_unit=bytes_per_unit,
                 roofline=dict(bound="hbm", achieved=gbs, peak=HBM, unit="GB/s", frac=gbs / HBM), note=note, kernels=dict(LAST_KERNELS),
                 cpu_baseline=dict(value=cpu, unit="units/s", kind="port", cores=os.cpu_count()) if cpu else None)
     if flops_per_unit:
@@ -151,3 +165,6 @@ emit("nmse", [G_, P_], B, ms, 2 * 8 * G_ * P_, cpu_rate(lambda: est.nmse(se0, zb
 sc, rt = one(0.3), one(0.0)
 ms = timed(lambda: h.check(L.jstsp_log2det_rate(h.ptr, F32, DEV, G_, P_, B, p(Zb), G_ * P_, p(sc), p(rt))))
 emit("log2det_rate", [G_, P_], B, ms, 8 * G_ * P_, cpu_rate(lambda: est.log2det_rate(zb0, 0.3), 50), "read X once; Gram + fp64 Jacobi eigenvalues")
+
+if world > 1:
+    dist.destroy_process_group()
