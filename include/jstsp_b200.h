@@ -216,7 +216,9 @@ int jstsp_sparse_admm(jstsp_handle* h, int dtype, int mem, int Mr, int Mt, int b
  *   sigma (noise variance) and L (expected non-zeros) one double per trial.  The spectral basis is an
  *   input, computed by the caller exactly where vamp.m:32 calls svd: for m <= n `basis` is the m x m
  *   complex eigenvector matrix U of A A^H and d its m eigenvalues (= squared singular values of A,
- *   each of which appears twice in the reference's real-embedded d).  m > n is not implemented. */
+ *   each of which appears twice in the reference's real-embedded d).  For m > n (VampGlmEst.m:407-411,
+ *   which works in the eigenbasis of A'A, :72-86) `basis` is the n x n eigenvector matrix V of A^H A
+ *   (the V of the same svd) and d its n eigenvalues. */
 int jstsp_vamp(jstsp_handle* h, int dtype, int mem, int m, int n, int batch, int nit, double damp,
                const void* y, long long ld_y, const void* A, long long ld_A, const double* sigma, const double* L,
                const void* basis, long long ld_basis, const void* d, long long ld_d, void* x, long long ld_x);

@@ -378,10 +378,11 @@ def vamp(y, A, sigma, L, *, precision="f64", handle=None, nit=100, damp=0.85):
     cd, rd = _CD[precision], _RD[precision]
     A = np.asarray(A, dtype=np.complex128)
     m, n = A.shape
-    if m > n:
-        raise NotImplementedError("vamp: m > n (VampGlmEst.m:407-411) is not implemented on the GPU path yet")
-    U, s, _ = np.linalg.svd(A, full_matrices=True)                # complex svd of A; embedding doubles each singular value
-    d = np.concatenate([s ** 2, np.zeros(m - s.size)])
+    U, s, Vh = np.linalg.svd(A, full_matrices=True)               # complex svd of A; embedding doubles each singular value
+    if m <= n:
+        d = np.concatenate([s ** 2, np.zeros(m - s.size)])
+    else:                                                         # VampGlmEst.m:72-86,407-411 work in the eigenbasis of A'A when M > N
+        U, d = Vh.conj().T, s ** 2
     yv = np.ascontiguousarray(np.asarray(y).reshape(1, -1), dtype=cd)
     Am, Um = _cm(A, cd), _cm(U, cd)
     dv = np.ascontiguousarray(d, dtype=rd)

@@ -27,6 +27,7 @@ struct AdmmP {
     int MC, nmc;                        // column chunk of the X-update/T1 kernel
     int type, angles, n_indx;
     int iter, imax;
+    int res_small_smem;                 // k_res: A / AHA / pA staged in shared memory (0: read through L2, 64 fp64 rows)
     const cx<T>* subY; long long ld_subY;
     const T* omega;    long long ld_omega;
     const cx<T>* A;    long long ld_A;
@@ -331,6 +332,9 @@ __global__ void __launch_bounds__(kThreads) k_res(AdmmP<T> p) {
     cx<T>* prod = reinterpret_cast<cx<T>*>(smem);
     cx<T>* t1s = prod + (size_t)R * CC;
     cx<T>* small = t1s + (size_t)N * CC;      // A (N x G) then AHA (G x G)   | 'std': pA (G x N)
+    // the small operands sit in shared memory when the tile leaves room, else they are read in place (L2-resident)
+    const cx<T>* sA = small;                  // A (N x G) | 'std': pA (G x N)
+    const cx<T>* sAHA = small + (size_t)N * G;
     const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
     const int rg = warp % NG, cg = warp / NG;
     if (cg < ExpandSmem<T, CB>::ncg(NG)) {
@@ -353,11 +357,14 @@ __global__ void __launch_bounds__(kThreads) k_res(AdmmP<T> p) {
         }
         const cx<T>* A = p.A + (long long)b * p.ld_A;
         const cx<T>* AHA = p.AHA + (long long)b * p.ld_AHA;
-        for (int t = threadIdx.x; t < N * G; t += kThreads) small[t] = A[t];
-        for (int t = threadIdx.x; t < G * G; t += kThreads) small[N * G + t] = AHA[t];
+        if (p.res_small_smem) {
+            for (int t = threadIdx.x; t < N * G; t += kThreads) small[t] = A[t];
+            for (int t = threadIdx.x; t < G * G; t += kThreads) small[N * G + t] = AHA[t];
+        } else { sA = A; sAHA = AHA; }
     } else {
         const cx<T>* pA = p.pA + (long long)b * p.ld_pA;
-        for (int t = threadIdx.x; t < G * N; t += kThreads) small[t] = pA[t];
+        if (p.res_small_smem) { for (int t = threadIdx.x; t < G * N; t += kThreads) small[t] = pA[t]; }
+        else sA = pA;
     }
     __syncthreads();
     cx<T>* out = (approx ? p.Res : p.V) + (size_t)b * G * P + (size_t)c0 * G;
@@ -365,10 +372,10 @@ __global__ void __launch_bounds__(kThreads) k_res(AdmmP<T> p) {
         int g = t % G, c = t / G;
         T re = 0, im = 0;
         if (approx) {
-            for (int n = 0; n < N; ++n) { cx<T> a = small[n + N * g], v = t1s[n + (size_t)N * c]; cmac<T>(re, im, a.re, -a.im, v.re, v.im); }
-            for (int k = 0; k < G; ++k) { cx<T> a = small[N * G + g + G * k], v = prod[k + (size_t)R * c]; cmac<T>(re, im, -a.re, -a.im, v.re, v.im); }
+            for (int n = 0; n < N; ++n) { cx<T> a = sA[n + N * g], v = t1s[n + (size_t)N * c]; cmac<T>(re, im, a.re, -a.im, v.re, v.im); }
+            for (int k = 0; k < G; ++k) { cx<T> a = sAHA[g + G * k], v = prod[k + (size_t)R * c]; cmac<T>(re, im, -a.re, -a.im, v.re, v.im); }
         } else {
-            for (int n = 0; n < N; ++n) { cx<T> a = small[g + G * n], v = prod[n + (size_t)R * c]; cmac<T>(re, im, a.re, a.im, v.re, v.im); }
+            for (int n = 0; n < N; ++n) { cx<T> a = sA[g + G * n], v = prod[n + (size_t)R * c]; cmac<T>(re, im, a.re, a.im, v.re, v.im); }
         }
         out[g + (size_t)G * c] = mk<T>(re, im);
     }
@@ -819,7 +826,12 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
     if (want_conv) { size_t need = 2 * sizeof(T) * (size_t)p.RP * XC; if (need > sm_xs) sm_xs = need; }
     const int RPr = approx ? p.GP8 : p.RP, NGr = approx ? p.GNG : p.NG, Rr = approx ? G : N;
     size_t sm_res = ExpandSmem<T, CB>::bytes(NGr, RPr);
-    { size_t epi = sizeof(cx<T>) * ((size_t)Rr * PCr + (size_t)N * PCr + (size_t)N * G + (size_t)G * G); if (epi > sm_res) sm_res = epi; }
+    {
+        const size_t tile = sizeof(cx<T>) * ((size_t)Rr * PCr + (size_t)N * PCr), small = sizeof(cx<T>) * ((size_t)N * G + (size_t)G * G);
+        p.res_small_smem = (tile + small <= h->smem_optin) ? 1 : 0;       // 64 fp64 rows: 128 KB + 128 KB would not fit
+        const size_t epi = tile + (p.res_small_smem ? small : 0);
+        if (epi > sm_res) sm_res = epi;
+    }
     size_t sm_q = ExpandSmem<T, CB>::bytes(p.GNG, p.GP8);
     { size_t epi = sizeof(cx<T>) * ((size_t)G * ExpandSmem<T, CB>::chunk_cols(p.GNG) + (size_t)G * G); if (epi > sm_q) sm_q = epi; }
     const size_t sm_v = sizeof(cx<T>) * ((size_t)G * kPV + (size_t)N * G);

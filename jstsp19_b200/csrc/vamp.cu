@@ -107,6 +107,11 @@ __global__ void __launch_bounds__(256) k_vamp_pre(VampP<T> p) {
     const double ratio = gam2x / gam2z;
     for (int k = threadIdx.x; k < K; k += blockDim.x) { const double iv = 1.0 / ((double)d[k] + ratio); inv[k] = (T)iv; acc += (double)d[k] * iv; }   // :400
     const double alf = block_sum<T>(acc) / (double)n - kEps;      // (2 * sum)/(2n) - eps: every eigenvalue counts twice in the embedding (:401)
+    if (m > n) {                                                  // r2 * (gam2x / gam2z), the first term of :408
+        const int mx = m;
+        cx<T>* t3 = p.t3 + (size_t)b * mx;
+        for (int k = threadIdx.x; k < n; k += blockDim.x) { const cx<T> r = r2[k]; t3[k] = mk<T>((T)(r.re * ratio), (T)(r.im * ratio)); }
+    }
     if (threadIdx.x == 0) { sc[S_G2X] = gam2x; sc[S_G2Z] = gam2z; sc[S_ALF] = alf; sc[S_G2ZOLD] = gam2z; sc[S_G1XOLD] = gam1x; }
 }
 
@@ -167,11 +172,12 @@ __global__ void __launch_bounds__(256) k_vamp_post(VampP<T> p, const cx<T>* x2v,
     const double alf = sc[S_ALF], gam2x = sc[S_G2X], gam2z = sc[S_G2Z], del = (double)m / (double)n;
     cx<T>* r1 = p.r1 + (size_t)b * n; const cx<T>* r2 = p.r2 + (size_t)b * n; const cx<T>* x2 = x2v + (long long)b * ld_t;
     cx<T>* p1 = p.p1 + (size_t)b * m; const cx<T>* p2 = p.p2 + (size_t)b * m; cx<T>* z2 = p.z2 + (size_t)b * m;
-    const cx<T>* rs = resid + (long long)b * ld_t; const cx<T>* ud = udt + (long long)b * ld_t;      // p2 - A r2 ; U (d .* t)
+    const cx<T>* rs = resid ? resid + (long long)b * ld_t : nullptr; const cx<T>* ud = udt + (long long)b * ld_t;      // p2 - A r2 ; U (d .* t)
     for (int k = threadIdx.x; k < n; k += blockDim.x)
         r1[k] = mk<T>((T)((x2[k].re - r2[k].re * (1.0 - alf)) / alf), (T)((x2[k].im - r2[k].im * (1.0 - alf)) / alf));        // :467
     for (int k = threadIdx.x; k < m; k += blockDim.x) {
-        double zr = (double)p2[k].re - rs[k].re + ud[k].re, zi = (double)p2[k].im - rs[k].im + ud[k].im;   // z2 = A r2 + U (d .* t)  (:406)
+        double zr = ud[k].re, zi = ud[k].im;                                                               // m > n: z2 = A x2 (:411)
+        if (resid) { zr += (double)p2[k].re - rs[k].re; zi += (double)p2[k].im - rs[k].im; }               // z2 = A r2 + U (d .* t)  (:406)
         if (i > 0) { zr = p.damp * zr + (1.0 - p.damp) * z2[k].re; zi = p.damp * zi + (1.0 - p.damp) * z2[k].im; }            // :415
         z2[k] = mk<T>((T)zr, (T)zi);
         p1[k] = mk<T>((T)((del * zr - p2[k].re * alf) / (del - alf)), (T)((del * zi - p2[k].im * alf) / (del - alf)));        // :468
@@ -246,10 +252,18 @@ static int run_vamp(Handle* h, int mem, int m, int n, int batch, int nit, double
         dim3 g(trans ? (cols + 7) / 8 : (rows + 255) / 256, batch);
         JSTSP_LAUNCH(h, PK_OTHER, (k_matvec<T><<<g, 256, 0, st>>>(q)));
     };
-    if (m > n) return fail(h, JSTSP_E_UNSUPPORTED, "vamp: the m > n branch (VampGlmEst.m:407-411) is not implemented yet");
     for (int it = 0; it < nit; ++it) {
         p.it = it;
         JSTSP_LAUNCH(h, PK_OTHER, (k_vamp_pre<T><<<batch, 256, 0, st>>>(p)));
+        if (m > n) {
+            // VampGlmEst.m:407-411 (M > N): basis = V (n x n) of A^H A, d its n eigenvalues
+            mv(p.A, p.ld_A, m, n, 1, p.p2, m, p.t0, mx, p.t3, mx, 0, nullptr, 0, nullptr, 0);            // t0 = r2 gam2x/gam2z + A^H p2
+            mv(p.basis, p.ld_b, n, n, 1, p.t0, mx, p.t1, mx, nullptr, 0, 0, nullptr, 0, nullptr, 0);     // t1 = V^H t0
+            mv(p.basis, p.ld_b, n, n, 0, p.t1, mx, p.t3, mx, nullptr, 0, 0, p.inv, K, nullptr, 0);       // t3 = x2 = V (inv .* t1)
+            mv(p.A, p.ld_A, m, n, 0, p.t3, mx, p.t2, mx, nullptr, 0, 0, nullptr, 0, nullptr, 0);         // t2 = z2 = A x2
+            JSTSP_LAUNCH(h, PK_OTHER, (k_vamp_post<T><<<batch, 256, 0, st>>>(p, p.t3, (const cx<T>*)nullptr, p.t2, (long long)mx)));
+            continue;
+        }
         // VampGlmEst.m:402-406 (M <= N)
         mv(p.A, p.ld_A, m, n, 0, p.r2, n, p.t0, mx, p.p2, m, 1, nullptr, 0, nullptr, 0);             // t0 = p2 - A r2
         mv(p.basis, p.ld_b, m, m, 1, p.t0, mx, p.t1, mx, nullptr, 0, 0, nullptr, 0, nullptr, 0);     // t1 = U^H t0

@@ -8,7 +8,6 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     gw_nargs(fn, nrhs, 4, nlhs, 1);
     int m = (int)mxGetM(prhs[1]), n = (int)mxGetN(prhs[1]);
     if ((int)mxGetNumberOfElements(prhs[0]) != m) mexErrMsgIdAndTxt("jstsp:size", "%s: length(y) must equal size(A,1)", fn);
-    if (m > n) mexErrMsgIdAndTxt("jstsp:unsupported", "%s: m > n (VampGlmEst.m:407-411) is not implemented", fn);
     double sigma = gw_scalar(prhs[2], fn, "sigma"), L = gw_scalar(prhs[3], fn, "L");
     mxArray* out[3] = {NULL, NULL, NULL};
     mxArray* in[1] = {(mxArray*)prhs[1]};
@@ -16,9 +15,10 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     void *t0, *t1, *tu;
     const mxComplexDouble* y = gw_complex(prhs[0], fn, "y", &t0);
     const mxComplexDouble* A = gw_complex(prhs[1], fn, "A", &t1);
-    const mxComplexDouble* U = gw_complex(out[0], fn, "U", &tu);
+    /* m <= n: U (m x m) of A A' (VampGlmEst.m:402-406); m > n: V (n x n) of A'A, which VampGlmEst.m:72-86 derives itself (:407-411) */
+    const mxComplexDouble* U = gw_complex(out[m <= n ? 0 : 2], fn, "U", &tu);
     double* d = (double*)mxCalloc(m, sizeof(double));
-    {   /* d = diag(S).^2, zero padded to m (vamp.m:33-34) */
+    {   /* d = diag(S).^2, zero padded to m (vamp.m:33-34); the first min(m,n) entries are the eigenvalues either way */
         void* ts; const mxComplexDouble* S = gw_complex(out[1], fn, "S", &ts);
         int k = m < n ? m : n;
         for (int i = 0; i < k; ++i) d[i] = S[i + (size_t)m * i].real * S[i + (size_t)m * i].real;

@@ -68,10 +68,10 @@ def test_delay_sweep(L):
     assert _rel(S1, S0a) < 2e-5
 
 
-@pytest.mark.parametrize("Nr,precision,tol", [(64, "f32", 3e-5), (48, "f64", 1e-9), (48, "f32", 3e-5)])
+@pytest.mark.parametrize("Nr,precision,tol", [(64, "f32", 3e-5), (64, "f64", 1e-9), (48, "f64", 1e-9), (48, "f32", 3e-5)])
 def test_large_array_rows(Nr, precision, tol):
-    """Config 4 geometry at reduced length: Nr = 64 receive rows (N = G = 64), L = 8 taps, Nt = 16.  The fp64 kernels stop at
-    48 rows (shared memory of the exact-LS / residual kernel); 64 rows in fp64 is refused loudly (next test)."""
+    """Config 4 geometry at reduced length: Nr = 64 receive rows (N = G = 64), L = 8 taps, Nt = 16.  At 64 fp64 rows the
+    residual kernel reads A / A'A through L2 instead of staging them (its product tile alone is 128 KB of shared memory)."""
     import jstsp19_b200 as jb
     shape = fx.Shape(Nt=16, Nr=Nr, L=8, Mr=8, T=8)
     t = fx.make_trial(shape, 5.0, 640)
@@ -83,10 +83,21 @@ def test_large_array_rows(Nr, precision, tol):
     assert _rel(S2, S0) < tol
 
 
-def test_fp64_at_64_rows_is_refused_by_name():
+def test_fp64_exact_ls_at_64_rows():
+    """'std' branch (proposed_algorithm.m:29,53) at config 4's row count in the MEX gateways' precision."""
+    import jstsp19_b200 as jb
+    t = fx.make_trial(fx.Shape(Nt=16, Nr=64, L=8, Mr=8, T=16), 5.0, 641)
+    args = (t["subY"], t["Omega"], t["A"], t["B"], 10, t["tau_Y"], t["tau_Z"], t["rho"], "std")
+    S0, Y0, c0 = est.proposed_algorithm_structured(*args)
+    S1, Y1, c1 = jb.proposed_algorithm(*args, precision="f64")
+    assert _rel(S1, S0) < 1e-7 and _rel(Y1, Y0) < 1e-7, (_rel(S1, S0), _rel(Y1, Y0))
+    np.testing.assert_allclose(np.asarray(c1, dtype=np.float64)[:, :2], c0[:, :2], rtol=1e-6)
+
+
+def test_more_than_64_rows_is_refused_by_name():
     import jstsp19_b200 as jb
     from jstsp19_b200._lib import JstspError
-    t = fx.make_trial(fx.Shape(Nt=16, Nr=64, L=8, Mr=8, T=8), 5.0, 641)
+    t = fx.make_trial(fx.Shape(Nt=8, Nr=72, L=2, Mr=8, T=4), 5.0, 642)
     with pytest.raises(JstspError) as e:
         jb.proposed_algorithm(t["subY"], t["Omega"], t["A"], t["B"], 5, t["tau_Y"], t["tau_Z"], t["rho"], "approximate", precision="f64")
-    assert e.value.code == -3 and "shared memory" in str(e.value) and "k_res" in str(e.value)
+    assert e.value.code == -3 and "64" in str(e.value)

@@ -106,6 +106,21 @@ def test_vamp_matches_oracle_fp64():
         assert _rel(x1, x0.real if False else x0) < 1e-8, (sigma, _rel(x1, x0))
 
 
+@pytest.mark.parametrize("precision,tol", [("f64", 1e-8), ("f32", 2e-3)])
+def test_vamp_tall_system_matches_oracle(precision, tol):
+    """m > n: VampGlmEst.m:407-411 (eigenbasis of A'A, which VampGlmEst.m:72-86 derives itself when M > N)."""
+    import jstsp19_b200 as jb
+    rng = np.random.default_rng(16)
+    m, n, k = 100, 60, 6
+    A = (rng.standard_normal((m, n)) + 1j * rng.standard_normal((m, n))) / np.sqrt(2 * m)
+    x = np.zeros(n, complex); x[rng.choice(n, k, replace=False)] = 3 * (rng.standard_normal(k) + 1j * rng.standard_normal(k))
+    y = A @ x + 0.01 * (rng.standard_normal(m) + 1j * rng.standard_normal(m))
+    for sigma, Lnz in ((1e-4, 2 * k), (1.0, 20)):
+        x0 = ovamp.vamp_literal(y, A, sigma, Lnz)
+        x1 = jb.vamp(y, A, sigma, Lnz, precision=precision)
+        assert _rel(x1, x0) < tol, (sigma, _rel(x1, x0))
+
+
 def test_vamp_config0_system():
     """vamp(y, Phi, 1, numOfnz) on the conventional-HBF system of plot_errorVSsnr.m:79-80,100 (512 x 512,
     condition number ~3e4).  On this system the 100-iteration VAMP recursion amplifies rounding: two fp64

@@ -278,3 +278,11 @@ def test_vamp_gateway_uses_matlab_svd():
     (x1,) = g(1, y, A, 1.0, 5)
     x0 = ovamp.vamp_literal(y, A, 1.0, 5)
     assert _rel(x1.reshape(-1), np.asarray(x0).reshape(-1)) < 1e-6
+    # tall system: the gateway hands V of the same svd to the library (VampGlmEst.m:407-411)
+    At = (rng.standard_normal((n, m)) + 1j * rng.standard_normal((n, m))) / np.sqrt(n)
+    xt = np.zeros(m, complex)
+    xt[rng.choice(m, 3, replace=False)] = rng.standard_normal(3) + 1j * rng.standard_normal(3)
+    yt = At @ xt + 0.01 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    (x1,) = g(1, yt, At, 1.0, 3)
+    x0 = ovamp.vamp_literal(yt, At, 1.0, 3)
+    assert _rel(x1.reshape(-1), np.asarray(x0).reshape(-1)) < 1e-6

@@ -131,6 +131,31 @@ def test_vamp_runs_and_recovers_sparse_vector():
     assert np.all(np.isfinite(xh)) and _rel(xh, x) < 0.2
 
 
+def test_vamp_tall_branch_equals_complex_form():
+    """m > n (VampGlmEst.m:407-411): the real-embedded transcription equals the same iteration written in complex arithmetic
+    on A with the eigenbasis of A'A - the form the kernels use (every eigenvalue appears twice in the embedding)."""
+    rng = np.random.default_rng(26)
+    m, n, k = 50, 30, 4
+    A = (rng.standard_normal((m, n)) + 1j * rng.standard_normal((m, n))) / np.sqrt(2 * m)
+    x = np.zeros(n, complex); x[rng.choice(n, k, replace=False)] = 3 * (rng.standard_normal(k) + 1j * rng.standard_normal(k))
+    y = A @ x + 0.01 * (rng.standard_normal(m) + 1j * rng.standard_normal(m))
+    xh = ovamp.vamp_literal(y, A, 1e-4, 2 * k)
+    assert np.all(np.isfinite(xh)) and _rel(xh, x) < 0.1
+    # one LMMSE half-step in both forms on random vectors
+    Bm = np.block([[A.real, -A.imag], [A.imag, A.real]])
+    r2, p2 = rng.standard_normal(n) + 1j * rng.standard_normal(n), rng.standard_normal(m) + 1j * rng.standard_normal(m)
+    ratio = 0.37
+    d2, V2 = np.linalg.eigh(Bm.T @ Bm)
+    emb = lambda v: np.concatenate([v.real, v.imag])
+    t = V2.T @ (emb(r2) * ratio + Bm.T @ emb(p2))
+    x2e = V2 @ (t / (d2 + ratio))
+    _, s, Vh = np.linalg.svd(A, full_matrices=True)
+    V = Vh.conj().T
+    x2c = V @ ((V.conj().T @ (r2 * ratio + A.conj().T @ p2)) / (s ** 2 + ratio))
+    assert np.allclose(emb(x2c), x2e, rtol=1e-10, atol=1e-12)
+    assert np.isclose(np.sum(d2 / (d2 + ratio)) / (2 * n), np.sum(s ** 2 / (s ** 2 + ratio)) / n)
+
+
 def test_nmse_follows_snr():
     """Order-of-magnitude pin against results/errorVSsnr.fig: the proposed
     estimator's NMSE falls monotonically with SNR."""
