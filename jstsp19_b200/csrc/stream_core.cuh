@@ -234,10 +234,16 @@ struct StreamPipe {
             }
             // release the slot: the LAST warp to finish it refills it (no CTA-wide barrier per stage,
             // warps may run up to STAGES-1 stages apart)
+            // Ordering: the warp's reads of the slot precede the (release) fence, the counter RMWs of all warps form one
+            // modification order, and the refilling thread's (acquire) fence follows its RMW - so every read of the slot
+            // happens before the bulk copy that overwrites it.  compute-sanitizer racecheck does not model this handshake
+            // (it tracks barriers, not atomics) and reports the slot reads against the refill; memcheck is clean.
             __syncwarp();
             if (lane == 0) {
+                __threadfence_block();
                 const int old = atomicAdd(&cnt[slot], 1);
                 if (old == kWarps - 1) {
+                    __threadfence_block();
                     cnt[slot] = 0;
                     if (t + STAGES < nst) issue(t + STAGES);
                 }
