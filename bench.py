@@ -423,12 +423,12 @@ def main():
         avg_ms = prof[top][0] / prof[top][1]
         achieved = kflops[top] / (avg_ms * 1e-3) / 1e12
         peak = pk["bf16_sus"] / 2.0 / 3.0          # TF32 dense = bf16/2; a 3xTF32-equivalent fp32 contraction is scored against TF32/3
-        traffic = None                             # DRAM bytes per launch of that kernel from the committed ncu --set full capture (592 trials)
+        traffic = None                             # DRAM bytes per launch of that kernel from the committed ncu --set full capture (scaled by the trial count)
         tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
         if os.path.exists(tp):
             t = json.load(open(tp)).get(top)
             if t:
-                traffic = t["dram_bytes_per_launch_592_trials"] * nb / 592.0
+                traffic = t["dram_bytes_per_launch_888_trials"] * nb / 888.0 if "dram_bytes_per_launch_888_trials" in t else t["dram_bytes_per_launch_592_trials"] * nb / 592.0
         roof = dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=traffic,
                     kernel=top, avg_launch_ms=avg_ms, share_of_step=prof[top][0] / tot_ms,
                     peak_source=f"{pk['src']} bf16_tflops_sustained/2 (TF32) /3 (3xTF32-equivalent fp32 accuracy), SURVEY.md 8(d)",
@@ -443,6 +443,14 @@ def main():
         r, dt = cpu_port_rate(args.cpu_trials)
         cpu = dict(value=r, unit=UNIT, cores=host_threads(), kind="port",
                    sample=f"{args.cpu_trials} trials of the workload ({dt:.1f} s), structured fp64 NumPy restatement of proposed_algorithm.m")
+        lp = os.path.join(ROOT, "profiles", "r01_cpu_literal.json")      # recorded, not re-timed: one literal trial takes minutes and ~8 GiB
+        if os.path.exists(lp):
+            with open(lp) as fh:
+                lit = json.load(fh)
+            if "metric_literal_admm" in lit:
+                cpu["literal_recorded"] = dict(value=lit["metric_literal_admm"]["per_s"], unit=UNIT, cores=lit.get("cores"), host=lit.get("host"),
+                                               note="the reference's own formulation (dense K1, K2 = kron(B.',A), R = K2'K2, proposed_algorithm.m:14-25) restated in NumPy; "
+                                                    "tools/literal_baseline.py, profiles/r01_cpu_literal.json")
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=warm, ms_per_step=ms / args.steps,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32" if args.precision == "f32" else "f64",
                 data="synthetic",
