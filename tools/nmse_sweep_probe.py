@@ -1,3 +1,6 @@
+"""NMSE statistics of the whole trial loop (engine.TrialPipeline) at the metric shape along the SNR sweep, Imax = 100 and 400:
+mean / median / quantiles of the spectral-norm NMSE (plot_errorVSsnr.m:138-141) and of the Frobenius error, 910 trials per point.
+    python tools/nmse_sweep_probe.py        (needs a GPU; numbers quoted in DESIGN.md section 6)"""
 import torch, sys
 sys.path.insert(0, '.')
 from jstsp19_b200 import synth
