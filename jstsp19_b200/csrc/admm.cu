@@ -1040,7 +1040,8 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
                     dim3 gs(pin.L, nb), gc(q.nmc, nb);
                     JSTSP_LAUNCH(h, PK_PSI_AUX, (psi::k_psi_res<<<gs, 256, sizeof(psi::SmallSmem), st>>>(q, pin)));
                     JSTSP_LAUNCH(h, PK_PSI_G, (psi::k_psi_g<<<gc, tc::THREADS, psi::G_SMEM, st>>>(q, pmaps, pin)));
-                    JSTSP_LAUNCH(h, PK_PSI_STEP, (psi::k_psi_step<<<gs, 256, sizeof(psi::SmallSmem), st>>>(q, pin, it + 1 < imax ? 1 : 0)));
+                    const bool more = it + 1 < imax;            // XV only feeds the next iteration
+                    JSTSP_LAUNCH(h, PK_PSI_STEP, (psi::k_psi_step<<<gs, 256, sizeof(psi::SmallSmem), st>>>(q, pin, more ? 1 : 0, more ? 1 : 0)));
                 }
             } else if (fast_v) {
                 JSTSP_LAUNCH(h, PK_RES, (k_vstep_fast<T><<<nb, kThreads, sm_fv, st>>>(q)));

@@ -433,21 +433,24 @@ __global__ void __launch_bounds__(256, 4) k_psi_res(AdmmP<float> p, In in) {
     JSTSP_STAMP(p, 6, cta_id, 5);
 }
 
+// alpha = res'res / (res' R res) (proposed_algorithm.m:48) from the per-tap / per-chunk partial sums; called by the first warp, same
+// summation order in every CTA of a trial (V and XV must be stepped by the same number)
+__device__ __forceinline__ float psi_alpha(const In& in, int b, int L, int nmc) {
+    double a = 0, c = 0;
+    for (int i = threadIdx.x; i < L; i += 32) a += in.rr[(size_t)b * L + i];
+    for (int i = threadIdx.x; i < nmc; i += 32) c += in.gg[(size_t)b * nmc + i];
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); c += __shfl_down_sync(0xffffffffu, c, o); }
+    return (float)(a / c);
+}
 // alpha = |Res|^2 / |G|^2 ; V += alpha Res ; S = soft(V) [masked] ; XV += alpha G ; operand image of Xs = (A S) B
 // (proposed_algorithm.m:48-58, proposed_algorithm_angles.m:68).  grid (L, nb), block 256
-__global__ void __launch_bounds__(256, 4) k_psi_step(AdmmP<float> p, In in, int make_q) {
+__global__ void __launch_bounds__(256, 4) k_psi_step(AdmmP<float> p, In in, int make_q, int do_xv) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     SmallSmem& sm = *reinterpret_cast<SmallSmem*>(sm_raw);
     __shared__ float s_alpha;
     const int b = blockIdx.y, l = blockIdx.x, Gt = in.Gt, G = p.G, L = in.L;
     if (make_q) load_small(sm, in, p, b);
-    if (threadIdx.x < 32) {                                       // alpha = res'res / (res' R res)  (.m:48)
-        double a = 0, c = 0;
-        for (int i = threadIdx.x; i < L; i += 32) a += in.rr[(size_t)b * L + i];
-        for (int i = threadIdx.x; i < p.nmc; i += 32) c += in.gg[(size_t)b * p.nmc + i];
-        for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); c += __shfl_down_sync(0xffffffffu, c, o); }
-        if (threadIdx.x == 0) s_alpha = (float)(a / c);
-    }
+    if (threadIdx.x < 32) { const float al = psi_alpha(in, b, L, p.nmc); if (threadIdx.x == 0) s_alpha = al; }   // alpha = res'res / (res' R res)  (.m:48)
     __syncthreads();
     const float alpha = s_alpha;
     const float thr = (float)(p.tauS[b] / p.rho[b]);
@@ -465,7 +468,7 @@ __global__ void __launch_bounds__(256, 4) k_psi_step(AdmmP<float> p, In in, int 
         V[t] = v; S[t] = s;
         if (make_q) sm.U[(t % G) + LDU * (t / G)] = s;
     }
-    {   // XV += alpha G on this tap's share of the columns, four independent 16-byte accesses in flight per thread
+    if (do_xv) {   // XV += alpha G on this tap's share of the columns, four independent 16-byte accesses in flight per thread
         const int M = p.M, per = (M + L - 1) / L, m0 = l * per, m1 = (m0 + per) < M ? (m0 + per) : M;
         float4* xv = reinterpret_cast<float4*>(in.XV + (size_t)b * N * M);
         const float4* g = reinterpret_cast<const float4*>(in.Gm + (size_t)b * N * M);
