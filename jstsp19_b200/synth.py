@@ -8,7 +8,8 @@ spatial-sampling mask with exactly ``Mr`` ones per column, dictionaries
 ``A = W_e' Dr`` and ``B_l = Dt' Psi_l`` and the driver-side parameters
 ``tau_Y, tau_Z, rho``.  ``build_from_draws`` takes the raw random draws so the
 CPU tests can check it against the oracle on identical draws; ``make_batch``
-draws them from a counter-based torch generator keyed by (seed, first trial).
+draws them from torch's counter-based (Philox) generator keyed by (seed, global block of 64 trials),
+so a trial's inputs do not depend on how the trials are sharded.
 
 Memory layout of every returned matrix: ``(batch, cols, rows)`` C-contiguous,
 i.e. per-trial COLUMN-MAJOR like the C ABI expects.
@@ -124,19 +125,37 @@ def build_from_draws(s: Shape, coef, u_r, u_t, noise_unit, sym_idx, mask_rank, s
                 pilots=sk.transpose(1, 2).contiguous().to(cdtype))
 
 
-def draw(s: Shape, batch, snr_db, seed, first_trial=0, device="cuda"):
-    """Raw draws of trials [first_trial, first_trial+batch): coefficient, angle uniforms, unit noise, 4-QAM symbol indices, mask ranks and
-    the noise variance.  The generator is keyed by (seed, first_trial) so a rank's shard does not depend on the number of ranks as long as
-    shards start at the same trial indices."""
+DRAW_BLOCK = 64      # trials per generator key
+
+
+def _draw_block(s: Shape, seed, block, device):
+    """The raw numbers of the DRAW_BLOCK trials of global block `block`: one Philox stream per (seed, block)."""
     g = torch.Generator(device=device)
-    g.manual_seed(int(seed) * 1000003 + int(first_trial))
+    g.manual_seed((int(seed) * 1000003 + int(block)) & 0x7FFFFFFFFFFFFFFF)
+    n = DRAW_BLOCK
     f = dict(device=device, dtype=torch.float64, generator=g)
-    coef = torch.complex(torch.randn(batch, s.L, s.Np, **f), torch.randn(batch, s.L, s.Np, **f)) / math.sqrt(2.0)
-    u_r = torch.rand(batch, s.L, s.Np, **f)
-    u_t = torch.rand(batch, s.L, s.Np, **f)
-    noise = torch.complex(torch.randn(batch, s.Nr, s.M, **f), torch.randn(batch, s.Nr, s.M, **f)) / math.sqrt(2.0)
-    sym = torch.randint(0, 4, (batch, s.Nt, s.M), device=device, generator=g)
-    rank = torch.rand(batch, s.Nr, s.M, **f).argsort(dim=1).argsort(dim=1)
+    coef = torch.randn(n, 2, s.L, s.Np, **f)
+    u_r = torch.rand(n, s.L, s.Np, **f)
+    u_t = torch.rand(n, s.L, s.Np, **f)
+    noise = torch.randn(n, 2, s.Nr, s.M, **f)
+    sym = torch.randint(0, 4, (n, s.Nt, s.M), device=device, generator=g)
+    order = torch.rand(n, s.Nr, s.M, **f)
+    return coef, u_r, u_t, noise, sym, order
+
+
+def draw(s: Shape, batch, snr_db, seed, first_trial=0, device="cuda"):
+    """Raw draws of the global trials [first_trial, first_trial+batch): coefficient, angle uniforms, unit noise, 4-QAM symbol indices, mask
+    ranks and the noise variance.  Trials are generated in blocks of DRAW_BLOCK keyed by (seed, global block index), so trial t gets the same
+    numbers whichever shard, batch size or GPU count it is computed under (results independent of the partition)."""
+    lo, hi = int(first_trial), int(first_trial) + int(batch)
+    parts = []
+    for blk in range(lo // DRAW_BLOCK, (hi + DRAW_BLOCK - 1) // DRAW_BLOCK):
+        a, b = max(lo, blk * DRAW_BLOCK) - blk * DRAW_BLOCK, min(hi, (blk + 1) * DRAW_BLOCK) - blk * DRAW_BLOCK
+        parts.append(tuple(t[a:b] for t in _draw_block(s, seed, blk, device)))
+    coef, u_r, u_t, noise, sym, order = (torch.cat(ts, dim=0) if len(ts) > 1 else ts[0].contiguous() for ts in zip(*parts))
+    coef = torch.complex(coef[:, 0], coef[:, 1]) / math.sqrt(2.0)
+    noise = torch.complex(noise[:, 0], noise[:, 1]) / math.sqrt(2.0)
+    rank = order.argsort(dim=1).argsort(dim=1)            # rank of each row within its column: the Mr smallest are sampled (randperm, proposed_hbf.m:37-41)
     snr = torch.as_tensor(snr_db, device=device, dtype=torch.float64).expand(batch) if not torch.is_tensor(snr_db) else snr_db.to(device).double()
     sigma2 = 10.0 ** (-snr / 10.0)
     return coef, u_r, u_t, noise, sym, rank, sigma2

@@ -119,3 +119,16 @@ def test_monte_carlo_reduce_gloo_world2():
     for r in (0, 1):
         assert res[r]["trials"] == 10 and res[r]["flagged"] == 1
         assert res[r]["mean_nmse"] == pytest.approx(expect)
+
+
+def test_draws_do_not_depend_on_the_partition():
+    """trial t gets the same random numbers whatever shard / batch / GPU count it is computed under
+    (blocks of synth.DRAW_BLOCK trials keyed by (seed, global block index))."""
+    from jstsp19_b200 import synth
+    s = synth.Shape(Nt=4, Nr=8, L=2, Mr=2, T=3)
+    whole = synth.draw(s, 100, 5.0, 7, 0, "cpu")
+    for lo, hi in [(0, 100 // 3), (100 // 3, 67), (67, 100), (31, 64), (32, 33)]:
+        part = synth.draw(s, hi - lo, 5.0, 7, lo, "cpu")
+        assert all(torch.equal(w[lo:hi], p) for w, p in zip(whole, part))
+    other = synth.draw(s, 8, 5.0, 8, 0, "cpu")
+    assert not torch.equal(other[0], whole[0][:8])
