@@ -686,11 +686,12 @@ __global__ void __launch_bounds__(THREADS, 2) k_fused_psi(AdmmP<float> p, const 
     if (warp == NWW) {
         // ===== TMA producer =====
         if (lane == 0) {
+            // the pilot tile first: pass 1 (and with it every later phase) waits for it, the workers have slack until X / V1 land
+            mbar_expect_tx(tile_full, TILE);
+            tc::tma_4d(tile, &maps.E, 0, c0, 0, in.ld_Psi ? b : 0, tile_full);
             mbar_expect_tx(&ld_full[0], 2 * SLOT);
             tc::tma_3d(S0, &maps.X, 0, c0, b, &ld_full[0]);
             tc::tma_3d(S1, &maps.V1, 0, c0, b, &ld_full[0]);
-            mbar_expect_tx(tile_full, TILE);
-            tc::tma_4d(tile, &maps.E, 0, c0, 0, in.ld_Psi ? b : 0, tile_full);
             if (S1t == 0) {                                  // no pass 1: the operand region is free for the XV tile right away
                 mbar_expect_tx(&ld_full[2], SLOT);
                 tc::tma_3d(opnd, &maps.XV, 0, c0, b, &ld_full[2]);
