@@ -180,6 +180,26 @@ def test_golden_fixture_frozen():
     assert _rel(S, g["S"]) < 1e-12 and _rel(Y, g["Y"]) < 1e-12
 
 
+def test_golden_solvers_fixture_frozen():
+    """tests/golden/solvers_small.npz (tools/make_golden.py): the restatement of every solver keeps reproducing its frozen outputs."""
+    g = dict(np.load(os.path.join(GOLD, "solvers_small.npz")))
+    a = (g["subY"], g["Omega"], g["A"], g["B"])
+    p = (float(g["tau_Y"]), float(g["tau_Z"]), float(g["rho"]))
+    S, Y, _ = est.proposed_algorithm_structured(*a, 15, *p, "approximate")
+    assert _rel(S, g["S_apx"]) < 1e-10 and _rel(Y, g["Y_apx"]) < 1e-10
+    S, Y, _ = est.proposed_algorithm_structured(*a, 8, *p, "std")
+    assert _rel(S, g["S_std"]) < 1e-9
+    assert _rel(est.svt_literal(g["subY"], float(g["svt_tau"])), g["X_svt"]) < 1e-12
+    assert _rel(est.mc_svt(g["subY"], g["Omega"], 15, p[0], 0.1), g["X_mc_svt"]) < 1e-10
+    assert _rel(est.mc_admm_structured(g["Htrue"], g["subY"], g["Omega"], 15, p[0], p[2])[0], g["X_mc_admm"]) < 1e-10
+    assert _rel(est.sparse_admm_structured(g["sp_H"], g["sp_OH"], g["sp_Dr"], g["sp_Dt"], 15)[0], g["S_sparse"]) < 1e-10
+    x, idx, _, _ = est.omp_literal(g["omp_A"], g["omp_v"], 8)
+    assert idx == [int(k) for k in g["omp_idx"]] and _rel(x, g["omp_x"]) < 1e-10
+    for name in ("wide", "tall"):
+        assert _rel(ovamp.vamp_literal(g[f"vamp_{name}_y"], g[f"vamp_{name}_A"], 1e-4, 10, nit=20), g[f"vamp_{name}_x"]) < 1e-9
+    assert g["hbf_Omega"].sum(axis=0).tolist() == [int(g["hbf_dims"][2])] * g["hbf_Omega"].shape[1]      # Mr ones per column (proposed_hbf.m:36-41)
+
+
 def test_log2det_rate_known_answers():
     """log2 det(I + c X X') against closed forms: orthogonal rows, and the matrix-determinant lemma for a rank-1 X."""
     rng = np.random.default_rng(3)
