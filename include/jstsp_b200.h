@@ -144,6 +144,9 @@ int jstsp_proposed_algorithm_pilots(jstsp_handle* h, const jstsp_admm_desc* d, i
 /* Path taken by the last jstsp_proposed_algorithm_psi call on this handle: 1 = dense kernels on the materialised
  * dictionary, 2 = Psi-domain tcgen05 kernel (0 = no call yet). */
 int jstsp_last_path(const jstsp_handle* h);
+/* Form of the Psi-domain path taken by the last pass: 1 = the whole solve (all Imax iterations of proposed_algorithm.m:32-70) ran
+ * in one persistent kernel per pass (csrc/admm_mega.cuh), 0 = four kernels per iteration (csrc/admm_psi.cuh). */
+int jstsp_last_variant(const jstsp_handle* h);
 
 /* ---- singular-value thresholding and the SVT-based benchmark solvers -------------- */
 /* X = svt(Y, tau)   replaces benchmark_algorithms/svt.m:1-15 (returns zeros when a

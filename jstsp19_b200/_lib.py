@@ -67,6 +67,7 @@ def _load():
     lib.jstsp_proposed_algorithm_psi.argtypes = [vp, C.POINTER(AdmmDesc), i, i, vp, vp, vp, vp, vp, ll, vp, ll, i, i, vp, vp, vp, vp, vp, vp]
     lib.jstsp_proposed_algorithm_pilots.argtypes = [vp, C.POINTER(AdmmDesc), i, i, vp, vp, vp, vp, vp, ll, vp, ll, i, i, vp, vp, vp, vp, vp, vp]
     lib.jstsp_last_path.argtypes = [vp]
+    lib.jstsp_last_variant.argtypes = [vp]
     lib.jstsp_svt.argtypes = [vp, i, i, i, i, i, vp, ll, vp, vp, ll]
     lib.jstsp_mc_svt.argtypes = [vp, i, i, i, i, i, i, vp, ll, vp, ll, vp, vp, vp, ll]
     lib.jstsp_omp.argtypes = [vp, i, i, i, i, i, i, vp, ll, vp, ll, vp, ll, vp, vp, vp, C.c_double]
@@ -91,7 +92,7 @@ lib = _load()
 EXPORTED = [
     "jstsp_create", "jstsp_destroy", "jstsp_last_error", "jstsp_version", "jstsp_set_stream",
     "jstsp_synchronize", "jstsp_launch_count", "jstsp_set_chunk", "jstsp_profile", "jstsp_profile_read", "jstsp_debug_buffer",
-    "jstsp_proposed_algorithm", "jstsp_proposed_algorithm_angles", "jstsp_proposed_algorithm_psi", "jstsp_proposed_algorithm_pilots", "jstsp_last_path",
+    "jstsp_proposed_algorithm", "jstsp_proposed_algorithm_angles", "jstsp_proposed_algorithm_psi", "jstsp_proposed_algorithm_pilots", "jstsp_last_path", "jstsp_last_variant",
     "jstsp_svt", "jstsp_mc_svt", "jstsp_mc_admm", "jstsp_omp", "jstsp_omp_kron", "jstsp_somp", "jstsp_sparse_admm", "jstsp_vamp",
     "jstsp_wideband_mmwave_channel", "jstsp_measure", "jstsp_create_beamformer", "jstsp_qam4mod", "jstsp_nmse", "jstsp_admm_parameters", "jstsp_log2det_rate",
 ]
@@ -140,6 +141,11 @@ class Handle:
             out[name.value.decode()] = (ms.value, n.value)
             slot += 1
         return out
+
+    @property
+    def last_variant(self) -> int:
+        """Form of the Psi-domain path of the last pass: 1 = one persistent kernel per pass (csrc/admm_mega.cuh), 0 = four kernels per iteration."""
+        return int(lib.jstsp_last_variant(self._h))
 
     @property
     def last_path(self) -> int:

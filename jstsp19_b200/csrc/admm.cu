@@ -59,6 +59,7 @@ struct AdmmP {
 #include "admm_fast.cuh"
 #include "admm_tc.cuh"
 #include "admm_psi.cuh"
+#include "admm_mega.cuh"
 #include <type_traits>
 namespace jstsp {
 
@@ -657,6 +658,10 @@ __global__ void __launch_bounds__(256) k_expand_pilots(const cx<T>* __restrict__
         o[i] = t >= 0 ? s[k + (size_t)Nt * t] : conj(s[k + (size_t)Nt * (-t)]);
     }
 }
+static bool mega_enabled() {
+    const char* e = getenv("JSTSP_MEGA");           // developer switch: 0 = the four-kernel form of the structured path
+    return !(e && atoi(e) == 0);
+}
 static bool psi_fast_enabled() {
     const char* e = getenv("JSTSP_PSI_DENSE");      // developer switch: force the materialised-B kernels
     return !(e && atoi(e) != 0);
@@ -973,6 +978,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
         if constexpr (std::is_same<T, float>::value) {
             if (use_psi) {
                 JSTSP_CUDA(h, cudaMemsetAsync(pin.XV, 0, esz * NM * nb, st));
+                JSTSP_CUDA(h, cudaMemsetAsync(pin.Gm, 0, esz * NM * nb, st));
                 JSTSP_CUDA(h, cudaMemsetAsync(pin.T1p, 0, esz * (size_t)nb * N * pin.L * psi::NT, st));
             }
         }
@@ -1001,8 +1007,19 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
         cx<T>* const Wslots = q.W;
         const size_t wslot = (size_t)N * N * nb;
         q.iter = 0;
-        if (imax > 0) JSTSP_LAUNCH(h, PK_EIG, (k_svt_weights<T><<<nb, 128, sm_j, st>>>(q)));      // W(0) from the zero Gram
-        for (int it = 0; it < imax; ++it) {
+        // whole solve in one persistent kernel (admm_mega.cuh) when the structured path also has the unitary DFT grid and L <= 4
+        bool use_mega = false;
+        if constexpr (std::is_same<T, float>::value) {
+            use_mega = use_psi && pin.dft && pin.L <= mega::MEGA_MAXL && mega_enabled() && mega::SMEM <= h->smem_optin;
+            if (use_mega && imax > 0) {
+                if ((rc = set_smem(h, mega::k_psi_mega, mega::SMEM))) return rc;
+                const int grid = nb < h->sm_count ? nb : h->sm_count;
+                JSTSP_LAUNCH(h, PK_PSI_MEGA, (mega::k_psi_mega<<<grid, mega::MTHREADS, mega::SMEM, st>>>(q, pmaps, pin, nb)));
+            }
+            h->last_variant = use_mega ? 1 : 0;
+        }
+        if (imax > 0 && !use_mega) JSTSP_LAUNCH(h, PK_EIG, (k_svt_weights<T><<<nb, 128, sm_j, st>>>(q)));      // W(0) from the zero Gram
+        for (int it = 0; it < imax && !use_mega; ++it) {
             q.iter = it;
             q.W = Wslots + (size_t)(it & 1) * wslot;
             if (angles) { dim3 g(1, nb); JSTSP_LAUNCH(h, PK_OTHER, (k_mask_grow<T><<<g, 64, 0, st>>>(q))); }
@@ -1175,3 +1192,4 @@ extern "C" int jstsp_proposed_algorithm_pilots(jstsp_handle* h, const jstsp_admm
 }
 
 extern "C" int jstsp_last_path(const jstsp_handle* h) { return h ? h->last_path : 0; }
+extern "C" int jstsp_last_variant(const jstsp_handle* h) { return h ? h->last_variant : 0; }

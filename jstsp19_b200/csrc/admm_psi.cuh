@@ -70,8 +70,8 @@ constexpr int G_OFF_OP = TILE, G_OFF_OUT = G_OFF_OP + G_NSLOT * QSLOT, G_OFF_BAR
 constexpr size_t G_SMEM = (size_t)G_OFF_BAR + BARS;
 static_assert(G_OFF_OUT % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte alignment");
 
-__host__ __device__ constexpr uint32_t instr_desc_bf16(int Mm, int Nn, int a_mn) {   // kind::f16, bf16 x bf16 -> fp32, B operand K-major
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)(Nn >> 3) << 17) | ((uint32_t)(Mm >> 4) << 24);
+__host__ __device__ constexpr uint32_t instr_desc_bf16(int Mm, int Nn, int a_mn, int b_mn = 0) {   // kind::f16, bf16 x bf16 -> fp32; a_mn / b_mn: operand is MN-major
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(Nn >> 3) << 17) | ((uint32_t)(Mm >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc),
@@ -300,8 +300,9 @@ __global__ void __launch_bounds__(256) k_check_dt(In in) {
 }
 // 64-point FFT of the N rows of `in` (element (n,k) at [n + N k]) into `out`, scaled; INV: exp(+...) kernel.  256 threads, radix-4 DIF:
 // one butterfly per thread and stage, digit-reversed positions resolved by the last stage's stores.  `in` is used as scratch.
-template <bool INV>
-__device__ __forceinline__ void fft64(cx<float>* __restrict__ in, cx<float>* __restrict__ out, const cx<float>* __restrict__ tw, float scale) {
+struct CtaSync { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
+template <bool INV, class Sync = CtaSync>
+__device__ __forceinline__ void fft64(cx<float>* __restrict__ in, cx<float>* __restrict__ out, const cx<float>* __restrict__ tw, float scale, Sync sync = Sync()) {
     const int n = threadIdx.x % N, j = threadIdx.x / N;          // j = 0..15
     auto twid = [&](int t) { cx<float> w = tw[t]; if (INV) w.im = -w.im; return w; };
     auto bfly = [&](cx<float> x0, cx<float> x1, cx<float> x2, cx<float> x3, cx<float> (&a)[4]) {
@@ -316,19 +317,19 @@ __device__ __forceinline__ void fft64(cx<float>* __restrict__ in, cx<float>* __r
     cx<float> a[4];
     // stage 0: length 64, i = j
     bfly(in[n + LDU * j], in[n + LDU * (j + 16)], in[n + LDU * (j + 32)], in[n + LDU * (j + 48)], a);
-    __syncthreads();
+    sync();
 #pragma unroll
     for (int q = 0; q < 4; ++q) in[n + LDU * (j + 16 * q)] = q ? a[q] * twid(q * j) : a[q];
-    __syncthreads();
+    sync();
     {   // stage 1: length 16, group j / 4, i = j % 4
         const int base = 16 * (j / 4), i = j % 4;
         cx<float> x0 = in[n + LDU * (base + i)], x1 = in[n + LDU * (base + i + 4)], x2 = in[n + LDU * (base + i + 8)], x3 = in[n + LDU * (base + i + 12)];
         bfly(x0, x1, x2, x3, a);
-        __syncthreads();
+        sync();
 #pragma unroll
         for (int q = 0; q < 4; ++q) in[n + LDU * (base + i + 4 * q)] = q ? a[q] * twid(4 * q * i) : a[q];
     }
-    __syncthreads();
+    sync();
     {   // stage 2: length 4, group j; position 4 j + q holds output index rev4(4 j + q) = 16 q + 4 (j % 4) + j / 4
         bfly(in[n + LDU * (4 * j)], in[n + LDU * (4 * j + 1)], in[n + LDU * (4 * j + 2)], in[n + LDU * (4 * j + 3)], a);
 #pragma unroll
