@@ -38,30 +38,34 @@ constexpr int NWK = 8;                           // worker warps
 constexpr int WTHREADS = 32 * NWK;
 constexpr int W_LD = 8, W_Q = 9, W_MMA = 10, W_JAC = 11, NJW = 4, JT = 32 * NJW;
 constexpr int MTHREADS = 32 * (W_JAC + NJW);     // 480
-constexpr int NQ = 3;                            // half-tap operand slots in flight
+constexpr int NQ = 2;                            // half-tap operand slots in flight (pass 1)
 constexpr int NIN = 4;                           // state-tile ring
 constexpr int MEGA_MAXL = 4;
 constexpr int KLBO = NRG * 128;                  // pass-2 small operand, MN-major: [8-column K group][row group][8 columns][8 rows] bf16, K groups KLBO apart
 constexpr int LDJ = 17;                          // leading dimension of the 16 x 16 fp64 Jacobi matrices (bank spread)
 constexpr int JN2 = LDJ * N;
+constexpr int NSLOT = 2;                         // trials interleaved per CTA: the eigen-solve of one hides behind the phases of the other
 
 constexpr int OFF_E = 0;                                   // two pilot tiles
-constexpr int OFF_IN = OFF_E + 2 * TILE;                   // state-tile ring (SWIZZLE_128B, 1024-byte aligned)
-constexpr int OFF_Q = OFF_IN + NIN * SLOT;                 // operand slots; phases R / S: U, V, R work matrices
-constexpr int OFF_KOP = OFF_Q + NQ * QSLOT;                // pass-2 small operand; phases R / S: operand image under construction
-constexpr int KOPREG = 25600;
-constexpr int OFF_Z = OFF_KOP + KOPREG;                    // planar Z tile; phases R / G / S: Jacobi work space
-constexpr int OFF_W = OFF_Z + MZREG;                        // W (fp32 complex 16 x 16)
-constexpr int OFF_A = OFF_W + WREG;                        // A, A'
-constexpr int OFF_TW = OFF_A + 2 * N * N * 8;              // FFT twiddles
-constexpr int OFF_UP = OFF_TW + NT * 8;                    // eigenvectors of the previous Gram matrix (warm start), fp64
-constexpr int OFF_MISC = OFF_UP + 2 * JN2 * 8;             // small reductions
+constexpr int OFF_IN = OFF_E + 2 * TILE;                   // state-tile ring (SWIZZLE_128B, 1024-byte aligned)  } phase G: together the resident
+constexpr int OFF_Q = OFF_IN + NIN * SLOT;                 // operand slots of pass 1                            } operand image of (A Res),
+constexpr int OFF_Z = OFF_Q + NQ * QSLOT;                  // planar Z tile                                      } MEGA_MAXL taps x QTAP bytes
+constexpr int OFF_KOP = OFF_Z + MZREG;                     // pass-2 small operand; phases R / S: the N x NT work matrices U, V
+constexpr int KOPREG = (MC / 8) * KLBO;
+constexpr int OFF_E2 = OFF_Z + (MEGA_MAXL * QTAP - NIN * SLOT - NQ * QSLOT);   // phase G only: third pilot tile behind the image tail, over the rest of Z, the
+constexpr int E2PAD = OFF_E2 + TILE - (OFF_KOP + KOPREG);                     // pass-2 operand region and E2PAD bytes more (all idle between the phases R and S)
+constexpr int OFF_W = OFF_KOP + KOPREG + E2PAD;            // W (fp32 complex 16 x 16) per trial slot
+constexpr int OFF_A = OFF_W + NSLOT * WREG;                // A, A' per trial slot
+constexpr int OFF_TW = OFF_A + NSLOT * 2 * N * N * 8;      // FFT twiddles
+constexpr int OFF_JAC = OFF_TW + NT * 8;                   // Jacobi warps: A, U (fp64, padded), similarity scratch, rotation parameters
+constexpr int JACREG = (4 * JN2 + 2 * N * N) * 8 + 512;
+constexpr int OFF_MISC = OFF_JAC + JACREG;                 // small reductions
 constexpr int OFF_BAR = OFF_MISC + 256;
 constexpr size_t SMEM = (size_t)OFF_BAR + 512;
 static_assert(OFF_IN % 1024 == 0 && OFF_Q % 1024 == 0, "tile alignment");
-static_assert((MC / 8) * KLBO <= KOPREG && 2 * LDU * NT * 8 <= KOPREG, "operand region too small");
-static_assert(MEGA_MAXL * QTAP <= NIN * SLOT + NQ * QSLOT, "resident operand image of phase G does not fit the state ring + operand slots");
-static_assert((2 * JN2 + 2 * N * N) * 8 + 512 <= MZREG, "Jacobi work space does not fit the Z tile");
+static_assert(2 * LDU * NT * 8 <= KOPREG, "work matrices do not fit the pass-2 operand region");
+static_assert(MEGA_MAXL * QTAP <= NIN * SLOT + NQ * QSLOT + MZREG, "resident operand image of phase G does not fit");
+static_assert(OFF_JAC % 16 == 0 && OFF_KOP % 16 == 0 && OFF_Z % 16 == 0 && OFF_E2 % 16 == 0 && E2PAD >= 0, "alignment");
 static_assert(SMEM <= 232448, "shared memory");
 
 __device__ __forceinline__ void wsync() { asm volatile("bar.sync 1, %0;" ::"n"(WTHREADS) : "memory"); }
@@ -87,17 +91,24 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
     if (lane == 0) tc::mbar_arrive(bar);
 }
 
+// Release of two state-ring slots this warp has read into registers.  The reads are generic-proxy accesses and the refill is an async-proxy
+// (TMA) write: without the proxy fence the refill was observed to overtake loads still in flight (a tile read back as its successor).
+__device__ __forceinline__ void ring_release(uint64_t* a, uint64_t* b, int lane) {
+    tc::fence_async_smem();
+    __syncwarp();
+    if (lane == 0) { tc::mbar_arrive(a); tc::mbar_arrive(b); }
+}
+
 // ---- fp64 Hermitian Jacobi eigen-solve of the 16 x 16 Gram matrix on the four Jacobi warps (same rotations, pairing and stopping
 // rules as jacobi_hermitian_block / jacobi_similarity_block of jacobi.cuh, specialised: named barrier, padded leading dimension) -----
 struct Jac16 {
     double *Are, *Aim, *Ure, *Uim, *Tre, *Tim, *c, *s, *er, *ei, *offacc, *red;
     int *pp, *qq;
-    __device__ void carve(unsigned char* work, unsigned char* uprev) {
+    __device__ void carve(unsigned char* work) {
         double* p = reinterpret_cast<double*>(work);
-        Are = p; p += JN2; Aim = p; p += JN2; Tre = p; p += N * N; Tim = p; p += N * N;
+        Are = p; p += JN2; Aim = p; p += JN2; Ure = p; p += JN2; Uim = p; p += JN2; Tre = p; p += N * N; Tim = p; p += N * N;
         c = p; p += 8; s = p; p += 8; er = p; p += 8; ei = p; p += 8; offacc = p; p += 8; red = p; p += 8;
         pp = reinterpret_cast<int*>(p); qq = pp + 8;
-        Ure = reinterpret_cast<double*>(uprev); Uim = Ure + JN2;
     }
 };
 __device__ __forceinline__ double jac_sum(Jac16& sm, double v, int jt) {       // deterministic sum over the 128 Jacobi threads
@@ -284,28 +295,40 @@ __device__ __forceinline__ void stg_u4x2(unsigned char* g, uint4 a, uint4 b) {  
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(g), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
 }
 
+// The MMA warp runs its loops with all 32 lanes (warp-uniform control flow and operands, so the descriptors live in uniform registers and
+// no per-lane broadcast loop is generated); one elected lane issues.
+__device__ __forceinline__ bool elect_one() {           // true in exactly one lane of the (converged) warp
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void umma_elect(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) { umma_bf16(d_tmem, a, b, idesc, accumulate); }
+__device__ __forceinline__ void commit_elect(uint64_t* bar) { tc::umma_commit(bar); }
 // accumulator of pass 1 / of G: 128 TMEM columns; even taps -> [0, 96) with operand rows [hi | mid | lo], odd taps -> [32, 128) with rows
 // [mid | lo | hi].  The first MMA of tap 0 initialises [0, 96); the first k step of tap 1 is split so that [96, 128) is initialised too.
 // RESIDENT: the whole image ([tap][QTAP]) sits in shared memory at slots_a (phase G); otherwise it streams through the NQ half-tap slots.
+// Descriptors: the address field counts 16-byte units, so every operand address is the base descriptor plus a small constant.
 template <bool RESIDENT>
 __device__ __forceinline__ void issue_taps(uint32_t acc, uint32_t tile_a, uint32_t slots_a, uint64_t* q_full, uint64_t* q_empty, uint32_t& q_n, int L) {
     constexpr uint32_t id96 = instr_desc_bf16(128, NS, 0), id64 = instr_desc_bf16(128, 64, 0), id32 = instr_desc_bf16(128, 32, 0);
+    const uint64_t a_base = tc::smem_desc(tile_a, RS, 128, 0), b_base = tc::smem_desc(slots_a, NRG * 128, 128, 0);
     for (int i = 0; i < 2 * L; ++i) {
         const int slot = q_n % NQ, l = i >> 1, hf = i & 1;
         if (!RESIDENT) { mbar_wait(&q_full[slot], (q_n / NQ) & 1); tc::tc_fence_after(); }
-        const uint32_t a0 = tile_a + (uint32_t)(L - 1 - l) * 16, b0 = RESIDENT ? slots_a + (uint32_t)i * QSLOT : slots_a + slot * QSLOT;
+        const uint64_t ad0 = a_base + (uint64_t)(L - 1 - l) + (uint64_t)(hf * (KC / 32) * 2 * (RS / 16));
+        const uint64_t bd0 = b_base + (uint64_t)((RESIDENT ? i : slot) * (QSLOT / 16));
+        const uint32_t d = acc + 32 * (l & 1);
 #pragma unroll
         for (int j = 0; j < KC / 32; ++j) {
-            const int ks = hf * (KC / 32) + j;
-            const uint64_t ad = tc::smem_desc(a0 + ks * 2 * RS, RS, 128, 0);
-            if (l == 1 && ks == 0) {
-                umma_bf16(acc + 32, ad, tc::smem_desc(b0 + j * QKS, NRG * 128, 128, 0), id64, 1u);
-                umma_bf16(acc + 96, ad, tc::smem_desc(b0 + j * QKS + 8 * 128, NRG * 128, 128, 0), id32, 0u);
+            const uint64_t ad = ad0 + (uint64_t)(j * 2 * (RS / 16)), bd = bd0 + (uint64_t)(j * (QKS / 16));
+            if (j == 0 && i == 2) {                                   // tap 1, first k step
+                umma_elect(acc + 32, ad, bd, id64, 1u);
+                umma_elect(acc + 96, ad, bd + (uint64_t)(8 * 128 / 16), id32, 0u);
             } else {
-                umma_bf16(acc + 32 * (l & 1), ad, tc::smem_desc(b0 + j * QKS, NRG * 128, 128, 0), id96, (l || ks) ? 1u : 0u);
+                umma_elect(d, ad, bd, id96, (i | j) ? 1u : 0u);
             }
         }
-        if (!RESIDENT) { tc::umma_commit(&q_empty[slot]); ++q_n; }
+        if (!RESIDENT) { commit_elect(&q_empty[slot]); ++q_n; }
     }
 }
 // this thread's 8 rows of column m: lo, mid, then the hi blocks (smallest terms first)
@@ -333,6 +356,13 @@ __device__ __forceinline__ void read_acc(uint32_t acc, uint32_t lane_base, int n
     do {                                                                                                                           \
         if (p.dbg && p.dbg_kernel == 10 && blockIdx.x == 0) { *reinterpret_cast<volatile long long*>(p.dbg + (slot)) = (long long)(value); __threadfence_system(); } \
     } while (0)
+#define MEGA_STAMP3(kid, slot)                                                                                                     \
+    do {                                                                                                                           \
+        if (p.dbg && p.dbg_kernel == (kid) && tid == 0 && l == 1 && b == (int)blockIdx.x && it < 16) p.dbg[((size_t)blockIdx.x * 16 + it) * 8 + (slot)] = clock64(); \
+    } while (0)
+// data dump for race triage (tools/mega_dump.py): per trial 1024 floats - checksums of what iteration 1 consumed
+#define MEGA_DUMP_ON (p.dbg && p.dbg_kernel == 14 && it == 1)
+#define MEGA_DUMP_ADD(idx, val) do { if (MEGA_DUMP_ON) atomicAdd(reinterpret_cast<float*>(p.dbg) + (size_t)b * 1024 + (idx), (val)); } while (0)
 #define MEGA_STAMP2(slot)                                                                                                          \
     do {                                                                                                                           \
         if (p.dbg && p.dbg_kernel == 8 && tid == 0 && c == 3 && b == (int)blockIdx.x && it < 16) p.dbg[((size_t)blockIdx.x * 16 + it) * 8 + (slot)] = clock64(); \
@@ -346,27 +376,38 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
     unsigned char* kop = smem + OFF_KOP;
     float* Zre = reinterpret_cast<float*>(smem + OFF_Z);
     float* Zim = Zre + N * MZP;
-    cx<float>* Wsm = reinterpret_cast<cx<float>*>(smem + OFF_W);
-    cx<float>* Asm = reinterpret_cast<cx<float>*>(smem + OFF_A);
-    cx<float>* AHsm = Asm + N * N;
+    cx<float>* Wsm = reinterpret_cast<cx<float>*>(smem + OFF_W);      // [slot][N * N]
+    cx<float>* Asm = reinterpret_cast<cx<float>*>(smem + OFF_A);      // [slot][A | A'][N * N]
     cx<float>* tw = reinterpret_cast<cx<float>*>(smem + OFF_TW);
     double* misc = reinterpret_cast<double*>(smem + OFF_MISC);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-    uint64_t *e_full = bars, *e_empty = bars + 2, *in_full = bars + 4, *in_empty = bars + 8, *q_full = bars + 12, *q_empty = bars + 16;
+    uint64_t *e_full = bars + 37, *e_empty = bars + 40, *r_done = bars + 43, *in_full = bars + 4, *in_empty = bars + 8, *q_full = bars + 12, *q_empty = bars + 16;
     uint64_t *acc_full = bars + 20, *acc_empty = bars + 22, *kop_full = bars + 24, *kop_empty = bars + 25, *t1_full = bars + 26;
-    uint64_t *q_ready = bars + 27, *g_done = bars + 28, *gram_ready = bars + 29, *w_ready = bars + 30, *img_ready = bars + 31;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+    uint64_t *g_done = bars + 27, *img_ready = bars + 28, *g_done_q = bars + 29, *q_ready = bars + 30, *gram_ready = bars + 32, *w_ready = bars + 34;   // the last three: one per trial slot
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 44);
 
     const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
     const int M = p.M, L = in.L, nch = M / MC, imax = p.imax, G = p.G;
     const size_t NM = (size_t)N * M;
+    // this CTA's trials blockIdx.x, + gridDim.x, ... are taken two at a time; the work items of a pair are (iteration, slot) in that order
+    const int ntr = (int)blockIdx.x < nb ? (nb - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+#define MEGA_ITEMS_BEGIN                                                                  \
+    for (int pr = 0; pr < ntr; pr += NSLOT) {                                             \
+        const int nw = (ntr - pr) < NSLOT ? (ntr - pr) : NSLOT;                           \
+        for (int it = 0; it < imax; ++it)                                                 \
+            for (int w = 0; w < nw; ++w) {                                                \
+                const int b = (int)blockIdx.x + (pr + w) * (int)gridDim.x;
+#define MEGA_ITEMS_END }}
 
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) { mbar_init(&e_full[s], 1); mbar_init(&e_empty[s], 1); mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], NWK); }
+        for (int s = 0; s < 3; ++s) { mbar_init(&e_full[s], 1); mbar_init(&e_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], NWK); }
+        mbar_init(r_done, NWK);
         for (int s = 0; s < NIN; ++s) { mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], NWK); }
         for (int s = 0; s < NQ; ++s) { mbar_init(&q_full[s], 1); mbar_init(&q_empty[s], 1); }
         mbar_init(kop_full, NWK); mbar_init(kop_empty, 1); mbar_init(t1_full, 1);
-        mbar_init(q_ready, NWK); mbar_init(g_done, NWK); mbar_init(gram_ready, NWK); mbar_init(w_ready, 1); mbar_init(img_ready, NWK);
+        mbar_init(g_done, NWK); mbar_init(img_ready, NWK); mbar_init(g_done_q, NWK);
+        for (int s = 0; s < NSLOT; ++s) { mbar_init(&q_ready[s], NWK); mbar_init(&gram_ready[s], NWK); mbar_init(&w_ready[s], 1); }
         mbar_fence_init();
     }
     if (warp == W_LD) {
@@ -381,53 +422,52 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
 
     if (warp == W_LD) {
         // ===== TMA producer: pilot tiles and state tiles =====
-        if (lane == 0) {
-            uint32_t e_n = 0, in_n = 0, gd_n = 0;
-            auto load_e = [&](int c, int b) {
-                const int s = e_n & 1;
-                MEGA_BEACON(3, 100000 + e_n * 100 + in_n);
-                if (e_n >= 2) mbar_wait(&e_empty[s], ((e_n >> 1) - 1) & 1);
-                MEGA_BEACON(3, 200000 + e_n * 100 + in_n);
-                mbar_expect_tx(&e_full[s], TILE);
-                if (in.t1_red & 1) { tc::tma_4d(etile + s * TILE, &maps.E, 0, c * MC, 0, in.ld_Psi ? b : 0, &e_full[s]); ++e_n; return; }
+        if (elect_one()) {
+            uint32_t euse[3] = {0, 0, 0}, in_n = 0, gd_n = 0, rd_n = 0;
+            // pilot tile of chunk c into buffer `buf` (phase F alternates 0 / 1, phase G cycles 0 / 1 / 2); a buffer is released by the last MMA that read it
+            auto load_e = [&](int buf, int c, int b) {
+                if (euse[buf] > 0) mbar_wait(&e_empty[buf], (euse[buf] - 1) & 1);
+                ++euse[buf];
+                unsigned char* dst = buf < 2 ? etile + buf * TILE : smem + OFF_E2;
+                mbar_expect_tx(&e_full[buf], TILE);
                 // [kc group][column][8 kc]: the ROWS columns of one group are RS contiguous bytes in the image - 16 bulk copies, no 16-byte tensor rows
                 const unsigned short* src = in.E + ((size_t)(in.ld_Psi ? b : 0) * NKG * (size_t)(M + 8) + (size_t)c * MC) * 8;
 #pragma unroll 4
-                for (int kg = 0; kg < NKG; ++kg) tma_bulk_g2s(etile + s * TILE + kg * RS, src + (size_t)kg * (M + 8) * 8, RS, &e_full[s]);
-                ++e_n;
+                for (int kg = 0; kg < NKG; ++kg) tma_bulk_g2s(dst + kg * RS, src + (size_t)kg * (M + 8) * 8, RS, &e_full[buf]);
             };
             auto load_in = [&](const CUtensorMap* map, int c, int b) {
                 const int s = in_n % NIN, use = in_n / NIN;
-                MEGA_BEACON(3, 300000 + e_n * 100 + in_n);
                 if (use > 0) mbar_wait(&in_empty[s], (use - 1) & 1);
-                MEGA_BEACON(3, 400000 + e_n * 100 + in_n);
                 mbar_expect_tx(&in_full[s], SLOT);
                 tc::tma_3d(inr + s * SLOT, map, 0, c * MC, b, &in_full[s]);
                 ++in_n;
             };
-            for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+            MEGA_ITEMS_BEGIN
                 const int sy_b = p.ld_subY ? b : 0;
-                for (int it = 0; it < imax; ++it) {
-                    // phase G of the previous iteration (or trial) is over: its operand image has left the ring, and the state it and phase F stored is
-                    // ordered before the TMA loads below - the proxy fence must sit HERE, in the thread that issues the async-proxy reads after acquiring
-                    // the barrier (a fence only on the writers' side was measured to let stale XV tiles through)
-                    if (it > 0 || b != (int)blockIdx.x) { mbar_wait(g_done, gd_n & 1); ++gd_n; fence_proxy_async_all(); }
-                    for (int c = 0; c < nch; ++c) {
-                        MEGA_BEACON(0, it * 1000 + 100 + c);
-                        load_e(c, b);
-                        load_in(&maps.X, c, b); load_in(&maps.V1, c, b); load_in(&maps.V2, c, b); load_in(&maps.SY, c, sy_b);
-                        load_in(&maps.XV, c, b); load_in(&maps.G, c, b);
-                    }
-                    for (int c = 0; c < nch; ++c) { MEGA_BEACON(0, it * 1000 + 300 + c); load_e(c, b); }
-                    MEGA_BEACON(0, it * 1000 + 999);
+                // Phase G of the previous work item is over: its operand image has left the ring, and the state stored two items ago (same trial) is
+                // ordered before the TMA loads below - the proxy fence must sit HERE, in the thread that issues the async-proxy reads after acquiring
+                // the barrier (a fence only on the writers' side was measured to let stale XV tiles through).
+                if (pr > 0 || it > 0 || w > 0) { mbar_wait(g_done, gd_n & 1); ++gd_n; fence_proxy_async_all(); }
+                for (int c = 0; c < nch; ++c) {
+                    MEGA_BEACON(0, it * 1000 + 100 + c);
+                    load_e(c & 1, c, b);
+                    load_in(&maps.X, c, b); load_in(&maps.V1, c, b); load_in(&maps.V2, c, b); load_in(&maps.SY, c, sy_b);
+                    load_in(&maps.XV, c, b); load_in(&maps.G, c, b);
                 }
-            }
+                for (int c = 0; c < nch; ++c) {
+                    MEGA_BEACON(0, it * 1000 + 300 + c);
+                    if (c == 2) { mbar_wait(r_done, rd_n & 1); ++rd_n; }     // the third buffer lies over the work matrices of phase R
+                    load_e(c % 3, c, b);
+                }
+                if (nch <= 2) { mbar_wait(r_done, rd_n & 1); ++rd_n; }
+                MEGA_BEACON(0, it * 1000 + 999);
+            MEGA_ITEMS_END
         }
         __syncwarp();
     } else if (warp == W_Q) {
         // ===== TMA producer: operand images, half a tap per slot, once per chunk =====
-        if (lane == 0) {
-            uint32_t q_n = 0, qr_n = 0;
+        if (elect_one()) {
+            uint32_t q_n = 0, qr_n[NSLOT] = {0, 0}, gq_n = 0;
             auto stream = [&](const unsigned char* img) {
                 for (int c = 0; c < nch; ++c)
                     for (int i = 0; i < 2 * L; ++i) {
@@ -438,100 +478,118 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
                         ++q_n;
                     }
             };
-            for (int b = blockIdx.x; b < nb; b += gridDim.x)
-                for (int it = 0; it < imax; ++it) {
-                    if (it > 0) { mbar_wait(q_ready, qr_n & 1); ++qr_n; fence_proxy_async_all(); stream(in.QopS + (size_t)b * L * QTAP); }
-                }
+            MEGA_ITEMS_BEGIN
+                // the operand slots are part of the previous item's resident phase-G image: wait until that phase is over (the image this item
+                // needs was finished one item earlier still, by the same trial's phase S)
+                if (pr > 0 || it > 0 || w > 0) { mbar_wait(g_done_q, gq_n & 1); ++gq_n; }
+                if (it > 0) { mbar_wait(&q_ready[w], qr_n[w] & 1); ++qr_n[w]; fence_proxy_async_all(); stream(in.QopS + (size_t)b * L * QTAP); }
+            MEGA_ITEMS_END
         }
         __syncwarp();
     } else if (warp == W_MMA) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer: one elected lane (elect.sync, so that the compiler knows the branch holds a single thread) =====
+        if (elect_one()) {
             constexpr uint32_t id2 = instr_desc_bf16(128, NS, 1, 1);
             const uint32_t e_a = smem_u32(etile), q_a = smem_u32(qsl), k_a = smem_u32(kop), img_a = smem_u32(inr);
-            uint32_t e_n = 0, q_n = 0, accn[2] = {0, 0}, kop_n = 0, ig_n = 0;
-            for (int b = blockIdx.x; b < nb; b += gridDim.x)
-                for (int it = 0; it < imax; ++it) {
+            uint32_t euse[3] = {0, 0, 0}, q_n = 0, accn[2] = {0, 0}, kop_n = 0, ig_n = 0;
+            const uint32_t e_addr[3] = {e_a, e_a + TILE, smem_u32(smem + OFF_E2)};
+            const uint64_t k_base = tc::smem_desc(k_a, KLBO, 128, 0);
+            MEGA_ITEMS_BEGIN
+                {
+                    (void)b;
                     // ---- phase F: P1(0), then P1(c), P2(c - 1) interleaved ----
                     for (int c = 0; c <= nch; ++c) {
-                        MEGA_BEACON(2, it * 1000 + 100 + c);
                         if (c < nch && it > 0) {
-                            const uint32_t e_i = e_n + c;
-                            mbar_wait(&e_full[e_i & 1], (e_i >> 1) & 1);
+                            const int eb = c & 1;
+                            mbar_wait(&e_full[eb], euse[eb] & 1);
                             if (accn[0] > 0) mbar_wait(&acc_empty[0], (accn[0] - 1) & 1);
                             tc::tc_fence_after();
-                            issue_taps<false>(ACC0, e_a + (e_i & 1) * TILE, q_a, q_full, q_empty, q_n, L);
-                            tc::umma_commit(&acc_full[0]);
+                            issue_taps<false>(ACC0, e_addr[eb], q_a, q_full, q_empty, q_n, L);
+                            commit_elect(&acc_full[0]);
                             ++accn[0];
                         }
                         if (c > 0) {
-                            const uint32_t e_j = e_n + c - 1;
-                            MEGA_BEACON(4, 1000 + e_j);
-                            mbar_wait(&e_full[e_j & 1], (e_j >> 1) & 1);
-                            MEGA_BEACON(4, 2000 + e_j);
+                            const int eb = (c - 1) & 1;
+                            mbar_wait(&e_full[eb], euse[eb] & 1);
                             mbar_wait(kop_full, kop_n & 1); ++kop_n;
-                            MEGA_BEACON(4, 3000 + e_j);
                             tc::tc_fence_after();
-                            const uint32_t tile_a = e_a + (e_j & 1) * TILE;
+                            // pass 2: A = pilot tile, MN-major (LBO = 8-column K group stride, SBO = kc group stride); B = K operand, MN-major
+                            const uint64_t a_base = tc::smem_desc(e_addr[eb], 128, RS, 0);
                             for (int l = 0; l < L; ++l) {
-                                const uint32_t a0 = tile_a + (uint32_t)(L - 1 - l) * 16;
+                                const uint64_t ad0 = a_base + (uint64_t)(L - 1 - l);
+                                const uint32_t d = tm + NS * l;
 #pragma unroll
                                 for (int ks = 0; ks < MC / 16; ++ks)
-                                    umma_bf16(tm + NS * l, tc::smem_desc(a0 + ks * 256, 128, RS, 0), tc::smem_desc(k_a + ks * 2 * KLBO, KLBO, 128, 0), id2,
-                                              (c > 1 || ks) ? 1u : 0u);
+                                    umma_elect(d, ad0 + (uint64_t)(ks * (256 / 16)), k_base + (uint64_t)(ks * (2 * KLBO / 16)), id2, (c > 1 || ks) ? 1u : 0u);
                             }
-                            tc::umma_commit(kop_empty);
-                            tc::umma_commit(&e_empty[e_j & 1]);
+                            commit_elect(kop_empty);
+                            commit_elect(&e_empty[eb]);
+                            ++euse[eb];
                         }
                     }
-                    tc::umma_commit(t1_full);
-                    e_n += nch;
+                    commit_elect(t1_full);
                     // ---- phase G: the operand image of (A Res) is resident (built by the workers over the idle state ring) ----
-                    MEGA_BEACON(2, it * 1000 + 299);
+                    const bool mdbg = p.dbg && p.dbg_kernel == 13 && lane == 0 && b == (int)blockIdx.x && it < 16;
+                    long long tw_img = 0, tw_e = 0, tw_acc = 0, t_iss = 0, tq = mdbg ? clock64() : 0;
                     mbar_wait(img_ready, ig_n & 1); ++ig_n;
+                    if (mdbg) { tw_img = clock64() - tq; }
+                    const long long tg0 = mdbg ? clock64() : 0;
                     for (int c = 0; c < nch; ++c) {
-                        MEGA_BEACON(2, it * 1000 + 300 + c);
-                        const uint32_t e_i = e_n + c;
-                        const int buf = c & 1;
-                        mbar_wait(&e_full[e_i & 1], (e_i >> 1) & 1);
+                        const int buf = c & 1, eb = c % 3;
+                        if (mdbg) tq = clock64();
+                        mbar_wait(&e_full[eb], euse[eb] & 1);
+                        if (mdbg) { tw_e += clock64() - tq; tq = clock64(); }
                         if (accn[buf] > 0) mbar_wait(&acc_empty[buf], (accn[buf] - 1) & 1);
+                        if (mdbg) { tw_acc += clock64() - tq; tq = clock64(); }
                         tc::tc_fence_after();
-                        issue_taps<true>(buf ? ACC1 : ACC0, e_a + (e_i & 1) * TILE, img_a, q_full, q_empty, q_n, L);
-                        tc::umma_commit(&acc_full[buf]);
-                        tc::umma_commit(&e_empty[e_i & 1]);
-                        ++accn[buf];
+                        issue_taps<true>(buf ? ACC1 : ACC0, e_addr[eb], img_a, q_full, q_empty, q_n, L);
+                        commit_elect(&acc_full[buf]);
+                        commit_elect(&e_empty[eb]);
+                        if (mdbg) t_iss += clock64() - tq;
+                        ++accn[buf]; ++euse[eb];
                     }
-                    e_n += nch;
+                    if (mdbg) { long long* d = p.dbg + ((size_t)blockIdx.x * 16 + it) * 8; d[0] = tw_img; d[1] = tw_e; d[2] = tw_acc; d[3] = t_iss; d[4] = clock64() - tg0; }
                 }
+            MEGA_ITEMS_END
         }
         __syncwarp();
     } else if (warp >= W_JAC) {
         // ===== Jacobi warps: W of iteration it + 1 from the Gram matrix the workers finish in phase F of iteration it =====
         const int jt = tid - 32 * W_JAC;
-        Jac16 js; js.carve(smem + OFF_Z, smem + OFF_UP);
-        uint32_t gr_n = 0;
-        for (int b = blockIdx.x; b < nb; b += gridDim.x) {
-            const double tau = p.tauY[b] / p.rho[b];
-            for (int it = 0; it + 1 < imax; ++it) {
-                mbar_wait(gram_ready, gr_n & 1); ++gr_n;
+        Jac16 js; js.carve(smem + OFF_JAC);
+        uint32_t gr_n[NSLOT] = {0, 0};
+        MEGA_ITEMS_BEGIN
+            if (it + 1 < imax) {
+                const double tau = p.tauY[b] / p.rho[b];
+                mbar_wait(&gram_ready[w], gr_n[w] & 1); ++gr_n[w];
                 MEGA_STAMP(6, jt == 0);
-                // warm start from the previous eigenvectors; every 16th iteration (and the first of a trial) restarts cold
+                // warm start from the previous eigenvectors of this trial; every 16th iteration (and the first of a trial) restarts cold
                 const bool warm = it > 0 && ((it + 1) % 16) != 0 && !(in.t1_red & 4);
                 const bool jdbg = p.dbg && p.dbg_kernel == 9 && jt == 0 && b == (int)blockIdx.x && it < 16;
                 long long* jd = p.dbg + ((size_t)blockIdx.x * 16 + it) * 8;
                 if (jdbg) jd[0] = clock64();
+                // the Gram matrix and the eigenvectors travel through global memory (L2): shared memory holds one solve, whichever trial it belongs to
+                const double2* gin = reinterpret_cast<const double2*>(p.gram + (size_t)b * p.nmc * 2 * N * N);
+                double* up = p.Uprev + (size_t)b * 2 * N * N;
+                for (int t = jt; t < N * N; t += JT) {
+                    const double2 g = __ldcg(gin + t);
+                    js.Are[(t % N) + LDJ * (t / N)] = g.x; js.Aim[(t % N) + LDJ * (t / N)] = g.y;
+                    if (warm) { js.Ure[(t % N) + LDJ * (t / N)] = __ldcg(up + t); js.Uim[(t % N) + LDJ * (t / N)] = __ldcg(up + N * N + t); }
+                }
+                jsync();
                 if (warm) jac16_similarity(js, jt);
                 if (jdbg) jd[1] = clock64();
                 int sweeps = 0;
                 const double fro2 = jac16_solve(js, jt, warm, 1e-10, sweeps);
                 if (jdbg) { jd[2] = clock64(); jd[4] = sweeps; }
-                jac16_weights(js, jt, tau, fro2, Wsm);
+                jac16_weights(js, jt, tau, fro2, Wsm + w * N * N);
+                for (int t = jt; t < N * N; t += JT) { up[t] = js.Ure[(t % N) + LDJ * (t / N)]; up[N * N + t] = js.Uim[(t % N) + LDJ * (t / N)]; }
                 jsync();
                 if (jdbg) jd[3] = clock64();
                 MEGA_STAMP(7, jt == 0);
-                if (jt == 0) tc::mbar_arrive(w_ready);
+                if (jt == 0) tc::mbar_arrive(&w_ready[w]);
             }
-        }
+        MEGA_ITEMS_END
     } else {
         // ===== workers =====
         const int quad = warp % 4, half = warp / 4;
@@ -540,37 +598,44 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
         const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
         cx<float>* U = reinterpret_cast<cx<float>*>(kop);     // phases R / S: N x NT work matrices (leading dimension LDU) over the idle pass-2 operand
         cx<float>* V = U + LDU * NT;
-        double* JAre = reinterpret_cast<double*>(smem + OFF_Z);
-        double* JAim = JAre + JN2;
-        uint32_t in_n = 0, accn[2] = {0, 0}, kop_n = 0, t1_n = 0, w_n = 0;
+        uint32_t in_n = 0, accn[2] = {0, 0}, kop_n = 0, t1_n = 0, w_n[NSLOT] = {0, 0};
         const bool narrow = (in.t1_red & 2) != 0;
         if (tid < NT) { float sn, cs; sincospif(-2.0f * (float)tid / NT, &sn, &cs); tw[tid] = mk<float>(cs, sn); }
         auto in_slot = [&](uint32_t i) { return inr + (i % NIN) * SLOT; };
         auto in_wait = [&](uint32_t i) { mbar_wait(&in_full[i % NIN], (i / NIN) & 1); };
+        float ap0 = 0.f, ap1 = 0.f;                           // alpha of the previous iteration, per trial slot
 
-        for (int b = blockIdx.x; b < nb; b += gridDim.x) {
-            const float rho = (float)p.rho[b];
-            const float irho = 1.0f / rho, kap = rho / (rho + 1.0f);
-            const float thr = (float)(p.tauS[b] / p.rho[b]);
-            const float sc = in.scale[b];
-            wsync();                                          // the previous trial is done with A / W
-            {
+        for (int pr = 0; pr < ntr; pr += NSLOT) {
+            const int nw = (ntr - pr) < NSLOT ? (ntr - pr) : NSLOT;
+            wsync();                                          // the previous pair is done with A / W
+            for (int w = 0; w < nw; ++w) {
+                const int b = (int)blockIdx.x + (pr + w) * (int)gridDim.x;
                 const cx<float>* A = p.A + (long long)b * p.ld_A;
                 const cx<float> a = tid < N * G ? A[tid] : mk<float>(0.f, 0.f);
-                Asm[tid] = a; AHsm[(tid / N) + N * (tid % N)] = mk<float>(a.re, -a.im);
-                Wsm[tid] = mk<float>(0.f, 0.f);               // svt of the all-zero first iterate is zero (svt.m:7-13)
+                cx<float>* As = Asm + w * 2 * N * N;
+                As[tid] = a; As[N * N + (tid / N) + N * (tid % N)] = mk<float>(a.re, -a.im);
+                Wsm[w * N * N + tid] = mk<float>(0.f, 0.f);   // svt of the all-zero first iterate is zero (svt.m:7-13)
             }
+            ap0 = 0.f; ap1 = 0.f;
             wsync();
-            float alpha_prev = 0.f;
-            cx<float>* Xg = p.X + (size_t)b * NM;
-            cx<float>* V1g = p.V1 + (size_t)b * NM;
-            cx<float>* V2g = p.V2 + (size_t)b * NM;
-            cx<float>* XVg = in.XV + (size_t)b * NM;
-            cx<float>* Gg = in.Gm + (size_t)b * NM;
-
-            for (int it = 0; it < imax; ++it) {
+          for (int it = 0; it < imax; ++it)
+            for (int w = 0; w < nw; ++w) {
+                const int b = (int)blockIdx.x + (pr + w) * (int)gridDim.x;
+                const float rho = (float)p.rho[b];
+                const float irho = 1.0f / rho, kap = rho / (rho + 1.0f);
+                const float thr = (float)(p.tauS[b] / p.rho[b]);
+                const float sc = in.scale[b];
+                const cx<float>* Ws = Wsm + w * N * N;
+                const cx<float>* As = Asm + w * 2 * N * N;
+                const cx<float>* AHs = As + N * N;
+                const float alpha_prev = w ? ap1 : ap0;
+                cx<float>* Xg = p.X + (size_t)b * NM;
+                cx<float>* V1g = p.V1 + (size_t)b * NM;
+                cx<float>* V2g = p.V2 + (size_t)b * NM;
+                cx<float>* XVg = in.XV + (size_t)b * NM;
+                cx<float>* Gg = in.Gm + (size_t)b * NM;
                 const bool more = it + 1 < imax;
-                if (it > 0) { mbar_wait(w_ready, w_n & 1); ++w_n; }
+                if (it > 0) { mbar_wait(&w_ready[w], w_n[w] & 1); ++w_n[w]; }
                 // ================= phase F =================
                 MEGA_STAMP(0, tid == 0);
                 double gram_r = 0.0, gram_i = 0.0;            // Gram entry (4 (combo % 4) + q / 4, 4 (combo / 4) + q % 4), combo = tid / 16, q = tid % 16
@@ -584,8 +649,10 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
                     in_wait(in_n); in_wait(in_n + 1);
                     MEGA_STAMP2(1);
                     tile_read8(in_slot(in_n), m, half, xo); tile_read8(in_slot(in_n + 1), m, half, v1);
-                    warp_arrive(&in_empty[in_n % NIN], lane); warp_arrive(&in_empty[(in_n + 1) % NIN], lane);
+                    ring_release(&in_empty[in_n % NIN], &in_empty[(in_n + 1) % NIN], lane);
                     in_n += 2;
+                    if (MEGA_DUMP_ON) { float sx = 0.f, sv = 0.f; for (int r = 0; r < NH; ++r) { sx += xo[r].re * xo[r].re + xo[r].im * xo[r].im; sv += v1[r].re * v1[r].re + v1[r].im * v1[r].im; } MEGA_DUMP_ADD(0 + c, sx); MEGA_DUMP_ADD(8 + c, sv); }
+                    if (MEGA_DUMP_ON && c == 0 && tid < 256) { reinterpret_cast<float*>(p.dbg)[(size_t)b * 1024 + 512 + 2 * tid] = Ws[tid].re; reinterpret_cast<float*>(p.dbg)[(size_t)b * 1024 + 512 + 2 * tid + 1] = Ws[tid].im; if (tid == 0) { reinterpret_cast<float*>(p.dbg)[(size_t)b * 1024 + 100] = alpha_prev; reinterpret_cast<float*>(p.dbg)[(size_t)b * 1024 + 101] = rho; } }
                     wsync();                                  // the Gram of the previous chunk has read Z
 #pragma unroll
                     for (int r = 0; r < NH; ++r) { Zre[(n0 + r) * MZP + m] = xo[r].re - irho * v1[r].re; Zim[(n0 + r) * MZP + m] = xo[r].im - irho * v1[r].im; }
@@ -602,7 +669,7 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
 #pragma unroll
                             for (int hf = 0; hf < NH / 4; ++hf) {
                                 cx<float> t[4];
-                                ld4c<float>(Wsm + N * k + n0 + 4 * hf, t);
+                                ld4c<float>(Ws + N * k + n0 + 4 * hf, t);
 #pragma unroll
                                 for (int u = 0; u < 4; ++u) w[4 * hf + u] = t[u];
                             }
@@ -636,13 +703,15 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
                         for (int r = 0; r < NH; ++r) { xs_r[r] = 0.f; xs_i[r] = 0.f; }
                     }
                     MEGA_STAMP2(3);
+                    if (MEGA_DUMP_ON) { float sx = 0.f; for (int r = 0; r < NH; ++r) sx += xs_r[r] * xs_r[r] + xs_i[r] * xs_i[r]; MEGA_DUMP_ADD(16 + c, sx); }
                     // ---- V2, subY -> C, V2, X, V1, K ----
                     cx<float> v2[NH], kt[NH];
                     {
                         cx<float> sy[NH];
                         in_wait(in_n); in_wait(in_n + 1);
                         tile_read8(in_slot(in_n), m, half, v2); tile_read8(in_slot(in_n + 1), m, half, sy);
-                        warp_arrive(&in_empty[in_n % NIN], lane); warp_arrive(&in_empty[(in_n + 1) % NIN], lane);
+                        if (MEGA_DUMP_ON) { float sx = 0.f, sv = 0.f; for (int r = 0; r < NH; ++r) { sx += v2[r].re * v2[r].re + v2[r].im * v2[r].im; sv += sy[r].re * sy[r].re + sy[r].im * sy[r].im; } MEGA_DUMP_ADD(24 + c, sx); MEGA_DUMP_ADD(32 + c, sv); }
+                        ring_release(&in_empty[in_n % NIN], &in_empty[(in_n + 1) % NIN], lane);
                         in_n += 2;
 #pragma unroll
                         for (int r = 0; r < NH; ++r) {
@@ -669,7 +738,8 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
                         cx<float> xv[NH], g[NH];
                         in_wait(in_n); in_wait(in_n + 1);
                         tile_read8(in_slot(in_n), m, half, xv); tile_read8(in_slot(in_n + 1), m, half, g);
-                        warp_arrive(&in_empty[in_n % NIN], lane); warp_arrive(&in_empty[(in_n + 1) % NIN], lane);
+                        if (MEGA_DUMP_ON) { float sx = 0.f, sv = 0.f; for (int r = 0; r < NH; ++r) { sx += xv[r].re * xv[r].re + xv[r].im * xv[r].im; sv += g[r].re * g[r].re + g[r].im * g[r].im; } MEGA_DUMP_ADD(40 + c, sx); MEGA_DUMP_ADD(48 + c, sv); }
+                        ring_release(&in_empty[in_n % NIN], &in_empty[(in_n + 1) % NIN], lane);
                         in_n += 2;
 #pragma unroll
                         for (int r = 0; r < NH; ++r) {
@@ -746,12 +816,13 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
                     MEGA_STAMP2(7);
                 }
                 MEGA_STAMP(1, tid == 0);
+                __threadfence();                              // X, V1, V2, XV stores performed at L2 (a CTA-scope release stops at L1; TMA reads L2)
                 fence_proxy_async_all();                      // X, V1, V2, XV stores -> the TMA loads of the next iteration
-                wsync();                                      // every Gram read of Z is done: the region now belongs to the Jacobi warps
-                if (more) {
+                if (more) {                                   // hand the Gram matrix to the Jacobi warps (through L2: they may still be busy with the other trial)
                     const int combo = tid / 16, q = tid % 16, gi = 4 * (combo % 4) + q / 4, gj = 4 * (combo / 4) + q % 4;
-                    JAre[gi + LDJ * gj] = gram_r; JAim[gi + LDJ * gj] = gram_i;
-                    warp_arrive(gram_ready, lane);
+                    reinterpret_cast<double2*>(p.gram + (size_t)b * p.nmc * 2 * N * N)[gi + N * gj] = make_double2(gram_r, gram_i);
+                    __threadfence();                          // the Jacobi warps read it from L2 (ld.cg): the store must have been performed there
+                    warp_arrive(&gram_ready[w], lane);
                 }
                 // ================= phase R: Res_l = A'(scale T1'_l Dt), |Res|^2, operand image of G =================
                 if (tid == 0) MEGA_BEACON(1, it * 1000 + 199);
@@ -761,6 +832,7 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
                 MEGA_STAMP(2, tid == 0);
                 double rr = 0.0;
                 for (int l = 0; l < L; ++l) {
+                    MEGA_STAMP3(11, 0);
                     {
                         float acc[16], a1[16], a2[16];
                         const uint32_t D = tm + NS * l + lane_base + 2 * n0;
@@ -778,10 +850,12 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
                     }
                     tc::tc_fence_before();
                     wsync();
-                    apply_a(AHsm, U, V, NT);                  // A' T1'_l
+                    MEGA_STAMP3(11, 1);
+                    apply_a(AHs, U, V, NT);                  // A' T1'_l
                     wsync();
-                    apply_a(Asm, V, U, NT);                   // A A' T1'_l = (A Res_l) Dt' / scale^2 (Dt unitary)
+                    apply_a(As, V, U, NT);                   // A A' T1'_l = (A Res_l) Dt' / scale^2 (Dt unitary)
                     wsync();
+                    MEGA_STAMP3(11, 2);
                     {   // operand image of tap l, written where phase G reads it (the state ring is idle between the phases F)
                         const int n = tid % N, kq = tid / N;
                         cx<float> q[4];
@@ -793,8 +867,10 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
                         });
                     }
                     wsync();                                  // U is free
+                    MEGA_STAMP3(11, 3);
                     fft64<false, WSync>(V, U, tw, 0.125f * sc);   // Res_l = (A' T1'_l) Dt
                     wsync();
+                    MEGA_STAMP3(11, 4);
                     cx<float>* Res = p.Res + (size_t)b * G * p.P + (size_t)G * NT * l;
                     for (int t = tid; t < N * NT; t += WTHREADS) {
                         const int r = t % N, cc = t / N;
@@ -802,9 +878,11 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
                         if (r < G) { Res[r + (size_t)G * cc] = v; rr += (double)v.re * v.re + (double)v.im * v.im; }
                     }
                     wsync();                                  // U is free again
+                    MEGA_STAMP3(11, 5);
                 }
                 tc::fence_async_smem();                       // image (generic stores) -> MMA operand reads (async proxy)
                 warp_arrive(img_ready, lane);
+                warp_arrive(r_done, lane);
                 if (tid == 0) MEGA_BEACON(1, it * 1000 + 300);
                 MEGA_STAMP(3, tid == 0);
                 // ================= phase G: G = (A Res) e per chunk, |G|^2 =================
@@ -824,7 +902,9 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
                 }
                 for (int o = 16; o > 0; o >>= 1) { gg += __shfl_down_sync(0xffffffffu, gg, o); rr += __shfl_down_sync(0xffffffffu, rr, o); }
                 if (lane == 0) { misc[warp] = gg; misc[8 + warp] = rr; }
-                fence_proxy_async_all();                      // G stores -> the TMA loads of the next iteration
+                __threadfence();                              // G stores performed at L2, where the TMA loads of the next iteration read them ...
+                fence_proxy_async_all();                      // ... and ordered for the async proxy
+                warp_arrive(g_done_q, lane);
                 warp_arrive(g_done, lane);                    // all MMAs of phase G have completed (last acc_full): the ring is free for the next phase F
                 wsync();
                 {
@@ -848,15 +928,17 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
                 {
                     const size_t off0 = (size_t)b * G * p.P;
                     cx<float> rn[4], vn[4];                   // Res / V of the next tap travel while this tap is processed
+                    const int er = tid % N, ec = tid / N;      // this thread's elements of a tap: row er, columns ec + 16 j
                     auto fetch = [&](int l) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const int t = tid + j * WTHREADS;
-                            if (t < G * NT) { rn[j] = p.Res[off0 + (size_t)G * NT * l + t]; vn[j] = p.V[off0 + (size_t)G * NT * l + t]; }
+                            const int t = er + G * (ec + 16 * j);
+                            if (er < G) { rn[j] = p.Res[off0 + (size_t)G * NT * l + t]; vn[j] = p.V[off0 + (size_t)G * NT * l + t]; }
                         }
                     };
                     fetch(0);
                     for (int l = 0; l < L; ++l) {
+                        MEGA_STAMP3(12, 0);
                         const size_t off = off0 + (size_t)G * NT * l;
                         const unsigned char* mask = p.angles ? p.smask + off : nullptr;
                         cx<float> rc[4], vc[4];
@@ -865,23 +947,26 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
                         if (l + 1 < L) fetch(l + 1);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const int t = tid + j * WTHREADS;
-                            if (t < G * NT) {
+                            const int t = er + G * (ec + 16 * j);
+                            cx<float> sv = mk<float>(0.f, 0.f);
+                            if (er < G) {
                                 const cx<float> v = mk<float>(vc[j].re + alpha * rc[j].re, vc[j].im + alpha * rc[j].im);
-                                cx<float> sv = mk<float>(soft1<float>(v.re, thr), soft1<float>(v.im, thr));
+                                sv = mk<float>(soft1<float>(v.re, thr), soft1<float>(v.im, thr));
                                 if (mask && !mask[t]) sv = mk<float>(0.f, 0.f);
                                 p.V[off + t] = v;
                                 if (!more) p.S[off + t] = sv;
-                                else U[(t % G) + LDU * (t / G)] = sv;
                             }
+                            if (more) U[er + LDU * (ec + 16 * j)] = sv;       // rows >= G of the padded work matrix are zero
                         }
                         if (!more) continue;
-                        if (G < N) for (int t = tid; t < N * NT; t += WTHREADS) if (t % N >= G) U[(t % N) + LDU * (t / N)] = mk<float>(0.f, 0.f);
                         wsync();
-                        apply_a(Asm, U, V, NT);               // A S_l                           (.m:58, left factor)
+                        MEGA_STAMP3(12, 1);
+                        apply_a(As, U, V, NT);               // A S_l                           (.m:58, left factor)
                         wsync();
+                        MEGA_STAMP3(12, 2);
                         fft64<true, WSync>(V, U, tw, 0.125f * sc);    // scale (A S_l) Dt'
                         wsync();
+                        MEGA_STAMP3(12, 3);
                         {   // operand image of tap l of the next pass 1, 32-byte stores straight to the image in global memory
                             const int n = tid % N, kq = tid / N;
                             cx<float> q[4];
@@ -891,13 +976,15 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
                             put_q4(n, 4 * kq, q, 1.0f, (l & 1) ? 2 : 0, [&](uint32_t o, uint4 a, uint4 bq) { stg_u4x2(img + o, a, bq); });
                         }
                         wsync();                              // U is free
+                        MEGA_STAMP3(12, 4);
                     }
                 }
                 if (more) {
+                    __threadfence();                          // image stores performed at L2 before the bulk copies of the next pass 1 read them
                     fence_proxy_async_all();
-                    warp_arrive(q_ready, lane);
+                    warp_arrive(&q_ready[w], lane);
                 }
-                alpha_prev = alpha;
+                if (w) ap1 = alpha; else ap0 = alpha;
                 if (tid == 0) MEGA_BEACON(1, it * 1000 + 500);
                 MEGA_STAMP(5, tid == 0);
             }

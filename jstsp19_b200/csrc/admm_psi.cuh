@@ -739,6 +739,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_fused_psi(AdmmP<float> p, const 
         tile_read8(S0, m, half, xo); tile_read8(S1, m, half, v1);
 #pragma unroll
         for (int r = 0; r < NH; ++r) { Zre[(n0 + r) * ZP + m] = xo[r].re - irho * v1[r].re; Zim[(n0 + r) * ZP + m] = xo[r].im - irho * v1[r].im; }
+        tc::fence_async_smem();                              // generic-proxy reads of S0 / S1 before the async-proxy refill (cross-proxy WAR)
         tc::worker_sync();                                   // S0 / S1 consumed, Z and W complete
         if (tid == 0) {
             mbar_expect_tx(&ld_full[1], 2 * SLOT);

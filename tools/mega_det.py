@@ -31,4 +31,9 @@ for imax in imaxs:
     same = [bool(torch.equal(runs[0], r)) for r in runs[1:]]
     err = [float((r - ref).norm() / ref.norm()) for r in runs]
     per = ((runs[0] - ref).flatten(1).norm(dim=1) / ref.flatten(1).norm(dim=1)).cpu().numpy()
+    for k, r in enumerate(runs):
+        e = ((r - ref).flatten(1).norm(dim=1) / ref.flatten(1).norm(dim=1)).cpu().numpy()
+        bad = np.nonzero(e > 1e-5)[0]
+        if len(bad):
+            print(f"   run {k}: trials off by > 1e-5: {[(int(i), int(i) % 148, int(i) // 148, float('%.1e' % e[i])) for i in bad]}  (trial, CTA, position in the CTA's list, error)")
     print(f"imax {imax:3d} variant {var}: bitwise repeatable {same}; rel diff to four-kernel {['%.2e' % e for e in err]}; per trial (run 0) {np.array2string(per, precision=1)}", flush=True)

@@ -40,6 +40,18 @@ if os.environ["JSTSP_DBG_KERNEL"] == "8":
         d = np.diff(t[:, it, :8], axis=1)
         print(f"it {it:2d}: " + " | ".join(f"{n} {np.median(d[:, i]):7.0f}" for i, n in enumerate(nm)) + f" | total {np.median(t[:, it, 7] - t[:, it, 0]):8.0f}")
     sys.exit(0)
+if os.environ["JSTSP_DBG_KERNEL"] in ("11", "12"):
+    nm = {"11": ["T1' from TMEM", "A', A A'", "operand image", "FFT", "Res store, |Res|^2"], "12": ["alpha, V, S", "A S", "inverse FFT", "operand image -> global"]}[os.environ["JSTSP_DBG_KERNEL"]]
+    print(f"variant {eng.h.last_variant}; tap 1 of phase {'R' if os.environ['JSTSP_DBG_KERNEL'] == '11' else 'S'}, cycles per stage, median over {ncta} CTAs")
+    for it in (0, 1, 2, 5, 10):
+        d = np.diff(t[:, it, :len(nm) + 1], axis=1)
+        print(f"it {it:2d}: " + " | ".join(f"{n} {np.median(d[:, i]):7.0f}" for i, n in enumerate(nm)) + f" | total {np.median(t[:, it, len(nm)] - t[:, it, 0]):8.0f}")
+    sys.exit(0)
+if os.environ["JSTSP_DBG_KERNEL"] == "13":
+    print(f"variant {eng.h.last_variant}; MMA warp in phase G, cycles, median over {ncta} CTAs")
+    for it in (0, 1, 2, 5, 10):
+        print(f"it {it:2d}: wait image {np.median(t[:, it, 0]):8.0f} | wait pilot tiles {np.median(t[:, it, 1]):8.0f} | wait accumulators {np.median(t[:, it, 2]):8.0f} | issue {np.median(t[:, it, 3]):8.0f} | phase total {np.median(t[:, it, 4]):8.0f}")
+    sys.exit(0)
 if os.environ["JSTSP_DBG_KERNEL"] == "9":
     print(f"variant {eng.h.last_variant}; Jacobi warps, cycles, median over {ncta} CTAs")
     for it in (0, 1, 2, 5, 10, 14):
@@ -53,5 +65,5 @@ for it in (0, 1, 2, 5, 10, 15):
     line = " | ".join(f"{n} {np.median(d[:, i]):8.0f}" for i, n in enumerate(names))
     tot = np.median(t[:, it, 5] - t[:, it, 0])
     jac = np.median(t[:, it, 7] - t[:, it, 6]) if it + 1 < imax else 0
-    nxt = np.median(t[:, it + 1, 0] - t[:, it, 5]) if it + 1 < imax else 0
-    print(f"it {it:2d}: {line} | total {tot:8.0f} | Jacobi {jac:8.0f} | gap to next F {nxt:8.0f}")
+    nxt = np.median(t[:, it + 1, 0] - t[:, it, 0]) if it + 1 < imax else 0
+    print(f"it {it:2d}: {line} | total {tot:8.0f} | Jacobi {jac:8.0f} | start of this F to start of the trial's next F {nxt:8.0f} ({min(2, nb // ncta)} trials interleaved)")
