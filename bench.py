@@ -153,6 +153,90 @@ def run_reference(args):
     emit(line)
 
 
+def secondary_configs(torch, dist, _lib, dev, local, rank, world, pk_hbm):
+    """BASELINE.json configs[2] (OMP over the Kronecker beamspace-delay dictionary, Nt = Nr = 64, K = 32, 4x grids: A 64 x 256, B 1024 x 128 per trial,
+    m = 100 as numOfnz of plot_errorVSsnr.m:20) and configs[3] (mc_svt / mc_admm / sparse_admm / vamp at the longest frame of plot_errorVSframelength.m,
+    T = 35, every operator per trial).  Device-resident operands, one warm-up + timed calls, max over ranks."""
+    import ctypes as C
+    import numpy as np
+    g = torch.Generator(device=dev); g.manual_seed(77 + rank)
+    h = _lib.Handle(local)
+    h.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    L = _lib.lib
+    p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    crandn = lambda *sh: (torch.randn(*sh, generator=g, device=dev) + 1j * torch.randn(*sh, generator=g, device=dev)).to(torch.complex64)
+
+    def timed(fn, steps=2):
+        fn(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    out = {}
+    # ---- config 2 ----
+    N, M, G, P, m, nbk = 64, 128, 256, 1024, 100, 148
+    A = (torch.exp(-2j * torch.pi * torch.outer(torch.arange(G, device=dev), torch.arange(N, device=dev)) / G) / N ** 0.5).to(torch.complex64).contiguous()
+    B = ((torch.randint(0, 2, (nbk, M, P), generator=g, device=dev) * 2 - 1) + 1j * (torch.randint(0, 2, (nbk, M, P), generator=g, device=dev) * 2 - 1)).to(torch.complex64) / (2 * M) ** 0.5
+    S = torch.zeros(nbk, P, G, dtype=torch.complex64, device=dev)
+    idx = torch.randint(0, G * P, (nbk, 12), generator=g, device=dev)
+    S.view(nbk, -1).scatter_(1, idx, crandn(nbk, 12) * 2)
+    Y = torch.matmul(torch.matmul(B, S), A.unsqueeze(0).expand(nbk, -1, -1)).contiguous()
+    Y += 0.02 * torch.randn(Y.shape, generator=g, device=dev, dtype=torch.float32).to(torch.complex64)
+    iset = torch.zeros(nbk, m, dtype=torch.int32, device=dev); xsel = torch.zeros(nbk, m, dtype=torch.complex64, device=dev); amb = torch.zeros(nbk, dtype=torch.int32, device=dev)
+    L.jstsp_profile(h.ptr, 2)
+    ms = timed(lambda: h.check(L.jstsp_omp_kron(h.ptr, _lib.F32, _lib.DEVICE, N, M, G, P, m, nbk, p(A), 0, p(B), P * M, p(Y), N * M, None, 0, p(iset), p(xsel), None, 0, p(amb), 1e-4)))
+    kern = h.profile_read(); L.jstsp_profile(h.ptr, 0)
+    corr = kern.get("omp_kron_corr_tc") or kern.get("omp_kron_corr")
+    cmac = N * M * P + G * N * P
+    out["config2_omp_kron"] = dict(workload="jstsp_omp_kron, A 64 x 256, B 1024 x 128 per trial, Y 64 x 128, m = 100 (dictionary 8192 x 262144 never formed)", value=world * nbk / ms * 1e3,
+                                   unit="trials/s", trials_per_gpu=nbk, ms_per_call=ms,
+                                   corr_kernel_tflops=(8 * cmac * nbk / (corr[0] / corr[1] * 1e-3) / 1e12) if corr and corr[1] else None,
+                                   corr_kernel_peak_tflops=peaks()["bf16_sus"] / 2.0, corr_kernel_pipe="tcgen05 kind::tf32 screen + fp64 re-decision")
+    del B, S, Y
+    # ---- config 3 (T = 35: 32 x 280) ----
+    nbs, Mr, Mt, IM = 592, 32, 280, 100
+    one = lambda v: torch.full((nbs,), v, dtype=torch.float64, device=dev)
+    OH = crandn(nbs, Mt, Mr); Om = (torch.rand(nbs, Mt, Mr, generator=g, device=dev) < 0.125).float().contiguous(); OH = (OH * Om).contiguous()
+    X = torch.empty_like(OH); tau, rho = one(0.02), one(0.1)
+    ms = timed(lambda: h.check(L.jstsp_mc_svt(h.ptr, _lib.F32, _lib.DEVICE, Mr, Mt, nbs, IM, p(OH), Mr * Mt, p(Om), Mr * Mt, p(tau), p(rho), p(X), Mr * Mt)))
+    by = IM * (3 * 8 * Mr * Mt + Mr * Mt // 8) + 8 * Mr * Mt
+    out["config3_mc_svt"] = dict(shape=[Mr, Mt, IM], value=world * nbs / ms * 1e3, unit="estimates/s", hbm_frac=by * nbs / (ms * 1e-3) / 1e9 / pk_hbm, algorithmic_bytes_per_estimate=by)
+    ms = timed(lambda: h.check(L.jstsp_mc_admm(h.ptr, _lib.F32, _lib.DEVICE, Mr, Mt, nbs, IM, None, 0, p(OH), Mr * Mt, p(Om), Mr * Mt, p(tau), p(rho), p(X), Mr * Mt, None, 0)))
+    by = IM * (5 * 8 * Mr * Mt + Mr * Mt // 8)
+    out["config3_mc_admm"] = dict(shape=[Mr, Mt, IM], value=world * nbs / ms * 1e3, unit="estimates/s", hbm_frac=by * nbs / (ms * 1e-3) / 1e9 / pk_hbm, algorithmic_bytes_per_estimate=by)
+    Mt8 = 8
+    Dr = (torch.exp(-2j * torch.pi * torch.outer(torch.arange(Mr, device=dev), torch.arange(Mr, device=dev)) / Mr) / Mr ** 0.5).to(torch.complex64).contiguous()
+    Dt = (torch.exp(-2j * torch.pi * torch.outer(torch.arange(Mt8, device=dev), torch.arange(Mt8, device=dev)) / Mt8) / Mt8 ** 0.5).to(torch.complex64).contiguous()
+    OHs = crandn(nbs, Mt8, Mr); Ss = torch.empty_like(OHs)
+    ms = timed(lambda: h.check(L.jstsp_sparse_admm(h.ptr, _lib.F32, _lib.DEVICE, Mr, Mt8, nbs, IM, None, 0, p(OHs), Mr * Mt8, p(Dr), 0, p(Dt), 0, p(Ss), Mr * Mt8, None, 0)))
+    by = IM * 4 * 8 * Mr * Mt8 + 8 * Mr * Mt8
+    out["config3_sparse_admm"] = dict(shape=[Mr, Mt8, IM], value=world * nbs / ms * 1e3, unit="estimates/s", hbm_frac=by * nbs / (ms * 1e-3) / 1e9 / pk_hbm, algorithmic_bytes_per_estimate=by)
+    # vamp.m with the reference's per-trial operator (plot_errorVSframelength.m:78: Phi = kron((B B').', A), here 256 x 1024 per trial); its svd (vamp.m:32) on the host
+    mm, nn, nbv = 256, 1024, 32
+    Av = (crandn(nbv, nn, mm) / mm ** 0.5).contiguous()
+    Uh, sh = [], []
+    for k in range(nbv):
+        U_, s_, _ = np.linalg.svd(Av[k].cpu().numpy().T.astype(np.complex128), full_matrices=True)
+        Uh.append(np.ascontiguousarray(U_.T)); sh.append(s_ ** 2)
+    Ud = torch.tensor(np.stack(Uh), dtype=torch.complex64, device=dev).contiguous(); dd = torch.tensor(np.stack(sh), dtype=torch.float32, device=dev).contiguous()
+    yv = crandn(nbv, mm); xv = torch.empty(nbv, nn, dtype=torch.complex64, device=dev)
+    sg, Ln = torch.full((nbv,), 1.0, dtype=torch.float64, device=dev), torch.full((nbv,), 50.0, dtype=torch.float64, device=dev)
+    ms = timed(lambda: h.check(L.jstsp_vamp(h.ptr, _lib.F32, _lib.DEVICE, mm, nn, nbv, 100, 0.85, p(yv), mm, p(Av), mm * nn, p(sg), p(Ln), p(Ud), mm * mm, p(dd), mm, p(xv), nn)))
+    by = 100 * 8 * (2 * mm * nn + 2 * mm * mm)
+    out["config3_vamp"] = dict(shape=[mm, nn, 100], value=world * nbv / ms * 1e3, unit="estimates/s", per_trial_operator=True, hbm_frac=by * nbv / (ms * 1e-3) / 1e9 / pk_hbm,
+                               algorithmic_bytes_per_estimate=by, note="A, A', U, U' of every trial streamed once per iteration; the svd of vamp.m:32 is host LAPACK, outside the timed region")
+    h.close()
+    return out
+
+
 _REAL_STDOUT = None
 
 
@@ -196,6 +280,7 @@ def main():
     ap.add_argument("--entry", default="psi", choices=["psi", "dense"],
                     help="psi: jstsp_proposed_algorithm_psi (dictionary given by its factors Dt, Psi_bar as the reference's drivers hold them); "
                          "dense: jstsp_proposed_algorithm (dense B, the reference function's own argument list)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short legs for BASELINE configs 2 (Kronecker OMP) and 3 (mc_svt / mc_admm / sparse_admm / vamp)")
     ap.add_argument("--no-dense", action="store_true", help="skip the short dense-B entry measurement that accompanies --entry psi")
     ap.add_argument("--shared-b", action="store_true", help="diagnostic: one pilot matrix B for all trials (L2-resident dictionary)")
     args = ap.parse_args()
@@ -319,6 +404,11 @@ def main():
                         stages="draws (torch) -> jstsp_wideband_mmwave_channel -> jstsp_measure -> jstsp_admm_parameters -> jstsp_proposed_algorithm_pilots -> jstsp_nmse",
                         mean_nmse=pst["mean_nmse"], trials=pst["trials"], flagged=pst["flagged"])
 
+    # ---- BASELINE configs 2 and 3, trial-sharded like the headline (every rank its own trials, device time, max over ranks) ----
+    secondary = None
+    if not args.no_secondary:
+        secondary = secondary_configs(torch, dist, _lib, dev, local, rank, world, pk_hbm=peaks()["hbm"])
+
     # ---- end-to-end through the HOST-buffer C ABI (pinned host memory) ----
     e2e = None
     if not args.no_e2e:
@@ -402,6 +492,7 @@ def main():
     # ---- roofline of the dominant kernel (live CUDA-event timing inside the library) ----
     pk = peaks()
     F_est = flops_per_estimate(N, M, G, P, IMAX)
+    F_iter = (F_est - 8 * P * P * M) // IMAX                  # SURVEY 8(d) flops of one iteration (the structured path never forms B B^H)
     kflops = {  # algorithmic real flops per launch of each kernel class (per trial x nb trials)
         "xupd_t1": 8 * (N * N * M + N * M * P + N * N * M) * nb,      # W Z, K B^H, next Gram
         "xs": 8 * (N * P * M) * nb,                                  # (A S) B
@@ -411,33 +502,43 @@ def main():
         "fused_tc": 8 * (2 * N * N * M + 2 * N * M * P) * nb,        # tcgen05 path: (A S) B, W Z, K B^H, next Gram in one kernel
         "fused_psi": 8 * (2 * N * N * M + 2 * N * M * P) * nb,       # Psi-domain tcgen05 path: same products out of the bf16 pilot tile
         "psi_g": 8 * (N * M * P) * nb,                               # G = (A Res) B for the line search
+        "psi_mega": F_iter * IMAX * nb,                              # the whole solve in one persistent kernel: SURVEY 8(d)'s flops per estimate x trials
     }
-    # algorithmic HBM bytes per launch of the Psi-domain fused kernel: state X,V1,V2,subY,XV in + X,V1,V2 out,
-    # mask bits, bf16 pilot image (2 x 2 x Nt x (M+L-1)), operand Q in and T1' out (8 N P each)
+    # algorithmic HBM bytes per launch.  fused_psi: state X,V1,V2,subY,XV in + X,V1,V2 out, mask bits, bf16 pilot image,
+    # operand Q in and T1' out.  psi_mega: SURVEY 8(d)'s streamed-state figure, Imax (9 x 8NM + 2 x 8GP) per estimate.
     kbytes = {"fused_psi": (8 * 8 * N * M + N * M // 8 + 4 * s.Nt * (M + s.L - 1) + 16 * N * P) * nb,
-              "psi_g": (8 * N * M + 4 * s.Nt * (M + s.L - 1) + 8 * N * P) * nb}
+              "psi_g": (8 * N * M + 4 * s.Nt * (M + s.L - 1) + 8 * N * P) * nb,
+              "psi_mega": IMAX * (9 * 8 * N * M + 2 * 8 * G * P) * nb}
+    # pipe a kernel's contractions run on -> measured peak it is scored against
+    tensor_pipe = {"fused_tc": ("tcgen05 kind::tf32, 3 tf32 terms", pk["bf16_sus"] / 2.0 / 3.0, "bf16_tflops_sustained / 2 (TF32) / 3 terms"),
+                   "fused_psi": ("tcgen05 kind::f16, 3 bf16 terms x exact bf16 pilots", pk["bf16_sus"] / 3.0, "bf16_tflops_sustained / 3 terms"),
+                   "psi_g": ("tcgen05 kind::f16, 3 bf16 terms x exact bf16 pilots", pk["bf16_sus"] / 3.0, "bf16_tflops_sustained / 3 terms"),
+                   "psi_mega": ("tcgen05 kind::f16, 3 bf16 terms x exact bf16 pilots", pk["bf16_sus"] / 3.0, "bf16_tflops_sustained / 3 terms")}
     tot_ms = sum(v[0] for v in prof.values()) or 1.0
     top = max((k for k in prof if k in kflops and prof[k][1] > 0), key=lambda k: prof[k][0], default=None)
     roof = None
     if top:
         avg_ms = prof[top][0] / prof[top][1]
-        achieved = kflops[top] / (avg_ms * 1e-3) / 1e12
-        peak = pk["bf16_sus"] / 2.0 / 3.0          # TF32 dense = bf16/2; a 3xTF32-equivalent fp32 contraction is scored against TF32/3
+        tf = kflops[top] / (avg_ms * 1e-3) / 1e12
+        pipe, tpeak, tsrc = tensor_pipe.get(top, ("fp32 FMA (CUDA cores)", 72.0, "148 SMs x 128 lanes x 2 x 1.9 GHz"))
         traffic = None                             # DRAM bytes per launch of that kernel from the committed ncu --set full capture (scaled by the trial count)
-        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tp):
-            t = json.load(open(tp)).get(top)
-            if t:
-                traffic = t["dram_bytes_per_launch_888_trials"] * nb / 888.0 if "dram_bytes_per_launch_888_trials" in t else t["dram_bytes_per_launch_592_trials"] * nb / 592.0
-        roof = dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=traffic,
-                    kernel=top, avg_launch_ms=avg_ms, share_of_step=prof[top][0] / tot_ms,
-                    peak_source=f"{pk['src']} bf16_tflops_sustained/2 (TF32) /3 (3xTF32-equivalent fp32 accuracy), SURVEY.md 8(d)",
-                    pipe={"fused_tc": "tcgen05 kind::tf32 x3 (tensor cores)", "fused_psi": "tcgen05 kind::f16, 3 bf16 terms x exact bf16 pilots (tensor cores)"}.get(top, "fp32 FMA (CUDA cores)"), fma_peak_tflops=72.0, frac_of_fma_peak=achieved / 72.0,
-                    kernels={k: dict(ms_total=v[0], launches=v[1]) for k, v in prof.items() if v[1]})
+        for tpn in ("r02_traffic.json", "r01_traffic.json"):
+            tp = os.path.join(ROOT, "profiles", tpn)
+            if traffic is None and os.path.exists(tp):
+                t = json.load(open(tp)).get(top)
+                if t:
+                    per = t.get("dram_bytes_per_launch_888_trials", t.get("dram_bytes_per_launch_592_trials", 0) * 888.0 / 592.0)
+                    traffic = per * nb / 888.0 * (IMAX / t.get("imax", IMAX))
+        views = dict(tensor=dict(bound="tensor", achieved=tf, peak=tpeak, unit="TFLOP/s", frac=tf / tpeak, pipe=pipe, peak_source=f"{pk['src']} {tsrc}",
+                                 algorithmic_flops_per_launch=kflops[top]))
         if top in kbytes:
             hb = kbytes[top] / (avg_ms * 1e-3) / 1e9
-            roof["hbm_view"] = dict(bound="hbm", achieved=hb, peak=pk["hbm"], unit="GB/s", frac=hb / pk["hbm"], algorithmic_bytes_per_launch=kbytes[top],
-                                    note="the same launch scored against measured HBM copy bandwidth; ncu shows this kernel latency-bound (DRAM 36 %, tensor pipe 17 % busy)")
+            views["hbm"] = dict(bound="hbm", achieved=hb, peak=pk["hbm"], unit="GB/s", frac=hb / pk["hbm"], peak_source=f"{pk['src']} hbm_gbs (copy bandwidth)",
+                                algorithmic_bytes_per_launch=kbytes[top])
+        best = max(views.values(), key=lambda v: v["frac"])           # the bound the kernel sits closest to
+        roof = dict(bound=best["bound"], achieved=best["achieved"], peak=best["peak"], unit=best["unit"], frac=best["frac"], traffic=traffic,
+                    kernel=top, avg_launch_ms=avg_ms, share_of_step=prof[top][0] / tot_ms, peak_source=best["peak_source"], views=views,
+                    kernels={k: dict(ms_total=v[0], launches=v[1]) for k, v in prof.items() if v[1]})
     cpu = None
     if not args.no_cpu:
         r, dt = cpu_port_rate(args.cpu_trials)
@@ -460,7 +561,7 @@ def main():
                             parallelism=f"trials sharded over {world} GPU(s), one NCCL all-reduce of NMSE sums"),
                 clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu,
                 algorithmic_gflop_per_estimate=F_est / 1e9, achieved_tflops_whole_step=F_est * value / 1e12,
-                nmse=stats, other_entry=other, pipeline=pipeline)
+                nmse=stats, other_entry=other, pipeline=pipeline, secondary=secondary)
     emit(line)
     if world > 1:
         dist.destroy_process_group()
