@@ -47,7 +47,9 @@ struct KronP {
     cx<T>* Bsel;                         // [b][m][M] B(p_j, :)
     int* state;                          // [b][2 + 3m]: nuniq, amb, sel[m], uniq_idx[m], mult[m]
     double* cand_val;                    // [b][nchunk][2] best, second
-    int* cand_idx;                       // [b][nchunk]
+    int* cand_idx;                       // [b][nchunk]    index of the best
+    int* cand_idx2;                      // [b][nchunk]    index of the runner-up of the chunk
+    float* abmax;                        // [b] (max |A entry|)(max |B entry|): scale of the rounding error of the tf32 screen
     double margin_tol;
     // tensor-core screening path (fp32, N == 64): packed K-major operands and per-tile candidates
     float* Bt;                           // [nB][P][2M]   row p = B(p,:) interleaved (re,im)
@@ -96,6 +98,17 @@ __global__ void __launch_bounds__(256) k_kron_setup(KronP<T> p, int nA, int nB) 
         }
     }
     if (p.flag && tid == 0) p.flag[b] = 0;
+    if (p.abmax) {                                                            // entrywise maxima of this trial's A and B
+        __shared__ float s_am[8], s_bm[8];
+        const cx<T>* A = p.A + (long long)b * p.ld_A; const cx<T>* B = p.B + (long long)b * p.ld_B;
+        float am = 0.f, bm = 0.f;
+        for (int i = tid; i < p.N * p.G; i += 256) am = fmaxf(am, (float)(A[i].re * A[i].re + A[i].im * A[i].im));
+        for (size_t i = tid; i < (size_t)p.P * p.M; i += 256) bm = fmaxf(bm, (float)(B[i].re * B[i].re + B[i].im * B[i].im));
+        for (int o = 16; o > 0; o >>= 1) { am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o)); bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, o)); }
+        if (tid % 32 == 0) { s_am[tid / 32] = am; s_bm[tid / 32] = bm; }
+        __syncthreads();
+        if (tid == 0) { for (int w = 1; w < 8; ++w) { am = fmaxf(am, s_am[w]); bm = fmaxf(bm, s_bm[w]); } p.abmax[b] = sqrtf(am) * sqrtf(bm); }
+    }
     if (p.Bt && b < nB) {
         const cx<T>* B = p.B + (long long)b * p.ld_B;
         float* bt = p.Bt + (size_t)b * 2 * p.P * p.M;
@@ -157,7 +170,7 @@ __device__ __forceinline__ void kron_corr_item(const KronP<T>& p, int chunk, int
         }
     }
     // ---- phase 2: C_c(g, p) = sum_n AH(g, n) T_c(n, p); arg-max of |C|^2, lowest j = g + G p on ties ----
-    double best = -1.0, second = -1.0; long long bidx = 0x7fffffffffffLL;
+    double best = -1.0, second = -1.0; long long bidx = 0x7fffffffffffLL, sidx = 0x7fffffffffffLL;
     for (int g0 = 0; g0 < G; g0 += KC_RB) {
         T ar[4][2], ai[4][2];
 #pragma unroll
@@ -189,32 +202,37 @@ __device__ __forceinline__ void kron_corr_item(const KronP<T>& p, int chunk, int
                 if (g < G && pp < P) {
                     const double mag = (double)ar[i][j] * ar[i][j] + (double)ai[i][j] * ai[i][j];
                     const long long jj = g + (long long)G * pp;
-                    if (mag > best || (mag == best && jj < bidx)) { second = best; best = mag; bidx = jj; }
-                    else if (mag > second) second = mag;
+                    if (mag > best || (mag == best && jj < bidx)) { second = best; sidx = bidx; best = mag; bidx = jj; }
+                    else if (mag > second || (mag == second && jj < sidx)) { second = mag; sidx = jj; }
                 }
             }
     }
     // ---- reduce (best, second, index) over the CTA ----
     for (int o = 16; o > 0; o >>= 1) {
         const double ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, second, o);
-        const long long oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-        if (ob > best || (ob == best && oi < bidx)) { second = best > os ? best : os; best = ob; bidx = oi; }
-        else { const double c = ob > os ? ob : os; if (c > second) second = c; }
+        const long long oi = __shfl_xor_sync(0xffffffffu, bidx, o), osi = __shfl_xor_sync(0xffffffffu, sidx, o);
+        // merge (best, runner-up) of the two lanes: the two largest of the four records, lowest index first on equal values
+        if (ob > best || (ob == best && oi < bidx)) {
+            if (best > os || (best == os && bidx < osi)) { second = best; sidx = bidx; } else { second = os; sidx = osi; }
+            best = ob; bidx = oi;
+        } else if (ob > second || (ob == second && oi < sidx)) { second = ob; sidx = oi; }
     }
-    __shared__ long long s_lidx[8];
-    if (lane == 0) { s_best[warp] = best; s_second[warp] = second; s_lidx[warp] = bidx; }
+    __shared__ long long s_lidx[8], s_lidx2[8];
+    if (lane == 0) { s_best[warp] = best; s_second[warp] = second; s_lidx[warp] = bidx; s_lidx2[warp] = sidx; }
     __syncthreads();
     if (tid == 0) {
-        double gb = -1.0, gs = -1.0; long long gi = 0x7fffffffffffLL;
+        double gb = -1.0, gs = -1.0; long long gi = 0x7fffffffffffLL, gi2 = 0x7fffffffffffLL;
         for (int w = 0; w < 8; ++w) {
-            const double wb = s_best[w], wsd = s_second[w];
-            if (wb > gb || (wb == gb && s_lidx[w] < gi)) { if (gb > gs) gs = gb; gb = wb; gi = s_lidx[w]; }
-            else if (wb > gs) gs = wb;
-            if (wsd > gs) gs = wsd;
+            const double wv[2] = {s_best[w], s_second[w]}; const long long wi[2] = {s_lidx[w], s_lidx2[w]};
+            for (int k = 0; k < 2; ++k) {
+                if (wv[k] > gb || (wv[k] == gb && wi[k] < gi)) { gs = gb; gi2 = gi; gb = wv[k]; gi = wi[k]; }
+                else if (wv[k] > gs || (wv[k] == gs && wi[k] < gi2)) { gs = wv[k]; gi2 = wi[k]; }
+            }
         }
         p.cand_val[((size_t)b * p.nchunk + chunk) * 2 + 0] = gb;
         p.cand_val[((size_t)b * p.nchunk + chunk) * 2 + 1] = gs;
         p.cand_idx[(size_t)b * p.nchunk + chunk] = (int)gi;
+        p.cand_idx2[(size_t)b * p.nchunk + chunk] = (int)gi2;
     }
     __syncthreads();
 }
@@ -464,25 +482,40 @@ __global__ void __launch_bounds__(KU_T) k_kron_update(KronP<T> p) {
     int* sel = st + 2; int* uniq_idx = sel + m; int* mult = uniq_idx + m;
     const int nu = st[0];
     if (p.flag && !p.screen && !p.flag[b]) return;                            // fallback launch: only trials the screen left undecided (the flag is rewritten by the next screen)
+    // ---- candidate list: every entry that the correlation pass could not rule out as the first maximum of |Phi' r|^2 (OMP.m:17).
+    //      More than one candidate -> all of them are re-evaluated in fp64 (a_g' R b_p', N M terms) and the first maximum of the
+    //      exact values is the pick, so the support equals an fp64 evaluation's whichever pass produced the list. ----
+    constexpr int MAXC = 128, MAXR = 8;
+    __shared__ int s_cand[MAXC];
+    __shared__ double s_cmag[MAXC];
+    __shared__ int s_rows[MAXR];
+    __shared__ int s_nc, s_nrow, s_fail;
+    __shared__ float s_vmax, s_band;
+    __shared__ double s_lim2;
+    if (tid == 0) { s_nc = 0; s_nrow = 0; s_fail = 0; s_lim2 = 0.0; }
     if (p.screen) {
-        // ---- candidates of the tf32 screen: every row maximum within `band` of the largest value is re-evaluated in fp64; a row
-        //      whose runner-up is in the band too is recomputed whole (exactly), since the screen does not keep that index ----
-        constexpr int MAXC = 128, MAXR = 8;
-        __shared__ int s_cand[MAXC];
-        __shared__ double s_cmag[MAXC];
-        __shared__ int s_rows[MAXR];
-        __shared__ int s_nc, s_nrow, s_fail;
-        __shared__ float s_vmax;
+        // tf32 screen: every row maximum within the band of the largest value; a row whose runner-up is in the band too is recomputed whole
+        // (exactly), since the screen does not keep that index.  The band is the larger of p.band and four times the screen's own rounding
+        // error relative to |C|max: 16 x 2^-10 (tf32 truncation of three operands, random-sign accumulation with a wide margin) x |R|_F x
+        // max|A| x max|B|.  A residual that is mostly noise therefore widens the band by itself; a list that overflows hands the
+        // iteration to the fp32 pass below.
         const float* rv1 = p.row_v1 + (size_t)b * P; const int* rg1 = p.row_g1 + (size_t)b * P; const float* rv2 = p.row_v2 + (size_t)b * P;
-        float vm = -1.f;
+        float vm = -1.f; double r2 = 0.0;
         for (int q = tid; q < P; q += KU_T) vm = fmaxf(vm, rv1[q]);
-        for (int o = 16; o > 0; o >>= 1) vm = fmaxf(vm, __shfl_xor_sync(0xffffffffu, vm, o));
-        if (lane == 0) s_red[warp][0] = vm;
-        if (tid == 0) { s_nc = 0; s_nrow = 0; }
+        for (size_t i = tid; i < NM; i += KU_T) { const cx<T> x = r[i]; r2 += (double)x.re * x.re + (double)x.im * x.im; }
+        for (int o = 16; o > 0; o >>= 1) { vm = fmaxf(vm, __shfl_xor_sync(0xffffffffu, vm, o)); r2 += __shfl_xor_sync(0xffffffffu, r2, o); }
+        if (lane == 0) { s_red[warp][0] = vm; s_red[warp][1] = r2; }
         __syncthreads();
-        if (tid == 0) { float a = -1.f; for (int w = 0; w < KU_W; ++w) a = fmaxf(a, (float)s_red[w][0]); s_vmax = a; }
+        if (tid == 0) {
+            float a = -1.f; double rr = 0.0;
+            for (int w = 0; w < KU_W; ++w) { a = fmaxf(a, (float)s_red[w][0]); rr += s_red[w][1]; }
+            s_vmax = a;
+            const float e = 16.f * 9.765625e-4f * (float)sqrt(rr) * (p.abmax ? p.abmax[b] : 1.f);
+            const float rel = a > 0.f ? 4.f * e * rsqrtf(a) : 1.f;
+            s_band = fminf(fmaxf(p.band, rel), 0.5f);
+        }
         __syncthreads();
-        const float vmax = s_vmax, lim = vmax * (1.f - p.band);
+        const float vmax = s_vmax, lim = vmax * (1.f - s_band);
         for (int q = tid; q < P; q += KU_T) {
             const bool whole = rv2[q] >= lim && rv2[q] >= 0.f;
             if (whole) { const int k = atomicAdd(&s_nrow, 1); if (k < MAXR) s_rows[k] = q; }
@@ -496,10 +529,31 @@ __global__ void __launch_bounds__(KU_T) k_kron_update(KronP<T> p) {
                 atomicAdd(ctr + 0, 1ull); atomicAdd(ctr + 1, (unsigned long long)failed); atomicAdd(ctr + 2, (unsigned long long)s_nc); atomicAdd(ctr + 3, (unsigned long long)s_nrow);
             }
             s_fail = failed; p.flag[b] = failed;
+            s_lim2 = (double)lim * (1.0 - (double)s_band);
         }
         __syncthreads();
         if (s_fail) return;
-        const int nc0 = s_nc, nrow = s_nrow;
+    } else {
+        // fp32 / fp64 correlation pass (k_kron_corr): best and runner-up of every chunk, with their indices.  Every record within the pass's own
+        // rounding band of the largest value (1e-4 relative on |C|^2 for fp32 sums of N M terms, 1e-11 for fp64, or the caller's margin_tol if
+        // wider) is a candidate.  (A chunk keeps two records, so a THIRD entry of one chunk inside a 1e-4 band would go unseen.)
+        if (tid == 0) {
+            double gb = -1.0;
+            for (int c = 0; c < p.nchunk; ++c) gb = fmax(gb, p.cand_val[((size_t)b * p.nchunk + c) * 2]);
+            const double band = fmax(p.margin_tol, sizeof(T) == 4 ? 1e-4 : 1e-11), lim = gb * (1.0 - band);
+            int nc = 0;
+            for (int c = 0; c < p.nchunk; ++c) {                              // chunks ascend in p, i.e. in j
+                const double wb = p.cand_val[((size_t)b * p.nchunk + c) * 2], wsd = p.cand_val[((size_t)b * p.nchunk + c) * 2 + 1];
+                if (wb >= lim && nc < MAXC) s_cand[nc++] = p.cand_idx[(size_t)b * p.nchunk + c];
+                if (wsd >= lim && wsd >= 0.0 && nc < MAXC) s_cand[nc++] = p.cand_idx2[(size_t)b * p.nchunk + c];
+            }
+            s_nc = nc; s_nrow = 0;
+            if (nc == 0) { s_cand[0] = 0; s_nc = 1; }                         // non-finite correlations: index 1, like max() of a NaN vector would not be - flagged by the caller's checks
+        }
+        __syncthreads();
+    }
+    {
+        const int nc0 = s_nc < MAXC ? s_nc : MAXC, nrow = s_nrow < MAXR ? s_nrow : MAXR;
         if (nc0 + nrow > 1 || nrow > 0) {
             for (int c = 0; c < nc0; ++c) {                                      // exact |a_g' R b_p'|^2 (OMP.m:17 for one column)
                 const int j = s_cand[c], g = j % G, pq = j / G;
@@ -520,7 +574,7 @@ __global__ void __launch_bounds__(KU_T) k_kron_update(KronP<T> p) {
             }
             // whole rows: u = R b_p' (N values), c_g = a_g' u for every g; entries inside a slightly wider band join the list with exact values
             double* u = reinterpret_cast<double*>(smem);                         // 2 N doubles (the least-squares scratch is not live yet)
-            const double lim2 = (double)lim * (1.0 - (double)p.band);
+            const double lim2 = s_lim2;
             for (int rr = 0; rr < nrow; ++rr) {
                 const int pq = s_rows[rr];
                 const cx<T>* bq = p.B + (long long)b * p.ld_B + pq;
@@ -543,6 +597,8 @@ __global__ void __launch_bounds__(KU_T) k_kron_update(KronP<T> p) {
                 __syncthreads();
             }
         }
+        // the whole-row pass may have overflowed the list: nothing has been written yet, the fp32 pass decides this iteration
+        if (p.screen && s_nc > MAXC) { if (tid == 0) p.flag[b] = 1; return; }
         if (tid == 0) {
             const int nc = s_nc < MAXC ? s_nc : MAXC;
             double gb = -1.0, gs = -1.0; int gi = nc > 0 ? s_cand[0] : 0;
@@ -553,29 +609,15 @@ __global__ void __launch_bounds__(KU_T) k_kron_update(KronP<T> p) {
                     if (wb > gb || (wb == gb && wi < gi)) { if (gb > gs) gs = gb; gb = wb; gi = wi; }
                     else if (wb > gs) gs = wb;
                 }
-                if (gs >= 0.0 && gb - gs <= p.margin_tol * gb) st[1]++;
+                // "ambiguous" now means: two EXACT (fp64) values closer than fp64 rounding of an N M-term sum - a genuine tie, resolved like max() by the lowest index
+                if (gs >= 0.0 && gb - gs <= 1e-12 * gb) st[1]++;
             }
-            p.index_set[(size_t)b * m + t] = gi + 1;
+            p.index_set[(size_t)b * m + t] = gi + 1;                              // 1-based (OMP.m:17)
             int dup = -1;
             for (int k = 0; k < nu; ++k) if (uniq_idx[k] == gi) dup = k;
             if (dup >= 0) { sel[t] = dup; mult[dup]++; }
             s_pick = gi; s_dup = dup;
         }
-    } else if (tid == 0) {
-        double gb = -1.0, gs = -1.0; int gi = 0x7fffffff;
-        for (int c = 0; c < p.nchunk; ++c) {                                  // chunks ascend in p, i.e. in j
-            const double wb = p.cand_val[((size_t)b * p.nchunk + c) * 2], wsd = p.cand_val[((size_t)b * p.nchunk + c) * 2 + 1];
-            const int wi = p.cand_idx[(size_t)b * p.nchunk + c];
-            if (wb > gb || (wb == gb && wi < gi)) { if (gb > gs) gs = gb; gb = wb; gi = wi; }
-            else if (wb > gs) gs = wb;
-            if (wsd > gs) gs = wsd;
-        }
-        if (gs >= 0.0 && gb - gs <= p.margin_tol * gb) st[1]++;
-        p.index_set[(size_t)b * m + t] = gi + 1;                              // 1-based (OMP.m:17)
-        int dup = -1;
-        for (int k = 0; k < nu; ++k) if (uniq_idx[k] == gi) dup = k;
-        if (dup >= 0) { sel[t] = dup; mult[dup]++; }
-        s_pick = gi; s_dup = dup;
     }
     __syncthreads();
     if (s_dup >= 0) return;                                                   // no new direction (see omp.cu)
@@ -766,6 +808,8 @@ static int run_omp_kron(Handle* h, int mem, int N, int M, int G, int P, int m, i
         q.state = a.take<int>((size_t)nb * (2 + 3 * m));
         q.cand_val = a.take<double>((size_t)nb * nchunk * 2);
         q.cand_idx = a.take<int>((size_t)nb * nchunk);
+        q.cand_idx2 = a.take<int>((size_t)nb * nchunk);
+        q.abmax = a.take<float>(nb);
         q.AH = a.take<cx<T>>(sharedA ? NG : NG * nb);
         if (use_tc) {
             q.Bt = a.take<float>((sharedB ? 1 : (size_t)nb) * 2 * PM);
