@@ -56,8 +56,14 @@ int jstsp_create(jstsp_handle** out, int device);
 void jstsp_destroy(jstsp_handle* h);
 const char* jstsp_last_error(const jstsp_handle* h);
 const char* jstsp_version(void);
-/* Use an existing cudaStream_t (passed as void*) instead of the handle's own stream. */
+/* Use an existing cudaStream_t (passed as void*) instead of the handle's own stream.  The handle owns ONE workspace: when the stream
+ * changes, the new stream is made to wait (event) for the work already queued on the old one, so calls issued under different streams
+ * are serialised rather than left to overwrite each other's state. */
 int jstsp_set_stream(jstsp_handle* h, void* cuda_stream);
+/* Number of trials of the last proposed_algorithm* / solver call whose output held a non-finite value (the reference's silent NaN
+ * propagation).  HOST-buffer calls return the same number themselves; DEVICE-buffer calls are asynchronous and
+ * return 0, so this function synchronises the handle's stream and reads the device counter.  < 0 on error. */
+long long jstsp_nonfinite_count(jstsp_handle* h);
 /* Block until everything enqueued on the handle's stream has finished. */
 int jstsp_synchronize(jstsp_handle* h);
 /* Number of kernel launches issued through this handle since creation. */
@@ -288,6 +294,29 @@ int jstsp_admm_parameters(jstsp_handle* h, int dtype, int mem, int N, int M, int
  * scale and rate are doubles in `mem` space. */
 int jstsp_log2det_rate(jstsp_handle* h, int dtype, int mem, int n, int m, int batch,
                        const void* X, long long ld_X, const double* scale, double* rate);
+
+/* Spectral efficiency of one receiver design of the capacity / energy-efficiency sweeps:
+ *   rate[b] = real(log2(det(eye(Mr) + scale[b] * Wsel' * (Y*Y') * Wsel))),  Wsel = W(:, cols(1:Mr))
+ * replaces plot_capacity.m:47,52,57,64 and plot_ee.m:47,52,57,64 (scale = 1/square_noise_variance * 1/Nt).  Y is the noiseless received
+ * block Nr x T (4th output of hbf.m:1 / 5th of proposed_hbf.m:1), W the Nr x Wc combiner, cols the 1-based column choice of the design
+ * (ind(1:Mr) of ind = randperm(Mr_e), plot_capacity.m:63), Mr entries per trial (ld_cols = 0: shared); NULL = the first Mr columns
+ * (W_c = W(:, 1:Lr), hbf.m:24).  Mr <= 64. */
+int jstsp_capacity(jstsp_handle* h, int dtype, int mem, int Nr, int T, int Wc, int Mr, int batch,
+                   const void* Y, long long ld_Y, const void* W, long long ld_W, const int* cols, long long ld_cols,
+                   const double* scale, double* rate);
+
+/* Power consumption of the four receiver designs of plot_ee.m:69-77 (Pcirc = 0, Psw = 5 mW, Pps = 15 mW, Plna = 20 mW, Pps_zc = 60 mW):
+ * power4 = { digital beamforming, conventional HBF with phase shifters, conventional HBF with ZC, proposed }.  Energy efficiency is
+ * mean(rate) / power (plot_ee.m:84-87).  Host arithmetic, no handle. */
+int jstsp_power_model(int Nr, int Mr, int Mr_e, double* power4);
+
+/* Least-squares baseline of the drivers, batched:  S = pinv(A) * Y * pinv(B)   (plot_errorVSsnr.m:83, plot_errorVSsnr_approx.m:61,67)
+ * and / or  YpinvB = Y * pinv(B)  (the right-hand sides handed to the joint OMP, plot_errorVSsnr.m:117).
+ * A N x G, B P x M, Y N x M, S G x P, YpinvB N x P; either output may be NULL (A may be NULL when S is).  Full-rank operands: pinv is
+ * formed through the Gram matrix of the short side (no singular-value truncation).  Returns the number of trials with a non-finite S. */
+int jstsp_ls_estimate(jstsp_handle* h, int dtype, int mem, int N, int M, int G, int P, int batch,
+                      const void* A, long long ld_A, const void* B, long long ld_B, const void* Y, long long ld_Y,
+                      void* S, long long ld_S, void* YpinvB, long long ld_YpinvB);
 
 #ifdef __cplusplus
 }

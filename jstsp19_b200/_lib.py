@@ -68,6 +68,11 @@ def _load():
     lib.jstsp_proposed_algorithm_pilots.argtypes = [vp, C.POINTER(AdmmDesc), i, i, vp, vp, vp, vp, vp, ll, vp, ll, i, i, vp, vp, vp, vp, vp, vp]
     lib.jstsp_last_path.argtypes = [vp]
     lib.jstsp_last_variant.argtypes = [vp]
+    lib.jstsp_nonfinite_count.argtypes = [vp]
+    lib.jstsp_nonfinite_count.restype = ll
+    lib.jstsp_ls_estimate.argtypes = [vp, i, i, i, i, i, i, i, vp, ll, vp, ll, vp, ll, vp, ll, vp, ll]
+    lib.jstsp_capacity.argtypes = [vp, i, i, i, i, i, i, i, vp, ll, vp, ll, vp, ll, vp, vp]
+    lib.jstsp_power_model.argtypes = [i, i, i, vp]
     lib.jstsp_svt.argtypes = [vp, i, i, i, i, i, vp, ll, vp, vp, ll]
     lib.jstsp_mc_svt.argtypes = [vp, i, i, i, i, i, i, vp, ll, vp, ll, vp, vp, vp, ll]
     lib.jstsp_omp.argtypes = [vp, i, i, i, i, i, i, vp, ll, vp, ll, vp, ll, vp, vp, vp, C.c_double]
@@ -92,7 +97,7 @@ lib = _load()
 EXPORTED = [
     "jstsp_create", "jstsp_destroy", "jstsp_last_error", "jstsp_version", "jstsp_set_stream",
     "jstsp_synchronize", "jstsp_launch_count", "jstsp_set_chunk", "jstsp_profile", "jstsp_profile_read", "jstsp_debug_buffer",
-    "jstsp_proposed_algorithm", "jstsp_proposed_algorithm_angles", "jstsp_proposed_algorithm_psi", "jstsp_proposed_algorithm_pilots", "jstsp_last_path", "jstsp_last_variant",
+    "jstsp_proposed_algorithm", "jstsp_proposed_algorithm_angles", "jstsp_proposed_algorithm_psi", "jstsp_proposed_algorithm_pilots", "jstsp_last_path", "jstsp_last_variant", "jstsp_nonfinite_count", "jstsp_ls_estimate", "jstsp_capacity", "jstsp_power_model",
     "jstsp_svt", "jstsp_mc_svt", "jstsp_mc_admm", "jstsp_omp", "jstsp_omp_kron", "jstsp_somp", "jstsp_sparse_admm", "jstsp_vamp",
     "jstsp_wideband_mmwave_channel", "jstsp_measure", "jstsp_create_beamformer", "jstsp_qam4mod", "jstsp_nmse", "jstsp_admm_parameters", "jstsp_log2det_rate",
 ]
@@ -141,6 +146,10 @@ class Handle:
             out[name.value.decode()] = (ms.value, n.value)
             slot += 1
         return out
+
+    def nonfinite_count(self) -> int:
+        """Trials of the last solver call with a non-finite output (synchronises the stream; for DEVICE-buffer calls, which return 0)."""
+        return int(lib.jstsp_nonfinite_count(self._h))
 
     @property
     def last_variant(self) -> int:

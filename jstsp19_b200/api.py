@@ -100,8 +100,10 @@ def _admm(subY, Omega, indx_S, A, B, Imax, tau_Y, tau_S, rho, type_, precision, 
     dp = lambda a: a.ctypes.data_as(C.c_void_p)
     ix = None
     if indx_S is not None:
-        ix = np.ascontiguousarray(np.asarray(indx_S).reshape(batch, -1) if np.asarray(indx_S).ndim > 1
-                                  else np.asarray(indx_S).reshape(1, -1), dtype=np.int32)
+        ixa = np.asarray(indx_S)
+        # per-trial rankings only when the leading dimension is the batch and it is not MATLAB's (n, 1) column; anything else is one shared ranking
+        per_trial = ixa.ndim == 2 and batch > 1 and ixa.shape[0] == batch and ixa.shape[1] != 1
+        ix = np.ascontiguousarray(ixa.reshape(batch, -1) if per_trial else ixa.reshape(1, -1), dtype=np.int32)
         d.n_indx = ix.shape[1]
         d.ld_indx = ix.shape[1] if ix.shape[0] == batch and batch > 1 else 0
     if psi is not None and pilots_L is not None:
@@ -361,7 +363,7 @@ def sparse_admm(Htrue, OH, Dr, Dt, Imax, *, precision="f64", handle=None, nargou
     S = np.empty((batch, Mt, Mr), dtype=cd)
     conv = np.empty((batch, int(Imax)), dtype=rd) if Ht is not None else None
     h.check(_lib.lib.jstsp_sparse_admm(h.ptr, _DT[precision], _lib.HOST, Mr, Mt, batch, int(Imax),
-                                       _ptr(Ht), Mr * Mt, _ptr(Om), Mr * Mt, _ptr(Drm), Mr * Mr if Drm.ndim == 3 else 0,
+                                       _ptr(Ht), (Mr * Mt if Ht.ndim == 3 else 0) if Ht is not None else 0, _ptr(Om), Mr * Mt, _ptr(Drm), Mr * Mr if Drm.ndim == 3 else 0,
                                        _ptr(Dtm), Mt * Mt if Dtm.ndim == 3 else 0, _ptr(S), Mr * Mt, _ptr(conv), int(Imax)))
     S = np.swapaxes(S, -1, -2)
     if bs is None:
@@ -552,3 +554,65 @@ def log2det_rate(X, scale, *, precision="f64", handle=None):
     out = np.empty(batch, dtype=np.float64)
     h.check(_lib.lib.jstsp_log2det_rate(h.ptr, _DT[precision], _lib.HOST, n, m, batch, _ptr(Xm), n * m, _ptr(sc), _ptr(out)))
     return float(out[0]) if bs is None else out
+
+
+def ls_estimate(A, Y, B, *, precision="f64", handle=None, want_YpinvB=False):
+    """S_ls = pinv(A)*Y*pinv(B), the least-squares baseline of plot_errorVSsnr.m:83 and plot_errorVSsnr_approx.m:61,67; with
+    ``want_YpinvB`` also Y*pinv(B), the right-hand sides the drivers hand to the joint OMP (plot_errorVSsnr.m:117).
+    A (N x G) and B (P x M) may be shared or per trial; Y is (N x M) or (batch x N x M)."""
+    h = handle or default_handle()
+    cd = _CD[precision]
+    bs = _batch_of(Y, 2)
+    batch = 1 if bs is None else bs
+    Am, Bm, Ym = _cm(A, cd), _cm(B, cd), _cm(Y, cd)
+    N, G = Am.shape[-1], Am.shape[-2]
+    P, M = Bm.shape[-1], Bm.shape[-2]
+    if Ym.shape[-1] != N or Ym.shape[-2] != M:
+        raise ValueError("Y must be N x M with A N x G and B P x M")
+    S = np.empty((batch, P, G), dtype=cd)
+    YpB = np.empty((batch, P, N), dtype=cd) if want_YpinvB else None
+    rc = _lib.lib.jstsp_ls_estimate(h.ptr, _DT[precision], _lib.HOST, N, M, G, P, batch, _ptr(Am), N * G if Am.ndim == 3 else 0,
+                                    _ptr(Bm), P * M if Bm.ndim == 3 else 0, _ptr(Ym), N * M, _ptr(S), G * P, _ptr(YpB), N * P)
+    h.check(rc)
+    S = np.swapaxes(S, -1, -2)
+    out = S[0] if bs is None else S
+    if want_YpinvB:
+        YpB = np.swapaxes(YpB, -1, -2)
+        return out, (YpB[0] if bs is None else YpB)
+    return out
+
+
+def capacity(Y, W, Mr, scale, cols=None, *, precision="f64", handle=None):
+    """real(log2(det(eye(Mr) + scale*Wsel'*(Y*Y')*Wsel))) with Wsel = W(:, cols(1:Mr)) - one receiver design of plot_capacity.m:47-64 /
+    plot_ee.m:47-64 (scale = 1/square_noise_variance*1/Nt).  ``cols`` are 1-based (ind = randperm(Mr_e), plot_capacity.m:63);
+    None keeps the first Mr columns (W_c = W(:, 1:Lr), hbf.m:24).  Y is the noiseless block (Nr x T) or a batch of them."""
+    h = handle or default_handle()
+    cd = _CD[precision]
+    bs = _batch_of(Y, 2)
+    batch = 1 if bs is None else bs
+    Ym, Wm = _cm(Y, cd), _cm(W, cd)
+    Nr, T = Ym.shape[-1], Ym.shape[-2]
+    Wc = Wm.shape[-2]
+    sc = _per_trial(scale, batch)
+    out = np.empty(batch, dtype=np.float64)
+    ci, ldc = None, 0
+    if cols is not None:
+        ci = np.ascontiguousarray(np.asarray(cols)[..., :Mr], dtype=np.int32)
+        ldc = Mr if ci.ndim == 2 else 0
+    h.check(_lib.lib.jstsp_capacity(h.ptr, _DT[precision], _lib.HOST, Nr, T, Wc, int(Mr), batch, _ptr(Ym), Nr * T, _ptr(Wm), Nr * Wc if Wm.ndim == 3 else 0,
+                                    _ptr(ci), ldc, _ptr(sc), _ptr(out)))
+    return float(out[0]) if bs is None else out
+
+
+def power_model(Nr, Mr, Mr_e):
+    """(power_dbf, power_hbf, power_hbf_zc, power_proposed) of plot_ee.m:69-77."""
+    out = np.empty(4, dtype=np.float64)
+    if _lib.lib.jstsp_power_model(int(Nr), int(Mr), int(Mr_e), _ptr(out)) != 0:
+        raise ValueError("power_model: bad argument")
+    return tuple(float(v) for v in out)
+
+
+def energy_efficiency(mean_capacity4, Nr, Mr, Mr_e):
+    """ee_dbf, ee_hbf_ps, ee_hbf_zc, ee_proposed = mean capacity / power of the design (plot_ee.m:84-87)."""
+    pw = power_model(Nr, Mr, Mr_e)
+    return tuple(float(c) / p for c, p in zip(mean_capacity4, pw))

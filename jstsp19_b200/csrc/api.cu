@@ -56,10 +56,27 @@ extern "C" const char* jstsp_last_error(const jstsp_handle* h) { return h ? h->e
 
 extern "C" int jstsp_set_stream(jstsp_handle* h, void* cuda_stream) {
     if (!h) return JSTSP_E_ARG;
+    cudaStream_t ns = static_cast<cudaStream_t>(cuda_stream);
+    if (ns == h->stream) return JSTSP_OK;
+    // The handle's workspace (ADMM state, Jacobi warm start, flags) is shared by every call: work queued on the old stream may still be
+    // using it, so the new stream waits for the old one before anything else is enqueued.
+    if (h->stream) {
+        if (cudaEventRecord(h->ev_fork, h->stream) == cudaSuccess) cudaStreamWaitEvent(ns, h->ev_fork, 0);
+        else cudaGetLastError();                  // the caller destroyed the old stream: its work has completed
+    }
     if (h->own_stream && h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
-    h->stream = static_cast<cudaStream_t>(cuda_stream);
+    h->stream = ns;
     h->own_stream = false;
     return JSTSP_OK;
+}
+
+extern "C" long long jstsp_nonfinite_count(jstsp_handle* h) {
+    if (!h || !h->d_flag) return -1;
+    int bad = 0;
+    if (cudaSetDevice(h->device) != cudaSuccess) return -1;
+    if (cudaMemcpyAsync(&bad, h->d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
+    return bad;
 }
 
 extern "C" int jstsp_synchronize(jstsp_handle* h) {

@@ -235,7 +235,9 @@ __global__ void __launch_bounds__(256) k_params(const cx<T>* Y, long long ld_Y, 
         double ev[64];
         for (int k = 0; k < N; ++k) ev[k] = sm.Are[k + N * k];
         for (int i = 0; i < N; ++i) for (int j = i + 1; j < N; ++j) if (ev[j] > ev[i]) { double t = ev[i]; ev[i] = ev[j]; ev[j] = t; }
-        const double lam = kth <= N ? ev[kth - 1] : 0.0;      // fewer than kth non-zero eigenvalues: eigs pads with zeros of Y'Y
+        // eigs works on the M x M matrix Y'Y: with fewer than kth eigenvalues it returns all min(N, M) non-trivial ones (plus exact zeros when M > N)
+        const int kk = kth <= (N < M ? N : M) ? kth : (M > N ? kth : (N < M ? N : M));
+        const double lam = kk <= N ? ev[kk - 1] : 0.0;
         tauY[b] = 1.0 / fy;
         rho[b] = sqrt(fmax(lam, 0.0) / fy);
     }
@@ -312,6 +314,7 @@ static int run_measure(Handle* h, int mem, const jstsp_meas_desc* d, const void*
     if (Nr <= 0 || Nt <= 0 || L <= 0 || TT <= 0 || Wc <= 0 || Wc > Nr || batch <= 0 || d->Lr < 0 || d->Lr > Wc) return fail(h, JSTSP_E_ARG, "bad dimension");
     if (!H || !Psi || !W) return fail(h, JSTSP_E_ARG, "NULL buffer");
     if (d->psi_mode == 0 && (d->Tp < TT || d->Tp < L)) return fail(h, JSTSP_E_ARG, "Psi_i must be at least T x T with T >= L");
+    if (d->psi_mode == 1 && L > TT) return fail(h, JSTSP_E_ARG, "more delay taps than training columns (the Toeplitz rows are built from T pilot symbols)");
     const bool host = mem == JSTSP_HOST;
     const size_t nH = (size_t)Nr * Nt * L, nN = (size_t)Nr * TT, nW = (size_t)Nr * Nr,
                  nPsi = d->psi_mode == 0 ? (size_t)d->Tp * d->Tp * Nt : (size_t)Nt * TT;
@@ -551,6 +554,63 @@ static int run_log2det(Handle* h, int mem, int n, int m, int batch, const void* 
     return JSTSP_OK;
 }
 
+// X = W(:, cols)' * Y  (Mr x T): the combiner columns a design keeps, applied to the noiseless received block
+//   hbf.m:24 (W_c = W(:, 1:Lr)), plot_capacity.m:63-64 / plot_ee.m:63-64 (W(:, ind(1:Mr)), ind = randperm(Mr_e))
+template <typename T>
+__global__ void __launch_bounds__(256) k_select_combine(const cx<T>* Y, long long ld_Y, const cx<T>* W, long long ld_W, const int* cols, long long ld_cols,
+                                                        int Nr, int T_, int Mr, cx<T>* X) {
+    const int b = blockIdx.x;
+    const cx<T>* y = Y + (long long)b * ld_Y; const cx<T>* w = W + (long long)b * ld_W;
+    const int* cs = cols ? cols + (long long)b * ld_cols : nullptr;
+    for (int e = threadIdx.x; e < Mr * T_; e += blockDim.x) {
+        const int r = e % Mr, t = e / Mr, c = cs ? cs[r] - 1 : r;                 // cols are 1-based like ind(1:Mr)
+        T re = 0, im = 0;
+        for (int n = 0; n < Nr; ++n) { const cx<T> a = w[n + (size_t)Nr * c], v = y[n + (size_t)Nr * t]; cmac<T>(re, im, a.re, -a.im, v.re, v.im); }
+        X[(size_t)b * Mr * T_ + e] = mk<T>(re, im);
+    }
+}
+
+template <typename T>
+static int run_capacity(Handle* h, int mem, int Nr, int T_, int Wc, int Mr, int batch, const void* Y, long long ld_Y, const void* W, long long ld_W,
+                        const int* cols, long long ld_cols, const double* scale, double* out) {
+    if (Nr <= 0 || T_ <= 0 || Mr <= 0 || Wc < Mr || batch <= 0 || !Y || !W || !scale || !out) return fail(h, JSTSP_E_ARG, "bad argument");
+    if (Mr > 64) return fail(h, JSTSP_E_UNSUPPORTED, "rate kernel covers <= 64 rows");
+    const bool host = mem == JSTSP_HOST;
+    const size_t NT = (size_t)Nr * T_, NW = (size_t)Nr * Wc, MT = (size_t)Mr * T_, esz = sizeof(cx<T>);
+    if (!ld_Y) ld_Y = NT;
+    const int nW = ld_W ? batch : 1;
+    if (cols && !ld_cols && batch > 1) ld_cols = 0;
+    int rc = ensure_workspace(h, esz * (MT * batch + (host ? NT * batch + NW * nW : 0)) + (host ? sizeof(int) * (size_t)Mr * batch + 2 * sizeof(double) * batch : 0) + 8192); if (rc) return rc;
+    Arena ar(h->ws, h->ws_bytes);
+    cx<T>* X = ar.take<cx<T>>(MT * batch);
+    const cx<T>* dY = (const cx<T>*)Y; const cx<T>* dW = (const cx<T>*)W; const int* dc = cols; const double* ds = scale; double* dout = out;
+    if (host) {
+        cx<T>* a = ar.take<cx<T>>(NT * batch); cx<T>* w = ar.take<cx<T>>(NW * nW);
+        JSTSP_CUDA(h, cudaMemcpy2DAsync(a, NT * esz, Y, (size_t)ld_Y * esz, NT * esz, batch, cudaMemcpyHostToDevice, h->stream));
+        JSTSP_CUDA(h, cudaMemcpy2DAsync(w, NW * esz, W, (size_t)(ld_W ? ld_W : NW) * esz, NW * esz, nW, cudaMemcpyHostToDevice, h->stream));
+        dY = a; ld_Y = NT; dW = w; if (ld_W) ld_W = NW;
+        if (cols) {
+            const int nc = ld_cols ? batch : 1;
+            int* c2 = ar.take<int>((size_t)Mr * nc);
+            JSTSP_CUDA(h, cudaMemcpy2DAsync(c2, sizeof(int) * Mr, cols, sizeof(int) * (size_t)(ld_cols ? ld_cols : Mr), sizeof(int) * Mr, nc, cudaMemcpyHostToDevice, h->stream));
+            dc = c2; if (ld_cols) ld_cols = Mr;
+        }
+        double* s2 = ar.take<double>(batch); double* o2 = ar.take<double>(batch);
+        JSTSP_CUDA(h, cudaMemcpyAsync(s2, scale, sizeof(double) * batch, cudaMemcpyHostToDevice, h->stream));
+        ds = s2; dout = o2;
+    }
+    JSTSP_LAUNCH(h, PK_OTHER, (k_select_combine<T><<<batch, 256, 0, h->stream>>>(dY, ld_Y, dW, ld_W, dc, ld_cols, Nr, T_, Mr, X)));
+    const size_t smem = JacobiSmem::bytes(Mr);
+    rc = set_smem(h, k_log2det<T>, smem); if (rc) return rc;
+    JSTSP_LAUNCH(h, PK_OTHER, (k_log2det<T><<<batch, 256, smem, h->stream>>>(X, (long long)MT, Mr, T_, ds, dout)));
+    JSTSP_CUDA(h, cudaGetLastError());
+    if (host) {
+        JSTSP_CUDA(h, cudaMemcpyAsync(out, dout, sizeof(double) * batch, cudaMemcpyDeviceToHost, h->stream));
+        JSTSP_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    return JSTSP_OK;
+}
+
 }  // namespace jstsp
 using namespace jstsp;
 extern "C" int jstsp_log2det_rate(jstsp_handle* h, int dtype, int mem, int n, int m, int batch,
@@ -559,6 +619,16 @@ extern "C" int jstsp_log2det_rate(jstsp_handle* h, int dtype, int mem, int n, in
     JSTSP_CUDA(h, cudaSetDevice(h->device));
     if (dtype == JSTSP_F32) return run_log2det<float>(h, mem, n, m, batch, X, ld_X, scale, rate);
     if (dtype == JSTSP_F64) return run_log2det<double>(h, mem, n, m, batch, X, ld_X, scale, rate);
+    return fail(h, JSTSP_E_ARG, "unknown dtype");
+}
+
+extern "C" int jstsp_capacity(jstsp_handle* h, int dtype, int mem, int Nr, int T, int Wc, int Mr, int batch,
+                              const void* Y, long long ld_Y, const void* W, long long ld_W, const int* cols, long long ld_cols,
+                              const double* scale, double* rate) {
+    if (!h) return JSTSP_E_ARG;
+    JSTSP_CUDA(h, cudaSetDevice(h->device));
+    if (dtype == JSTSP_F32) return run_capacity<float>(h, mem, Nr, T, Wc, Mr, batch, Y, ld_Y, W, ld_W, cols, ld_cols, scale, rate);
+    if (dtype == JSTSP_F64) return run_capacity<double>(h, mem, Nr, T, Wc, Mr, batch, Y, ld_Y, W, ld_W, cols, ld_cols, scale, rate);
     return fail(h, JSTSP_E_ARG, "unknown dtype");
 }
 

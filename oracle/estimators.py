@@ -456,3 +456,31 @@ def log2det_rate(X, scale):
     X = np.asarray(X, dtype=np.complex128)
     n = X.shape[0]
     return float(np.real(np.log2(np.linalg.det(np.eye(n) + scale * (X @ X.conj().T)))))
+
+
+def ls_estimate(A, Y, B):
+    """S_ls = pinv(A)*Y*pinv(B)  (plot_errorVSsnr.m:83; plot_errorVSsnr_approx.m:61,67 with Y = the estimator's second output)."""
+    return np.linalg.pinv(np.asarray(A, complex)) @ np.asarray(Y, complex) @ np.linalg.pinv(np.asarray(B, complex))
+
+
+def y_pinv_b(Y, B):
+    """Y_hbf_nr*pinv(B): the right-hand sides of the joint OMP call (plot_errorVSsnr.m:117)."""
+    return np.asarray(Y, complex) @ np.linalg.pinv(np.asarray(B, complex))
+
+
+def capacity_literal(Y, W, cols, scale):
+    """real(log2(det(eye(Mr) + scale*W(:,cols)'*(Y*Y')*W(:,cols))))  (plot_capacity.m:47,52,57,64; plot_ee.m:47,52,57,64).
+    ``cols`` 1-based, like ind(1:Mr) of ind = randperm(Mr_e) (plot_capacity.m:63) or 1:Lr (hbf.m:24)."""
+    Y = np.asarray(Y, complex); W = np.asarray(W, complex)
+    Ws = W[:, np.asarray(cols, int) - 1]
+    Mr = Ws.shape[1]
+    return float(np.real(np.log2(np.linalg.det(np.eye(Mr) + scale * (Ws.conj().T @ (Y @ Y.conj().T) @ Ws)))))
+
+
+def ee_power_model(Nr, Mr, Mr_e):
+    """power_dbf, power_hbf, power_hbf_zc, power_proposed  (plot_ee.m:69-77)."""
+    Pcirc, Psw, Pps, Plna, Pps_zc = 0, 0.005, 0.015, 0.02, 0.06                  # plot_ee.m:69-73
+    return (Pcirc + Nr * Nr * Plna + Nr * (Nr + 1) * Pps_zc,                       # :74
+            Pcirc + Mr * Nr * Plna + Nr * (Mr + 1) * Pps,                          # :75
+            Pcirc + Mr * Nr * Plna + Nr * (Mr + 1) * Pps_zc,                       # :76
+            Pcirc + Mr_e * Nr * Plna + Mr_e * Psw + Nr * (Mr_e + 1) * Pps)         # :77
