@@ -645,7 +645,7 @@ static bool tc_enabled() {
     return e ? atoi(e) != 0 : false;
 }
 // structured dictionary B = (I (x) Dt') Psi_bar of jstsp_proposed_algorithm_psi (host-level description)
-struct PsiArgs { const void* Dt; long long ld_Dt; const void* Psi; long long ld_Psi; int Nt, Gt, L; int pilots; };   // pilots: Psi holds the sequences s_k (Nt x M), Psi_bar is expanded on the device
+struct PsiArgs { const void* Dt; long long ld_Dt; const void* Psi; long long ld_Psi; int Nt, Gt, L; int pilots; int recovered; };   // recovered: no factors were given, Psi_bar is recovered on the device from the dense B (k_recover_psi)   // pilots: Psi holds the sequences s_k (Nt x M), Psi_bar is expanded on the device
 // Psi_bar(k, j, l) = row l of toeplitz(s_k) at column j (proposed_hbf.m:15-18, plot_errorVSsnr.m:63-67): s_k(j - l) for j >= l, conj(s_k(l - j)) below the diagonal
 template <typename T>
 __global__ void __launch_bounds__(256) k_expand_pilots(const cx<T>* __restrict__ pil, long long ld_pil, cx<T>* __restrict__ psi, long long ld_psi, int Nt, int M, int L) {
@@ -672,14 +672,26 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
                     void* S_, void* Y_, void* conv_, bool angles, const PsiArgs* ps = nullptr) {
     constexpr int CB = DT<T>::CB, KB = DT<T>::KB;
     const int N = d->N, M = d->M, G = d->G, P = d->P, batch = d->batch, imax = d->imax;
+    // The reference function's own argument list carries only the dense B (proposed_algorithm.m:1).  When the shape admits the Psi-domain
+    // kernels, Psi_bar = Dt B_l is recovered on the device and checked there for the structure the drivers give B (plot_errorVSsnr.m:133-136:
+    // Toeplitz 4-QAM pilots behind the unitary 64-point DFT grid); only if the check passes does the structured path run.
+    PsiArgs rec{};
+    bool recovered = false;
+    if constexpr (std::is_same<T, float>::value) {
+        if (!ps && B_ && d->type == JSTSP_APPROXIMATE && !conv_ && N == psi::N && G <= psi::N && M % tc::MC == 0 && P % psi::NT == 0 && P / psi::NT >= 1 &&
+            P / psi::NT <= psi::MAXL && P / psi::NT <= M && getenv("JSTSP_NO_RECOVER") == nullptr) {
+            rec = PsiArgs{nullptr, 0, nullptr, d->ld_B ? (long long)psi::NT * M * (P / psi::NT) : 0, psi::NT, psi::NT, P / psi::NT, 0, 1};
+            ps = &rec; recovered = true;
+        }
+    }
     if (N <= 0 || M <= 0 || G <= 0 || P <= 0 || batch <= 0 || imax < 0) return fail(h, JSTSP_E_ARG, "non-positive dimension");
     if (!subY_ || !omega_ || !A_ || (!B_ && !ps) || !tauY_ || !tauS_ || !rho_ || !S_) return fail(h, JSTSP_E_ARG, "NULL buffer");
-    if (ps) {
+    if (ps && !recovered) {
         if (!ps->Dt || !ps->Psi) return fail(h, JSTSP_E_ARG, "NULL buffer");
         if (ps->Nt <= 0 || ps->Gt <= 0 || ps->L <= 0 || ps->L * ps->Gt != P) return fail(h, JSTSP_E_ARG, "structured dictionary: P must equal L * Gt");
     }
     // B is built on the device from (Dt, Psi_bar): one dictionary per trial unless both factors are shared
-    const long long ldB_in = ps ? ((ps->ld_Psi || ps->ld_Dt) ? (long long)P * M : 0) : d->ld_B;
+    const long long ldB_in = (ps && !recovered) ? ((ps->ld_Psi || ps->ld_Dt) ? (long long)P * M : 0) : d->ld_B;
     if (angles && (!indx_ || d->n_indx <= 0)) return fail(h, JSTSP_E_ARG, "indx_S missing");
     if (N > 64 || G > 64) return fail(h, JSTSP_E_UNSUPPORTED, "proposed_algorithm kernels cover N <= 64 and G <= 64 rows");
     const bool approx = d->type == JSTSP_APPROXIMATE;
@@ -701,7 +713,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
     const int eig_threads = getenv("JSTSP_EIG_THREADS") ? atoi(getenv("JSTSP_EIG_THREADS")) : (N <= 16 ? 32 : 128);
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
     const bool segP = (P * esz0) % 16 == 0, segM = (M * esz0) % 16 == 0;
-    const bool b_ok = host || ps || (al16(B_) && ((size_t)d->ld_B * esz0) % 16 == 0);
+    const bool b_ok = host || (ps && !recovered) || (al16(B_) && ((size_t)d->ld_B * esz0) % 16 == 0);
     const bool rows8 = (N % 8 == 0) && (G % 8 == 0);
     const bool io_ok = host || (al16(subY_) && al16(omega_) && ((size_t)d->ld_subY * esz0) % 16 == 0 && ((size_t)d->ld_omega * sizeof(T)) % 16 == 0);
     const bool fast_v = approx && !no_fast && rows8 && segP && b_ok && io_ok && P <= cta_width(p.GNG) && P <= cta_width(p.NG) &&
@@ -720,7 +732,8 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
     if constexpr (std::is_same<T, float>::value) {
         psi_shape = ps && fast_v && !want_conv && N == psi::N && M % tc::MC == 0 && ps->Nt == psi::NT && ps->Gt <= psi::NT && ps->L <= psi::MAXL && G <= psi::N &&
                     psi_fast_enabled() && psi::SMEM <= h->smem_optin && tc::encode_fn() != nullptr &&
-                    (host || (al16(ps->Psi) && al16(ps->Dt)));
+                    (host || recovered || (al16(ps->Psi) && al16(ps->Dt)));
+        if (recovered && !psi_shape) { ps = nullptr; recovered = false; }      // plain dense call
         if (ps) use_tc = false;
     }
     // chunk geometry
@@ -748,6 +761,8 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
     psi::In pin{};                       // structured entry: device-side description (fp32 fast path)
     const cx<T> *psi_dev = nullptr, *dt_dev = nullptr, *pil_dev = nullptr;
     cx<T>* psi_exp = nullptr;            // pilots entry with DEVICE buffers: the expanded Psi_bar
+    cx<T>* psi_rec = nullptr;            // dense entry: Psi_bar recovered from B
+    cx<T>* dt_gen = nullptr;             // dense entry: the unitary 64-point DFT grid
     float* asop_ws = nullptr;            // tensor-core path: A S expanded into the pass-1 operand image (hi | lo)
     const int Wn = cta_width(p.NG);
     const long long Mpad = (long long)ceil_div(M, Wn) * Wn;      // B^T is stored in Wn-wide column tiles
@@ -771,7 +786,8 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
         }
         if (fast_xs && !use_tc) bt_ws = a.take<cx<T>>((size_t)P * Mpad * (sharedB ? 1 : nb));    // (unused once the structured path is confirmed)
         if (ps) {
-            b_ws = a.take<cx<T>>((size_t)P * M * (sharedB ? 1 : nb));
+            if (!recovered) b_ws = a.take<cx<T>>((size_t)P * M * (sharedB ? 1 : nb));
+            if (recovered) { psi_rec = a.take<cx<T>>((size_t)ps->Nt * M * ps->L * (ps->ld_Psi ? nb : 1)); dt_gen = a.take<cx<T>>((size_t)ps->Nt * ps->Gt); }
             if (ps->pilots && !host) psi_exp = a.take<cx<T>>((size_t)ps->Nt * M * ps->L * (ps->ld_Psi ? nb : 1));
             if (psi_shape) {
                 const int nE = ps->ld_Psi ? nb : 1;
@@ -802,9 +818,10 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
                 const cx<T>* s_subY = a.take<cx<T>>(d->ld_subY ? NM * nb : NM);
                 const T* s_omega = a.take<T>(d->ld_omega ? NM * nb : NM);
                 const cx<T>* s_A = a.take<cx<T>>((size_t)N * G * (d->ld_A ? nb : 1));
-                const cx<T>* s_B = ps ? nullptr : a.take<cx<T>>((size_t)P * M * (d->ld_B ? nb : 1));
-                const cx<T>* s_Psi = ps ? a.take<cx<T>>((size_t)ps->Nt * M * ps->L * (ps->ld_Psi ? nb : 1)) : nullptr;
-                const cx<T>* s_Dt = ps ? a.take<cx<T>>((size_t)ps->Nt * ps->Gt * (ps->ld_Dt ? nb : 1)) : nullptr;
+                const bool fac = ps && !recovered;          // the factors travel
+                const cx<T>* s_B = fac ? nullptr : a.take<cx<T>>((size_t)P * M * (d->ld_B ? nb : 1));
+                const cx<T>* s_Psi = fac ? a.take<cx<T>>((size_t)ps->Nt * M * ps->L * (ps->ld_Psi ? nb : 1)) : nullptr;
+                const cx<T>* s_Dt = fac ? a.take<cx<T>>((size_t)ps->Nt * ps->Gt * (ps->ld_Dt ? nb : 1)) : nullptr;
                 const cx<T>* s_Pil = (ps && ps->pilots) ? a.take<cx<T>>((size_t)ps->Nt * M * (ps->ld_Psi ? nb : 1)) : nullptr;
                 const double *s_rho = a.take<double>(nb), *s_tauY = a.take<double>(nb), *s_tauS = a.take<double>(nb);
                 const int* s_indx = angles ? a.take<int>((size_t)d->n_indx * (d->ld_indx ? nb : 1)) : nullptr;
@@ -889,7 +906,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
             JSTSP_CUDA(h, up(q.subY, subY_, NM, d->ld_subY, esz));
             JSTSP_CUDA(h, up(q.omega, omega_, NM, d->ld_omega, sizeof(T)));
             JSTSP_CUDA(h, up(q.A, A_, (size_t)N * G, d->ld_A, esz));
-            if (!ps) JSTSP_CUDA(h, up(q.B, B_, (size_t)P * M, d->ld_B, esz));
+            if (!ps || recovered) JSTSP_CUDA(h, up(q.B, B_, (size_t)P * M, d->ld_B, esz));
             else {
                 if (ps->pilots) {   // the sequences travel (Nt x M per trial, L times fewer bytes); Psi_bar is expanded on the device, on the copy stream
                     JSTSP_CUDA(h, up(pil_dev, ps->Psi, (size_t)ps->Nt * M, ps->ld_Psi, esz));
@@ -916,7 +933,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
             q.subY = (const cx<T>*)subY_ + (long long)b0 * d->ld_subY;
             q.omega = (const T*)omega_ + (long long)b0 * d->ld_omega;
             q.A = (const cx<T>*)A_ + (long long)b0 * d->ld_A;
-            if (!ps) q.B = (const cx<T>*)B_ + (long long)b0 * d->ld_B;
+            if (!ps || recovered) q.B = (const cx<T>*)B_ + (long long)b0 * d->ld_B;
             q.rho = rho_ + b0; q.tauY = tauY_ + b0; q.tauS = tauS_ + b0;
             if (angles) q.indx = indx_ + (long long)b0 * d->ld_indx;
             q.Yout = Y_ ? (cx<T>*)Y_ + (long long)b0 * d->ld_Y : nullptr;
@@ -924,17 +941,25 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
         bool use_psi = false;
         psi::Maps pmaps;
         if (ps) {
-            const long long ldP = ps->ld_Psi ? ((host || ps->pilots) ? (long long)ps->Nt * M * ps->L : ps->ld_Psi) : 0, ldD = ps->ld_Dt ? (host ? (long long)ps->Nt * ps->Gt : ps->ld_Dt) : 0;
+            const long long ldP = ps->ld_Psi ? ((host || ps->pilots || recovered) ? (long long)ps->Nt * M * ps->L : ps->ld_Psi) : 0, ldD = ps->ld_Dt ? (host ? (long long)ps->Nt * ps->Gt : ps->ld_Dt) : 0;
+            if constexpr (std::is_same<T, float>::value) {
+                if (recovered) {
+                    JSTSP_LAUNCH(h, PK_SETUP, (psi::k_make_dft64<<<1, 256, 0, st>>>(dt_gen)));
+                    dim3 g(ceil_div(M, 64), ps->L, ps->ld_Psi ? nb : 1);
+                    JSTSP_LAUNCH(h, PK_SETUP, (psi::k_recover_psi<<<g, 256, 0, st>>>(q.B, q.ld_B, psi_rec, ldP, ps->L, M)));
+                }
+            }
             if (ps->pilots && !host) {
                 dim3 g(4 * h->sm_count, ps->ld_Psi ? nb : 1);
                 JSTSP_LAUNCH(h, PK_SETUP, (k_expand_pilots<T><<<g, 256, 0, st>>>((const cx<T>*)ps->Psi + (long long)b0 * ps->ld_Psi, ps->ld_Psi, psi_exp, ldP, ps->Nt, M, ps->L)));
             }
-            const cx<T>* Pd = host ? psi_dev : (ps->pilots ? psi_exp : (const cx<T>*)ps->Psi + (long long)b0 * ps->ld_Psi);
-            const cx<T>* Dd = host ? dt_dev : (const cx<T>*)ps->Dt + (long long)b0 * ps->ld_Dt;
+            const cx<T>* Pd = recovered ? psi_rec : host ? psi_dev : (ps->pilots ? psi_exp : (const cx<T>*)ps->Psi + (long long)b0 * ps->ld_Psi);
+            const cx<T>* Dd = recovered ? dt_gen : host ? dt_dev : (const cx<T>*)ps->Dt + (long long)b0 * ps->ld_Dt;
             if constexpr (std::is_same<T, float>::value) {
                 if (psi_shape) {
                     // pack the pilots (bf16 image) and the mask (bits) and check their structure on the device
                     pin.Psi = Pd; pin.ld_Psi = ldP; pin.Dt = Dd; pin.ld_Dt = ldD; pin.Nt = ps->Nt; pin.Gt = ps->Gt; pin.L = ps->L;
+                    pin.snap_tol = recovered ? 2e-5f : 0.f;      // recovered pilots carry the fp32 rounding of B = Dt' Psi and of Dt B_l (~1e-6 of the scale)
                     const int nE = ps->ld_Psi ? nb : 1;
                     JSTSP_CUDA(h, cudaMemsetAsync(pin.bad, 0, 2 * sizeof(int), st));
                     { dim3 g(ceil_div(M + 8, 16), nE); JSTSP_LAUNCH(h, PK_SETUP, (psi::k_pack_psi<<<g, 256, 0, st>>>(pin, M))); }
@@ -945,6 +970,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
                     int bad_h[2] = {0, 0};
                     JSTSP_CUDA(h, cudaMemcpyAsync(bad_h, pin.bad, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
                     JSTSP_CUDA(h, cudaStreamSynchronize(st));
+                    if (getenv("JSTSP_DEBUG_RECOVER")) fprintf(stderr, "[jstsp] structure check: recovered=%d bad=%d dft_bad=%d nE=%d ldP=%lld\n", (int)recovered, bad_h[0], bad_h[1], nE, (long long)ldP);
                     pin.t1_red = getenv("JSTSP_PSI_T1RED") ? atoi(getenv("JSTSP_PSI_T1RED")) : 0;
                     pin.dft = dft_shape && bad_h[1] == 0;      // unitary DFT grid: the Dt rotations run as FFTs
                     use_psi = bad_h[0] == 0;       // otherwise: no Toeplitz / bf16-exact pilots or a non-binary mask -> dense kernels on the materialised B
@@ -958,7 +984,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
                     h->last_path = use_psi ? 2 : 1;
                 }
             }
-            if (!use_psi) {
+            if (!use_psi && !recovered) {
                 // dense dictionary from its factors, operand of the dense kernels
                 const int nBd = ldB_in ? nb : 1;
                 const size_t smb = sizeof(cx<T>) * ((size_t)ps->Nt * ps->Gt + (size_t)ps->Nt * 64);
@@ -1138,6 +1164,7 @@ extern "C" int jstsp_proposed_algorithm(jstsp_handle* h, const jstsp_admm_desc* 
     if (!h) return JSTSP_E_ARG;
     if (!d) return fail(h, JSTSP_E_ARG, "NULL descriptor");
     JSTSP_CUDA(h, cudaSetDevice(h->device));
+    h->last_path = 1; h->last_variant = 0;
     if (dtype == JSTSP_F32) return run_admm<float>(h, d, mem, subY, omega, nullptr, A, B, tau_Y, tau_S, rho, S, Y, conv, false);
     if (dtype == JSTSP_F64) return run_admm<double>(h, d, mem, subY, omega, nullptr, A, B, tau_Y, tau_S, rho, S, Y, conv, false);
     return fail(h, JSTSP_E_ARG, "unknown dtype");
@@ -1151,6 +1178,7 @@ extern "C" int jstsp_proposed_algorithm_angles(jstsp_handle* h, const jstsp_admm
     if (!h) return JSTSP_E_ARG;
     if (!d) return fail(h, JSTSP_E_ARG, "NULL descriptor");
     JSTSP_CUDA(h, cudaSetDevice(h->device));
+    h->last_path = 1; h->last_variant = 0;
     if (dtype == JSTSP_F32) return run_admm<float>(h, d, mem, subY, omega, indx_S, A, B, tau_Y, tau_S, rho, S, Y, conv, true);
     if (dtype == JSTSP_F64) return run_admm<double>(h, d, mem, subY, omega, indx_S, A, B, tau_Y, tau_S, rho, S, Y, conv, true);
     return fail(h, JSTSP_E_ARG, "unknown dtype");

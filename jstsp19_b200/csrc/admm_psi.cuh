@@ -124,6 +124,8 @@ struct In {                      // the structured dictionary of one pass (devic
     double* gg;                  // [b][nmc] |G(:,chunk)|^2
     int* bad;                    // [0] structure violations seen by the packing kernels, [1] entries of Dt that differ from the unitary 64-point DFT
     int t1_red;                  // 1: T1' is accumulated over chunks by red.global.add into [b][N][L*Nt]; 0: per-chunk partials [b][nmc][N][L*Nt]
+    float snap_tol;              // > 0: the pilots were recovered from a dense dictionary (k_recover_psi) and carry fp32 rounding noise: components within
+                                 // snap_tol * scale of +-scale are snapped, the Toeplitz check compares with the same tolerance
     int dft;                     // Dt is the unitary DFT grid of wideband_mmwave_channel.m:9-10 with Gt = Nt = 64: rotations run as radix-4 FFTs
 };
 struct Maps { CUtensorMap E, X, V1, V2, XV, G, SY; };
@@ -137,6 +139,7 @@ __global__ void __launch_bounds__(256) k_pack_psi(In in, int M) {
     float sc = fabsf(Ps[0].re);
     if (sc == 0.f) sc = fabsf(Ps[0].im);
     if (sc == 0.f) sc = 1.f;
+    const float tol = in.snap_tol * sc;
     if (blockIdx.x == 0 && threadIdx.x == 0) in.scale[b] = sc;
     const int k = threadIdx.x % NT;
     int nbad = 0;
@@ -148,12 +151,13 @@ __global__ void __launch_bounds__(256) k_pack_psi(In in, int M) {
         if (t >= 0 && t < M) e = Ps[k + (size_t)Nt * t];                                  // tap 0, column t
         else if (t < 0) e = Ps[k + (size_t)Nt * M * (size_t)(-t)];                        // tap -t, column 0
         const unsigned short br = bf16_bits(e.re / sc), bi = bf16_bits(e.im / sc);
-        if (bf16_val(br) * sc != e.re || bf16_val(bi) * sc != e.im) ++nbad;               // not exact in bf16 after the common scaling
+        if (tol > 0.f) { if (t < M && (fabsf(bf16_val(br) * sc - e.re) > tol || fabsf(bf16_val(bi) * sc - e.im) > tol || fabsf(bf16_val(br)) != 1.f || fabsf(bf16_val(bi)) != 1.f)) ++nbad; }
+        else if (bf16_val(br) * sc != e.re || bf16_val(bi) * sc != e.im) ++nbad;          // not exact in bf16 after the common scaling
         for (int l = 1; l < L; ++l) {                                                     // Toeplitz: tap l reads e(j - l) at column j = t + l
             const int j = t + l;
             if (j >= 0 && j < M && (t >= 0 || l != -t)) {
                 const cx<float> v = Ps[k + (size_t)Nt * j + (size_t)Nt * M * l];
-                if (v.re != e.re || v.im != e.im) ++nbad;
+                if (tol > 0.f ? (fabsf(v.re - e.re) > 2.f * tol || fabsf(v.im - e.im) > 2.f * tol) : (v.re != e.re || v.im != e.im)) ++nbad;
             }
         }
         // kc = 2k (re), 2k+1 (im): both in group k / 4
@@ -204,6 +208,37 @@ __global__ void __launch_bounds__(256) k_build_b(const cx<T>* __restrict__ Psi, 
         T re = 0, im = 0;
         for (int k = 0; k < Nt; ++k) { const cx<T> d = sD[k + (size_t)Nt * g], v = sP[k + (size_t)Nt * jj]; cmac<T>(re, im, d.re, -d.im, v.re, v.im); }
         out[(size_t)(l * Gt + g) + (size_t)P * (j0 + jj)] = mk<T>(re, im);
+    }
+}
+
+// ---- Psi_bar recovered from a dense dictionary: B((l-1)Gt+1 : l Gt, :) = Dt' Psi_bar(:,:,l) with the unitary 64-point DFT grid means
+//      Psi_bar(:,:,l) = Dt B_l.  The reference function's own argument list (proposed_algorithm.m:1) carries only B; when B has the
+//      structure its drivers give it (plot_errorVSsnr.m:133-136) this puts the call on the Psi-domain tensor-core path.  Whether it has is
+//      decided by k_pack_psi on the result (4-QAM components and Toeplitz taps within rounding noise), never assumed.
+// grid (ceil(M / 64), L, nB), block 256
+__global__ void __launch_bounds__(256) k_recover_psi(const cx<float>* __restrict__ B, long long ld_B, cx<float>* __restrict__ Psi, long long ld_Psi, int L, int M) {
+    __shared__ cx<float> sB[NT * 65];                             // B_l(g, 64 columns), padded
+    __shared__ cx<float> stw[NT];
+    const int b = blockIdx.z, l = blockIdx.y, j0 = blockIdx.x * 64, P = L * NT;
+    if (threadIdx.x < NT) { float sn, cs; sincospif(-2.0f * (float)threadIdx.x / NT, &sn, &cs); stw[threadIdx.x] = mk<float>(0.125f * cs, 0.125f * sn); }
+    const cx<float>* Bb = B + (long long)b * ld_B;
+    for (int t = threadIdx.x; t < NT * 64; t += 256) { const int g = t % NT, jj = t / NT; sB[g + 65 * jj] = j0 + jj < M ? Bb[(size_t)(l * NT + g) + (size_t)P * (j0 + jj)] : mk<float>(0.f, 0.f); }
+    __syncthreads();
+    cx<float>* out = Psi + (long long)b * ld_Psi + (size_t)NT * M * l;
+    for (int t = threadIdx.x; t < NT * 64; t += 256) {
+        const int k = t % NT, jj = t / NT;
+        if (j0 + jj >= M) continue;
+        float re = 0.f, im = 0.f;
+        for (int g = 0; g < NT; ++g) { const cx<float> d = stw[(k * g) % NT], v = sB[g + 65 * jj]; cmac<float>(re, im, d.re, d.im, v.re, v.im); }
+        out[k + (size_t)NT * (j0 + jj)] = mk<float>(re, im);
+    }
+}
+// Dt(k, g) = exp(-2 pi j k g / 64) / 8 (wideband_mmwave_channel.m:9-10 with Gt = Mt = 64)
+__global__ void __launch_bounds__(256) k_make_dft64(cx<float>* Dt) {
+    for (int t = threadIdx.x; t < NT * NT; t += 256) {
+        const int k = t % NT, g = t / NT;
+        double sn, cs; sincospi(-2.0 * (double)((k * g) % NT) / NT, &sn, &cs);
+        Dt[t] = mk<float>((float)(0.125 * cs), (float)(0.125 * sn));
     }
 }
 
