@@ -666,6 +666,9 @@ static bool psi_fast_enabled() {
     const char* e = getenv("JSTSP_PSI_DENSE");      // developer switch: force the materialised-B kernels
     return !(e && atoi(e) != 0);
 }
+}  // namespace jstsp
+#include "admm_large.cuh"
+namespace jstsp {
 template <typename T>
 static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* subY_, const void* omega_, const int* indx_,
                     const void* A_, const void* B_, const double* tauY_, const double* tauS_, const double* rho_,
@@ -685,6 +688,14 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
         }
     }
     if (N <= 0 || M <= 0 || G <= 0 || P <= 0 || batch <= 0 || imax < 0) return fail(h, JSTSP_E_ARG, "non-positive dimension");
+    // large-array route (admm_large.cuh): pilots entry, fp32, 'approximate', no diagnostics / ranking; B is never formed
+    if constexpr (std::is_same<T, float>::value) {
+        if (ps && ps->pilots && !recovered && d->type == JSTSP_APPROXIMATE && !conv_ && !angles && getenv("JSTSP_NO_LARGE") == nullptr &&
+            ps->L * ps->Gt == P && lg::large_shape(N, M, G, ps->Nt, ps->Gt, ps->L)) {
+            if (!subY_ || !omega_ || !A_ || !ps->Dt || !ps->Psi || !tauY_ || !tauS_ || !rho_ || !S_) return fail(h, JSTSP_E_ARG, "NULL buffer");
+            return lg::run_large(h, d, mem, subY_, omega_, A_, ps, tauY_, tauS_, rho_, S_, Y_);
+        }
+    }
     if (!subY_ || !omega_ || !A_ || (!B_ && !ps) || !tauY_ || !tauS_ || !rho_ || !S_) return fail(h, JSTSP_E_ARG, "NULL buffer");
     if (ps && !recovered) {
         if (!ps->Dt || !ps->Psi) return fail(h, JSTSP_E_ARG, "NULL buffer");

@@ -94,7 +94,7 @@ extern "C" int jstsp_set_chunk(jstsp_handle* h, int max_trials_per_pass) {
     return JSTSP_OK;
 }
 
-static const char* kProfNames[PK_COUNT] = {"xupd_t1", "res", "q", "vupd", "xs", "eig", "setup", "svt_step", "omp", "other", "fused_tc", "expand_as", "fused_psi", "psi_res", "psi_g", "psi_step", "omp_kron_corr", "somp", "omp_kron_corr_tc", "psi_mega"};
+static const char* kProfNames[PK_COUNT] = {"xupd_t1", "res", "q", "vupd", "xs", "eig", "setup", "svt_step", "omp", "other", "fused_tc", "expand_as", "fused_psi", "psi_res", "psi_g", "psi_step", "omp_kron_corr", "somp", "omp_kron_corr_tc", "psi_mega", "lg_state", "lg_pass1", "lg_pass2", "lg_small"};
 
 extern "C" int jstsp_profile(jstsp_handle* h, int enable) {
     if (!h) return JSTSP_E_ARG;

@@ -49,7 +49,7 @@ __host__ __device__ __forceinline__ long long ceil_div_ll(long long a, long long
 // ---------------------------------------------------------------------------
 // Optional per-kernel-class device timing (CUDA events on the launching stream), switched on
 // by jstsp_profile(); bench.py reads it for the live roofline numbers.
-enum { PK_XUPD_T1 = 0, PK_RES, PK_Q, PK_VUPD, PK_XS, PK_EIG, PK_SETUP, PK_SVT_STEP, PK_OMP, PK_OTHER, PK_FUSED_TC, PK_EXPAND, PK_FUSED_PSI, PK_PSI_AUX, PK_PSI_G, PK_PSI_STEP, PK_OMP_CORR, PK_SOMP, PK_OMP_CORR_TC, PK_PSI_MEGA, PK_COUNT };
+enum { PK_XUPD_T1 = 0, PK_RES, PK_Q, PK_VUPD, PK_XS, PK_EIG, PK_SETUP, PK_SVT_STEP, PK_OMP, PK_OTHER, PK_FUSED_TC, PK_EXPAND, PK_FUSED_PSI, PK_PSI_AUX, PK_PSI_G, PK_PSI_STEP, PK_OMP_CORR, PK_SOMP, PK_OMP_CORR_TC, PK_PSI_MEGA, PK_LG_STATE, PK_LG_PASS1, PK_LG_PASS2, PK_LG_SMALL, PK_COUNT };
 struct Prof {
     bool on = false;
     struct Rec { int slot; cudaEvent_t a, b; };
