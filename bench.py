@@ -233,6 +233,36 @@ def secondary_configs(torch, dist, _lib, dev, local, rank, world, pk_hbm):
     by = 100 * 8 * (2 * mm * nn + 2 * mm * mm)
     out["config3_vamp"] = dict(shape=[mm, nn, 100], value=world * nbv / ms * 1e3, unit="estimates/s", per_trial_operator=True, hbm_frac=by * nbv / (ms * 1e-3) / 1e9 / pk_hbm,
                                algorithmic_bytes_per_estimate=by, note="A, A', U, U' of every trial streamed once per iteration; the svd of vamp.m:32 is host LAPACK, outside the timed region")
+    del Av, Ud, OH, Om, X
+    # ---- config 4 at its real size (large-array route, csrc/admm_large.cuh): Nt = 256, Nr = 64, 128 frames, L = 8; subY 64 x 32768, dictionary 2048 x 32768 never formed ----
+    N4, Nt4, L4, T4, nb4, IM4 = 64, 256, 8, 128, 4, 100
+    M4, P4 = T4 * Nt4, L4 * Nt4
+    pil = (((torch.randint(0, 2, (nb4, M4, Nt4), generator=g, device=dev) * 2 - 1) + 1j * (torch.randint(0, 2, (nb4, M4, Nt4), generator=g, device=dev) * 2 - 1)).to(torch.complex64) / 2 ** 0.5).contiguous()
+    om4 = torch.zeros(nb4, M4, N4, device=dev)
+    om4.scatter_(2, torch.rand(nb4, M4, N4, generator=g, device=dev).topk(4, dim=2).indices, 1.0)        # 4 of 64 RF chains per training instant (proposed_hbf.m:36-41)
+    sY4 = (crandn(nb4, M4, N4) * om4).contiguous()
+    A4 = (crandn(N4, N4) / N4 ** 0.5).contiguous()
+    Dt4 = (torch.exp(-2j * torch.pi * torch.outer(torch.arange(Nt4, device=dev), torch.arange(Nt4, device=dev)) / Nt4) / Nt4 ** 0.5).to(torch.complex64).contiguous()
+    S4 = torch.empty(nb4, P4, N4, dtype=torch.complex64, device=dev); Y4 = torch.empty(nb4, M4, N4, dtype=torch.complex64, device=dev)
+    tY4 = (1.0 / sY4.abs().pow(2).sum(dim=(1, 2))).double().contiguous(); tS4 = torch.full((nb4,), 0.5, dtype=torch.float64, device=dev); rh4 = torch.full((nb4,), 0.05, dtype=torch.float64, device=dev)
+    d4 = _lib.AdmmDesc()
+    d4.N, d4.M, d4.G, d4.P, d4.imax, d4.type, d4.batch = N4, M4, N4, P4, IM4, 0, nb4
+    d4.ld_subY, d4.ld_omega, d4.ld_A, d4.ld_B, d4.ld_S, d4.ld_Y, d4.ld_conv = N4 * M4, N4 * M4, 0, 0, N4 * P4, N4 * M4, 0
+    run4 = lambda: h.check(L.jstsp_proposed_algorithm_pilots(h.ptr, C.byref(d4), _lib.F32, _lib.DEVICE, p(sY4), p(om4), None, p(A4), p(Dt4), 0, p(pil), Nt4 * M4, Nt4, L4,
+                                                            p(tY4), p(tS4), p(rh4), p(S4), p(Y4), None))
+    L.jstsp_profile(h.ptr, 2)
+    ms = timed(run4, steps=1)
+    kern = h.profile_read(); L.jstsp_profile(h.ptr, 0)
+    assert h.last_path == 3, "config 4 did not take the large-array route"
+    fl = 3 * 8.0 * N4 * P4 * M4                       # the three big products of an iteration (SURVEY 8d flop count at this shape), each issued as 3 bf16 MMAs
+    p1, p2 = kern.get("lg_pass1"), kern.get("lg_pass2")
+    out["config4_large_array"] = dict(workload="jstsp_proposed_algorithm_pilots('approximate', Imax=100), Nt=256 Nr=64 K=128 L=8: subY 64 x 32768, dictionary 2048 x 32768 never formed",
+                                      value=world * nb4 / ms * 1e3, unit="estimates/s", trials_per_gpu=nb4, ms_per_call=ms, ms_per_trial_iteration=ms / nb4 / IM4,
+                                      tensor_flops_per_iteration=fl * 3,
+                                      pass1_tflops_bf16=(fl * nb4 / (p1[0] / p1[1] * 1e-3) / 1e12) if p1 and p1[1] else None,      # per launch: one product of all trials, fl / 3 algorithmic flops x 3 MMAs
+                                      pass2_tflops_bf16=(fl * nb4 / (p2[0] / p2[1] * 1e-3) / 1e12) if p2 and p2[1] else None,
+                                      tensor_peak_tflops=peaks()["bf16_sus"], kernel_ms={k: round(v[0], 3) for k, v in kern.items() if v[1]},
+                                      note="bf16 x 3 split of the fp32 operand against the exact bf16 pilot image: 3 MMA flops per algorithmic flop; pass*_tflops count the MMA flops issued")
     h.close()
     return out
 

@@ -1,0 +1,108 @@
+"""Large-array route of proposed_algorithm('approximate') (csrc/admm_large.cuh; BASELINE.json configs[4]: Nt = 256, Nr = 64, 128 frames,
+L = 8 delay taps - the plot_errorVSdelays.m:45-49,127-128 shape scaled up, rho from the largest eigenvalue, 5 dB).  The dictionary
+B (2048 x 32768, 512 MiB per trial) is never formed: the call goes through jstsp_proposed_algorithm_pilots (Dt and the pilot sequences).
+
+  * smaller shapes of the same route (32 / 48 / 64 rows, 64 / 128 / 256 antennas, 3-8 taps) against the fp64 oracle at 100 iterations,
+  * the real size against the oracle run live for 3 iterations on two seeded trials,
+  * the real size at 100 iterations against the frozen oracle outputs of tools/make_golden_config4.py (tests/golden/config4_full.npz),
+  * error behaviour (pilots that are not 4-QAM), bit-for-bit repeatability, last_path.
+
+Stated tolerance: relative Frobenius error of S and Y <= 5e-5 against fp64 (measured 4e-6 .. 1.2e-5; fp32 state, three-term bf16 split
+operands, fp32 accumulation over up to 32768 columns), NMSE as the drivers compute it (plot_errorVSdelays.m:139-141) within 1e-4 relative."""
+import os
+
+import numpy as np
+import pytest
+
+import jstsp19_b200 as jb
+from jstsp19_b200._lib import JstspError, default_handle
+from oracle import estimators as est
+from oracle import fixtures as fx
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CONFIG4 = fx.Shape(Nt=256, Nr=64, L=8, Mr=4, T=128)
+TOL = 5e-5
+_C4 = {}
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def _run(trials, L, imax, **kw):
+    st = lambda key: np.stack([t[key] for t in trials])
+    par = ([t["tau_Y"] for t in trials], [t["tau_Z"] for t in trials], [t["rho"] for t in trials], "approximate")
+    return jb.proposed_algorithm_pilots(st("subY"), st("Omega"), st("A"), trials[0]["Dt"], st("pilots"), L, imax, *par, precision="f32", nargout=2, **kw)
+
+
+def _config4_trials():
+    if "t" not in _C4:
+        _C4["t"] = [fx.make_trial(CONFIG4, 5.0, seed, rho_rule="sigma1") for seed in (4001, 4002)]
+    return _C4["t"]
+
+
+@pytest.mark.parametrize("Nt,Nr,L,T,snr", [(64, 32, 4, 8, 5.0), (128, 64, 8, 4, 15.0), (256, 48, 3, 2, -5.0), (64, 64, 1, 8, 0.0)])
+def test_large_route_shapes_against_oracle(Nt, Nr, L, T, snr):
+    sh = fx.Shape(Nt=Nt, Nr=Nr, L=L, Mr=4, T=T)
+    trials = [fx.make_trial(sh, snr, 7100 + k, rho_rule="sigma1" if k % 2 else "sigma6") for k in range(3)]
+    S, Y = _run(trials, L, 100)
+    assert default_handle().last_path == 3
+    for k, t in enumerate(trials):
+        S0, Y0, _ = est.proposed_algorithm_structured(t["subY"], t["Omega"], t["A"], t["B"], 100, t["tau_Y"], t["tau_Z"], t["rho"], "approximate", want_conv=False)
+        n1, n0 = est.nmse(S[k].astype(np.complex128), t["Zbar"]), est.nmse(S0, t["Zbar"])
+        print(f"Nt={Nt} Nr={Nr} L={L} trial {k}: S {_rel(S[k], S0):.2e} Y {_rel(Y[k], Y0):.2e} NMSE {n1:.5e} vs {n0:.5e}")
+        assert _rel(S[k], S0) < TOL and _rel(Y[k], Y0) < TOL
+        assert abs(n1 - n0) <= 1e-4 * n0
+
+
+def test_config4_real_size_against_live_oracle():
+    trials = _config4_trials()
+    S, Y = _run(trials, CONFIG4.L, 3)
+    assert default_handle().last_path == 3
+    assert S.shape == (2, 64, 2048) and Y.shape == (2, 64, 32768)
+    for k, t in enumerate(trials):
+        S0, Y0, _ = est.proposed_algorithm_structured(t["subY"], t["Omega"], t["A"], t["B"], 3, t["tau_Y"], t["tau_Z"], t["rho"], "approximate", want_conv=False)
+        print(f"config 4, 3 iterations, trial {k}: S {_rel(S[k], S0):.2e} Y {_rel(Y[k], Y0):.2e}")
+        assert _rel(S[k], S0) < TOL and _rel(Y[k], Y0) < TOL
+
+
+def test_config4_real_size_100_iterations_against_frozen_oracle():
+    g = np.load(os.path.join(GOLD, "config4_full.npz"))
+    assert list(g["seeds"]) == [4001, 4002] and int(g["imax"]) == 100
+    trials = _config4_trials()
+    for k, t in enumerate(trials):                    # the seeded inputs are the ones the frozen run used
+        assert np.allclose([t["tau_Y"], t["tau_Z"], t["rho"]], g[f"params{k}"], rtol=1e-12)
+    S, Y = _run(trials, CONFIG4.L, 100)
+    S2, _ = _run(trials, CONFIG4.L, 100)
+    assert np.array_equal(S, S2)                      # ordered reductions: repeatable bit for bit
+    for k, t in enumerate(trials):
+        n1, n0 = est.nmse(S[k].astype(np.complex128), t["Zbar"]), float(g[f"nmse{k}"])
+        eS, eY = _rel(S[k], g[f"S{k}"]), _rel(Y[k][:, :64], g[f"Yhead{k}"])
+        print(f"config 4, 100 iterations, trial {k}: S {eS:.2e} Y(:,1:64) {eY:.2e} |Y| {np.linalg.norm(Y[k]):.6e} vs {float(g[f'Ynorm{k}']):.6e} NMSE {n1:.6e} vs {n0:.6e}")
+        assert eS < TOL and eY < TOL
+        assert abs(np.linalg.norm(Y[k].astype(np.complex128)) - float(g[f"Ynorm{k}"])) <= 1e-5 * float(g[f"Ynorm{k}"])
+        assert abs(n1 - n0) <= 1e-4 * n0
+
+
+def test_large_route_rejects_pilots_that_are_not_4qam():
+    sh = fx.Shape(Nt=64, Nr=32, L=4, Mr=4, T=8)
+    t = fx.make_trial(sh, 5.0, 7200)
+    bad = dict(t)
+    bad["pilots"] = t["pilots"] * (1.0 + 0.25 * np.arange(t["pilots"].shape[1])[None, :] / t["pilots"].shape[1])
+    with pytest.raises(JstspError) as e:
+        _run([bad], 4, 2)
+    assert "4-QAM" in str(e.value)
+
+
+def test_large_route_shared_and_per_trial_pilots_agree():
+    sh = fx.Shape(Nt=64, Nr=32, L=4, Mr=4, T=8)
+    t = fx.make_trial(sh, 5.0, 7300)
+    t2 = fx.make_trial(sh, 0.0, 7301)
+    t2 = dict(t2); t2["pilots"] = t["pilots"]; t2["A"] = t["A"]          # same pilots, same A: shared operands (stride 0)
+    S_a, Y_a = _run([t, t2], 4, 20)
+    par = ([t["tau_Y"], t2["tau_Y"]], [t["tau_Z"], t2["tau_Z"]], [t["rho"], t2["rho"]], "approximate")
+    S_b, Y_b = jb.proposed_algorithm_pilots(np.stack([t["subY"], t2["subY"]]), np.stack([t["Omega"], t2["Omega"]]), t["A"], t["Dt"], t["pilots"], 4, 20, *par,
+                                            precision="f32", nargout=2)
+    assert np.array_equal(S_a, S_b) and np.array_equal(Y_a, Y_b)
