@@ -431,7 +431,7 @@ def main():
             dist.all_reduce(pms, op=dist.ReduceOp.MAX)
         pst = pmc.reduce()
         pipeline = dict(value=nb * world * 2 / (float(pms.item()) * 1e-3), unit="trials/s", ms_per_step=float(pms.item()) / 2,
-                        stages="draws (torch) -> jstsp_wideband_mmwave_channel -> jstsp_measure -> jstsp_admm_parameters -> jstsp_proposed_algorithm_pilots -> jstsp_nmse",
+                        stages="jstsp_draw_trials (Philox4x32-10 on the device) -> jstsp_wideband_mmwave_channel -> jstsp_measure -> jstsp_admm_parameters -> jstsp_proposed_algorithm_pilots -> jstsp_nmse",
                         mean_nmse=pst["mean_nmse"], trials=pst["trials"], flagged=pst["flagged"])
 
     # ---- BASELINE configs 2 and 3, trial-sharded like the headline (every rank its own trials, device time, max over ranks) ----

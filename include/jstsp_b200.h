@@ -310,6 +310,22 @@ int jstsp_capacity(jstsp_handle* h, int dtype, int mem, int Nr, int T, int Wc, i
  * mean(rate) / power (plot_ee.m:84-87).  Host arithmetic, no handle. */
 int jstsp_power_model(int Nr, int Mr, int Mr_e, double* power4);
 
+/* Random draws of one batch of Monte-Carlo trials, generated on the device (csrc/rng.cu).  Replaces the calls to MATLAB's global stream in
+ * the trial loop: randn / rand of wideband_mmwave_channel.m:19-22, randn of plot_errorVSsnr.m:60, randsrc of qam4mod.m:7-8 (via
+ * plot_errorVSsnr.m:63-67) and randperm of proposed_hbf.m:37.  The reference fixes no seed, so the distributions are its behaviour, not the
+ * numbers.  Every value is Philox4x32-10 of counter = (block index, stream id, global trial index) under key = seed: trial t gets the same
+ * numbers whichever batch, shard or GPU count computes it.  DEVICE buffers only; any output may be NULL.
+ *   sigma2   [batch] noise variances 10^(-snr/10)                                   (in)
+ *   normals  [batch][L][Np][2] double, N(0,1): (randn, randn) of each path gain      -> jstsp_wideband_mmwave_channel
+ *   uniforms [batch][L][Np][2] double, U(0,1): (rand, rand) of each path's angles    -> jstsp_wideband_mmwave_channel
+ *   pilots   [batch][T][Nt] complex of `dtype`: s_k(t) at [t][k], (+-1 +-j)/sqrt 2    -> jstsp_measure (psi_mode 1), jstsp_proposed_algorithm_pilots
+ *   noise    [batch][T][Nr] complex of `dtype`: sqrt(sigma2/2) (randn + j randn)      -> jstsp_measure
+ *   perm     [batch][T][Nr] int32, 1-based: randperm(Nr) of each training instant    -> jstsp_measure */
+int jstsp_draw_trials(jstsp_handle* h, int dtype, unsigned long long seed, long long first_trial, int batch, int Nr, int Nt, int L, int Np, int T,
+                      const double* sigma2, double* normals, double* uniforms, void* pilots, void* noise, int* perm);
+/* The generator itself on the host (known-answer tests): out[4] = Philox4x32-10(ctr[4], key[2]).  No handle, no device. */
+void jstsp_philox4x32_10(const unsigned* ctr, const unsigned* key, unsigned* out);
+
 /* Least-squares baseline of the drivers, batched:  S = pinv(A) * Y * pinv(B)   (plot_errorVSsnr.m:83, plot_errorVSsnr_approx.m:61,67)
  * and / or  YpinvB = Y * pinv(B)  (the right-hand sides handed to the joint OMP, plot_errorVSsnr.m:117).
  * A N x G, B P x M, Y N x M, S G x P, YpinvB N x P; either output may be NULL (A may be NULL when S is).  Full-rank operands: pinv is

@@ -921,9 +921,11 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
             else {
                 if (ps->pilots) {   // the sequences travel (Nt x M per trial, L times fewer bytes); Psi_bar is expanded on the device, on the copy stream
                     JSTSP_CUDA(h, up(pil_dev, ps->Psi, (size_t)ps->Nt * M, ps->ld_Psi, esz));
-                    dim3 g(4 * h->sm_count, ps->ld_Psi ? nb : 1);
-                    k_expand_pilots<T><<<g, 256, 0, cs>>>(pil_dev, ps->ld_Psi ? (long long)ps->Nt * M : 0, const_cast<cx<T>*>(psi_dev), ps->ld_Psi ? (long long)ps->Nt * M * ps->L : 0, ps->Nt, M, ps->L);
-                    h->launches++;
+                    if (!psi_shape) {      // the structured path packs its pilot image straight from the sequences
+                        dim3 g(4 * h->sm_count, ps->ld_Psi ? nb : 1);
+                        k_expand_pilots<T><<<g, 256, 0, cs>>>(pil_dev, ps->ld_Psi ? (long long)ps->Nt * M : 0, const_cast<cx<T>*>(psi_dev), ps->ld_Psi ? (long long)ps->Nt * M * ps->L : 0, ps->Nt, M, ps->L);
+                        h->launches++;
+                    }
                 } else
                 JSTSP_CUDA(h, up(psi_dev, ps->Psi, (size_t)ps->Nt * M * ps->L, ps->ld_Psi, esz));
                 JSTSP_CUDA(h, up(dt_dev, ps->Dt, (size_t)ps->Nt * ps->Gt, ps->ld_Dt, esz));
@@ -960,7 +962,7 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
                     JSTSP_LAUNCH(h, PK_SETUP, (psi::k_recover_psi<<<g, 256, 0, st>>>(q.B, q.ld_B, psi_rec, ldP, ps->L, M)));
                 }
             }
-            if (ps->pilots && !host) {
+            if (ps->pilots && !host && !psi_shape) {
                 dim3 g(4 * h->sm_count, ps->ld_Psi ? nb : 1);
                 JSTSP_LAUNCH(h, PK_SETUP, (k_expand_pilots<T><<<g, 256, 0, st>>>((const cx<T>*)ps->Psi + (long long)b0 * ps->ld_Psi, ps->ld_Psi, psi_exp, ldP, ps->Nt, M, ps->L)));
             }
@@ -973,7 +975,11 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
                     pin.snap_tol = recovered ? 2e-5f : 0.f;      // recovered pilots carry the fp32 rounding of B = Dt' Psi and of Dt B_l (~1e-6 of the scale)
                     const int nE = ps->ld_Psi ? nb : 1;
                     JSTSP_CUDA(h, cudaMemsetAsync(pin.bad, 0, 2 * sizeof(int), st));
-                    { dim3 g(ceil_div(M + 8, 16), nE); JSTSP_LAUNCH(h, PK_SETUP, (psi::k_pack_psi<<<g, 256, 0, st>>>(pin, M))); }
+                    if (ps->pilots) {      // sequences given: the image is e_k(t) itself (Toeplitz by construction), only the 4-QAM / bf16 exactness is checked
+                        const cx<float>* pl = host ? (const cx<float>*)pil_dev : (const cx<float>*)ps->Psi + (long long)b0 * ps->ld_Psi;
+                        dim3 g(ceil_div(M + 8, 32), nE);
+                        JSTSP_LAUNCH(h, PK_SETUP, (lg::k_lg_pack_e<<<g, 256, 0, st>>>(pl, ps->ld_Psi ? (host ? (long long)ps->Nt * M : ps->ld_Psi) : 0, pin.E, pin.scale, pin.bad, ps->Nt, M, M + 8, ps->L)));
+                    } else { dim3 g(ceil_div(M + 8, 16), nE); JSTSP_LAUNCH(h, PK_SETUP, (psi::k_pack_psi<<<g, 256, 0, st>>>(pin, M))); }
                     if (nE == 1 && nb > 1) JSTSP_LAUNCH(h, PK_SETUP, (psi::k_spread_scale<<<ceil_div(nb, 256), 256, 0, st>>>(pin.scale, nb)));
                     { dim3 g(ceil_div(M, 256), nb); JSTSP_LAUNCH(h, PK_SETUP, (psi::k_pack_omega<<<g, 256, 0, st>>>(pin, q.omega, q.ld_omega, M))); }
                     const bool dft_shape = ps->Gt == psi::NT && getenv("JSTSP_PSI_NOFFT") == nullptr;
@@ -997,6 +1003,11 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
             }
             if (!use_psi && !recovered) {
                 // dense dictionary from its factors, operand of the dense kernels
+                if (ps->pilots && psi_shape) {      // the structured path was refused after all: expand the sequences now
+                    const cx<T>* pl = host ? pil_dev : (const cx<T>*)ps->Psi + (long long)b0 * ps->ld_Psi;
+                    dim3 g(4 * h->sm_count, ps->ld_Psi ? nb : 1);
+                    JSTSP_LAUNCH(h, PK_SETUP, (k_expand_pilots<T><<<g, 256, 0, st>>>(pl, ps->ld_Psi ? (host ? (long long)ps->Nt * M : ps->ld_Psi) : 0, const_cast<cx<T>*>(Pd), ldP, ps->Nt, M, ps->L)));
+                }
                 const int nBd = ldB_in ? nb : 1;
                 const size_t smb = sizeof(cx<T>) * ((size_t)ps->Nt * ps->Gt + (size_t)ps->Nt * 64);
                 if ((rc = set_smem(h, psi::k_build_b<T>, smb))) return rc;

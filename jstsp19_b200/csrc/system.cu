@@ -9,6 +9,7 @@
 // Randomness is an INPUT: the functions that draw in the reference (randn / rand / randperm) take
 // the draws as arrays in the reference's consumption order, so a MEX gateway can obtain them from
 // MATLAB's own generator (mexCallMATLAB) and the batched engine from its counter-based generator.
+#include <algorithm>
 #include "common.cuh"
 #include "jacobi.cuh"
 
@@ -65,6 +66,16 @@ __global__ void __launch_bounds__(256) k_channel(ChanP<T> p) {
         double s, c; sincos(-2.0 * M_PI * (double)i * g / Gt, &s, &c);
         p.Dt[(size_t)b * Mt * Gt + t] = mk<T>((T)(c / sqrt((double)Mt)), (T)(s / sqrt((double)Mt)));          // .m:10
     }
+    // tables: steering vectors of the tap-1 rays, DFT twiddles of both grids (the products below index them instead of calling sincos per term)
+    double* arr = pht + Np;                    // [Np][Mr][2]
+    double* att = arr + 2 * Np * Mr;           // [Np][Mt][2]
+    double* twr = att + 2 * Np * Mt;           // [Gr][2]   exp(+2 pi j q / Gr)
+    double* twt = twr + 2 * Gr;                // [Gt][2]   exp(-2 pi j q / Gt)
+    for (int t = threadIdx.x; t < Np * Mr; t += blockDim.x) { double sn, cs; sincos(-M_PI * phr[t / Mr] * (t % Mr), &sn, &cs); arr[2 * t] = cs; arr[2 * t + 1] = sn; }
+    for (int t = threadIdx.x; t < Np * Mt; t += blockDim.x) { double sn, cs; sincos(-M_PI * pht[t / Mt] * (t % Mt), &sn, &cs); att[2 * t] = cs; att[2 * t + 1] = sn; }
+    for (int t = threadIdx.x; t < Gr; t += blockDim.x) { double sn, cs; sincos(2.0 * M_PI * (double)t / Gr, &sn, &cs); twr[2 * t] = cs; twr[2 * t + 1] = sn; }
+    for (int t = threadIdx.x; t < Gt; t += blockDim.x) { double sn, cs; sincos(-2.0 * M_PI * (double)t / Gt, &sn, &cs); twt[2 * t] = cs; twt[2 * t + 1] = sn; }
+    __syncthreads();
     cx<T>* Hl = p.ws + (size_t)b * (Mr * Mt + Mr * Gt);
     cx<T>* tmp = Hl + Mr * Mt;
     const double scale = 1.0 / sqrt((double)Np);
@@ -76,8 +87,9 @@ __global__ void __launch_bounds__(256) k_channel(ChanP<T> p) {
             for (int k = 0; k < Np; ++k) {
                 const double w = (double)(p.ncl - k / p.nray) * scale / sqrt(2.0);
                 const double cr = nrm[2 * (l * Np + k)] * w, ci = nrm[2 * (l * Np + k) + 1] * w;
-                double s, c; sincos(-M_PI * (phr[k] * i - pht[k] * j), &s, &c);      // a_r(i) conj(a_t(j))
-                re += cr * c - ci * s; im += cr * s + ci * c;
+                const double ac = arr[2 * (k * Mr + i)], as = arr[2 * (k * Mr + i) + 1], bc = att[2 * (k * Mt + j)], bs = att[2 * (k * Mt + j) + 1];
+                const double c = ac * bc + as * bs, sn = as * bc - ac * bs;         // a_r(i) conj(a_t(j))
+                re += cr * c - ci * sn; im += cr * sn + ci * c;
             }
             Hl[t] = mk<T>((T)re, (T)im);
             if (p.H) p.H[(size_t)b * Mr * Mt * L + (size_t)l * Mr * Mt + t] = Hl[t];
@@ -89,9 +101,10 @@ __global__ void __launch_bounds__(256) k_channel(ChanP<T> p) {
                 const int i = t % Mr, g = t / Mr;
                 double re = 0.0, im = 0.0;
                 for (int j = 0; j < Mt; ++j) {
-                    double s, c; sincos(-2.0 * M_PI * (double)j * g / Gt, &s, &c);
+                    const int q = (int)(((long long)j * g) % Gt);
+                    const double c = twt[2 * q], sn = twt[2 * q + 1];
                     const cx<T> hv = Hl[i + Mr * j];
-                    re += hv.re * c - hv.im * s; im += hv.re * s + hv.im * c;
+                    re += hv.re * c - hv.im * sn; im += hv.re * sn + hv.im * c;
                 }
                 tmp[t] = mk<T>((T)(re / sqrt((double)Mt)), (T)(im / sqrt((double)Mt)));
             }
@@ -100,9 +113,10 @@ __global__ void __launch_bounds__(256) k_channel(ChanP<T> p) {
                 const int gr = t % Gr, g = t / Gr;
                 double re = 0.0, im = 0.0;
                 for (int i = 0; i < Mr; ++i) {
-                    double s, c; sincos(2.0 * M_PI * (double)i * gr / Gr, &s, &c);   // conj(Dr(i,gr))
+                    const int q = (int)(((long long)i * gr) % Gr);                    // conj(Dr(i,gr))
+                    const double c = twr[2 * q], sn = twr[2 * q + 1];
                     const cx<T> v = tmp[i + Mr * g];
-                    re += v.re * c - v.im * s; im += v.re * s + v.im * c;
+                    re += v.re * c - v.im * sn; im += v.re * sn + v.im * c;
                 }
                 p.Zbar[(size_t)b * Gr * Gt * L + (size_t)(l * Gt + g) * Gr + gr] = mk<T>((T)(re / sqrt((double)Mr)), (T)(im / sqrt((double)Mr)));
             }
@@ -178,6 +192,72 @@ __global__ void __launch_bounds__(256) k_measure(MeasP<T> p) {
             if (p.Omega) p.Omega[(size_t)b * Wc * TT + (size_t)t * Wc + q] = om;
         }
         if (p.Yout) p.Yout[(size_t)b * Wc * TT + (size_t)t * Wc + q] = mk<T>(om * re, om * im);     // Omega .* (W_e' R) (:42)
+    }
+}
+
+// Same synthesis for pilot-sequence input (psi_mode 1) with the operands staged in shared memory: H (all taps), the (columns + L - 1) window
+// of e_k(t) = s_k(t) | conj(s_k(-t)), then R and W.  Thread = (column, 8 rows): per (tap, antenna) one pilot load and one broadcast 8-row
+// slice of H feed 8 complex MACs.  grid (ceil(T / CTc), batch), block 256, CTc = 256 / (Nr / 8) columns per CTA.
+template <typename T>
+__global__ void __launch_bounds__(256) k_measure_tiled(MeasP<T> p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int b = blockIdx.y, Nr = p.Nr, Nt = p.Nt, L = p.L, TT = p.T_, Wc = p.Wc;
+    const int RG = Nr / 8, CTc = 256 / RG, WP = CTc + L - 1;
+    cx<T>* sH = reinterpret_cast<cx<T>*>(smem);                  // [(l * Nt + k)][Nr]
+    cx<T>* sW = sH + (size_t)L * Nt * Nr;                        // [Nr][Wc]
+    cx<T>* sP = sW + (size_t)Nr * Wc;                            // [k][WP]; reused as R [column][Nr]
+    const cx<T>* H = p.H + (long long)b * p.ld_H;
+    const cx<T>* Pil = p.Psi + (long long)b * p.ld_Psi;
+    const cx<T>* W = p.W + (long long)b * p.ld_W;
+    const int t0 = blockIdx.x * CTc;
+    for (int e = threadIdx.x; e < L * Nt * Nr; e += 256) sH[e] = H[e];                       // H(r, k, l) at r + Nr k + Nr Nt l
+    for (int e = threadIdx.x; e < Nr * Wc; e += 256) sW[e] = W[e];
+    for (int e = threadIdx.x; e < Nt * WP; e += 256) {
+        const int k = e % Nt, w = e / Nt, tau = t0 - (L - 1) + w;
+        cx<T> v = mk<T>(T(0), T(0));
+        if (tau >= 0 && tau < TT) v = Pil[k + (size_t)Nt * tau];
+        else if (tau < 0 && -tau < TT) v = conj(Pil[k + (size_t)Nt * (-tau)]);                // row l of toeplitz(s_k) below the diagonal
+        sP[(size_t)k * WP + w] = v;
+    }
+    __syncthreads();
+    const int c = threadIdx.x % CTc, rg = threadIdx.x / CTc, t = t0 + c;
+    T ar[8] = {}, ai[8] = {};
+    for (int l = 0; l < L; ++l) {
+        const cx<T>* pw = sP + (c + (L - 1) - l);
+        const cx<T>* hh = sH + (size_t)l * Nt * Nr + 8 * rg;
+        for (int k = 0; k < Nt; ++k) {
+            const cx<T> ps = pw[(size_t)k * WP];
+            const cx<T>* hv = hh + (size_t)k * Nr;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) cmac<T>(ar[u], ai[u], hv[u].re, hv[u].im, ps.re, ps.im);
+        }
+    }
+    __syncthreads();                                             // the pilot window is dead: its space takes R
+    cx<T>* sR = sP;
+    if (t < TT) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int r = 8 * rg + u;
+            T re = ar[u], im = ai[u];
+            if (p.Ynl) p.Ynl[(size_t)b * Nr * TT + (size_t)t * Nr + r] = mk<T>(re, im);       // noiseless Y (proposed_hbf.m:14-20)
+            if (p.N) { const cx<T> nv = p.N[(long long)b * p.ld_N + r + (size_t)Nr * t]; re += nv.re; im += nv.im; }   // R = Y + N (:22)
+            sR[(size_t)c * Nr + r] = mk<T>(re, im);
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < Wc * CTc; e += 256) {
+        const int q = e % Wc, cc = e / Wc, tt = t0 + cc;
+        if (tt >= TT) break;
+        T re = 0, im = 0;
+        for (int r = 0; r < Nr; ++r) { const cx<T> w = sW[r + (size_t)Nr * q], x = sR[(size_t)cc * Nr + r]; cmac<T>(re, im, w.re, -w.im, x.re, x.im); }
+        T om = T(1);
+        if (p.perm) {          // Omega(indices(1:Lr), t) = 1 with indices = randperm(Wc)  (proposed_hbf.m:36-41)
+            om = T(0);
+            const int* pr = p.perm + (long long)b * p.ld_perm + (size_t)tt * Wc;
+            for (int j = 0; j < p.Lr; ++j) if (pr[j] == q + 1) om = T(1);
+            if (p.Omega) p.Omega[(size_t)b * Wc * TT + (size_t)tt * Wc + q] = om;
+        }
+        if (p.Yout) p.Yout[(size_t)b * Wc * TT + (size_t)tt * Wc + q] = mk<T>(om * re, om * im);     // Omega .* (W_e' R) (:42)
     }
 }
 
@@ -287,7 +367,9 @@ static int run_channel(Handle* h, int mem, int L, int Mr, int Mt, int ncl, int n
         }
         p.normals = dn; p.uniforms = du;
         p.H = dev[0]; p.Zbar = dev[1]; p.Ar = dev[2]; p.At = dev[3]; p.Dr = dev[4]; p.Dt = dev[5];
-        JSTSP_LAUNCH(h, PK_OTHER, (k_channel<T><<<batch, 256, 2 * sizeof(double) * Np, h->stream>>>(p)));
+        const size_t sm_ch = sizeof(double) * 2 * ((size_t)Np + (size_t)Np * Mr + (size_t)Np * Mt + Gr + Gt);
+        { int rc = set_smem(h, k_channel<T>, sm_ch); if (rc) return rc; }
+        JSTSP_LAUNCH(h, PK_OTHER, (k_channel<T><<<batch, 256, sm_ch, h->stream>>>(p)));
         JSTSP_CUDA(h, cudaGetLastError());
         if (host) {
             for (int k = 0; k < 6; ++k) if (outs[k]) JSTSP_CUDA(h, cudaMemcpyAsync(outs[k], dev[k], ns[k] * sizeof(cx<T>), cudaMemcpyDeviceToHost, h->stream));
@@ -353,9 +435,17 @@ static int run_measure(Handle* h, int mem, const jstsp_meas_desc* d, const void*
         p.Omega = Omega ? (host ? ar.take<T>(nY) : (T*)Omega) : nullptr;
         p.Ynl = Ynl ? (host ? ar.take<cx<T>>(nYn) : (cx<T>*)Ynl) : nullptr;
         if (!pass) { int rc = ensure_workspace(h, ar.off); if (rc) return rc; continue; }
-        int tiles = (TT + 31) / 32; if (tiles > 64) tiles = 64; if (tiles < 1) tiles = 1;
-        dim3 grid(tiles, batch);
-        JSTSP_LAUNCH(h, PK_OTHER, (k_measure<T><<<grid, 256, 0, h->stream>>>(p)));
+        const int RG = Nr / 8, CTc = (Nr % 8 == 0 && RG >= 1 && 256 % RG == 0) ? 256 / RG : 0;
+        const size_t sm_t = CTc ? sizeof(cx<T>) * ((size_t)L * Nt * Nr + (size_t)Nr * Wc + std::max((size_t)Nt * (CTc + L - 1), (size_t)CTc * Nr)) : 0;
+        if (CTc && d->psi_mode == 1 && !Psibar && !We && sm_t <= h->smem_optin && getenv("JSTSP_MEASURE_SIMPLE") == nullptr) {
+            { int rc = set_smem(h, k_measure_tiled<T>, sm_t); if (rc) return rc; }
+            dim3 grid(ceil_div(TT, CTc), batch);
+            JSTSP_LAUNCH(h, PK_OTHER, (k_measure_tiled<T><<<grid, 256, sm_t, h->stream>>>(p)));
+        } else {
+            int tiles = (TT + 31) / 32; if (tiles > 64) tiles = 64; if (tiles < 1) tiles = 1;
+            dim3 grid(tiles, batch);
+            JSTSP_LAUNCH(h, PK_OTHER, (k_measure<T><<<grid, 256, 0, h->stream>>>(p)));
+        }
         JSTSP_CUDA(h, cudaGetLastError());
         if (host) {
             if (Yout) JSTSP_CUDA(h, cudaMemcpyAsync(Yout, p.Yout, nY * sizeof(cx<T>), cudaMemcpyDeviceToHost, h->stream));

@@ -168,23 +168,44 @@ class TrialPipeline:
         self.Dt = synth._dft(s.Nt, s.Nt, self.device, torch.complex128).T.contiguous().to(cd)[None]
 
     def run_from_draws(self, coef, u_r, u_t, noise_unit, sym_idx, mask_rank, sigma2, imax=100, keep=False):
-        s, dev, h = self.s, self.device, self.eng.h
-        cd, rd, dt = _CD[self.precision], _RD[self.precision], _DT[self.precision]
-        b = coef.shape[0]
-        Nr, Nt, L, M, P = s.Nr, s.Nt, s.L, s.M, s.P
-        self.eng._bind_stream()
-        lib = _lib.lib
+        """The trial-loop body on explicit draws (synth.draw's tensors; used by the parity tests, which hand the same draws to the fp64 restatement)."""
+        s, dev = self.s, self.device
+        cd = _CD[self.precision]
         # draws in the reference's order (wideband_mmwave_channel.m:19-22): (randn, randn) and (rand, rand) per (tap, ray)
         normals = (torch.view_as_real(coef.to(torch.complex128)) * (2.0 ** 0.5)).contiguous()           # (b, L, Np, 2)
         uniforms = torch.stack([u_r.double(), u_t.double()], dim=-1).contiguous()
-        H = torch.empty(b, L, Nt, Nr, dtype=cd, device=dev)
-        Zbar = torch.empty(b, P, Nr, dtype=cd, device=dev)
-        h.check(lib.jstsp_wideband_mmwave_channel(h.ptr, dt, _lib.DEVICE, L, Nr, Nt, s.ncl, s.nray, Nr, Nt, b, _p(normals), _p(uniforms),
-                                                  _p(H), _p(Zbar), None, None, None, None))
         qam = torch.tensor([1 + 1j, -1 + 1j, 1 - 1j, -1 - 1j], dtype=torch.complex128, device=dev) / (2.0 ** 0.5)   # qam4mod.m:7-8
         pilots = qam[sym_idx].transpose(1, 2).contiguous().to(cd)                                        # (b, M, Nt): row k = s_k
         noise = (noise_unit.to(torch.complex128) * torch.sqrt(sigma2.double())[:, None, None]).transpose(1, 2).contiguous().to(cd)   # :60
         perm = (mask_rank.argsort(dim=1).transpose(1, 2) + 1).to(torch.int32).contiguous()               # (b, M, Nr): rows in sampling order
+        return self._body(normals, uniforms, pilots, noise, perm, imax, keep)
+
+    def device_draws(self, batch, snr_db, seed, first_trial=0):
+        """Draws of the global trials [first_trial, first_trial + batch) from the library's Philox4x32-10 generator (csrc/rng.cu), keyed by
+        (seed, global trial): normals, uniforms, pilots, noise, perm in the layouts jstsp_wideband_mmwave_channel / jstsp_measure read, and sigma2."""
+        s, dev, h = self.s, self.device, self.eng.h
+        cd, dt = _CD[self.precision], _DT[self.precision]
+        b, Np = int(batch), s.ncl * s.nray
+        snr = torch.as_tensor(snr_db, dtype=torch.float64).to(dev).expand(b) if not torch.is_tensor(snr_db) else snr_db.to(dev).double()
+        sigma2 = (10.0 ** (-snr / 10.0)).contiguous()                                                    # plot_errorVSsnr.m:49
+        normals = torch.empty(b, s.L, Np, 2, dtype=torch.float64, device=dev); uniforms = torch.empty_like(normals)
+        pilots = torch.empty(b, s.M, s.Nt, dtype=cd, device=dev); noise = torch.empty(b, s.M, s.Nr, dtype=cd, device=dev)
+        perm = torch.empty(b, s.M, s.Nr, dtype=torch.int32, device=dev)
+        self.eng._bind_stream()
+        h.check(_lib.lib.jstsp_draw_trials(h.ptr, dt, int(seed), int(first_trial), b, s.Nr, s.Nt, s.L, Np, s.M, _p(sigma2), _p(normals), _p(uniforms), _p(pilots), _p(noise), _p(perm)))
+        return normals, uniforms, pilots, noise, perm, sigma2
+
+    def _body(self, normals, uniforms, pilots, noise, perm, imax, keep):
+        s, dev, h = self.s, self.device, self.eng.h
+        cd, rd, dt = _CD[self.precision], _RD[self.precision], _DT[self.precision]
+        b = normals.shape[0]
+        Nr, Nt, L, M, P = s.Nr, s.Nt, s.L, s.M, s.P
+        self.eng._bind_stream()
+        lib = _lib.lib
+        H = torch.empty(b, L, Nt, Nr, dtype=cd, device=dev)
+        Zbar = torch.empty(b, P, Nr, dtype=cd, device=dev)
+        h.check(lib.jstsp_wideband_mmwave_channel(h.ptr, dt, _lib.DEVICE, L, Nr, Nt, s.ncl, s.nray, Nr, Nt, b, _p(normals), _p(uniforms),
+                                                  _p(H), _p(Zbar), None, None, None, None))
         md = MeasDesc()
         md.Nr, md.Nt, md.L, md.T, md.Wc, md.Lr, md.psi_mode, md.Tp, md.batch = Nr, Nt, L, M, Nr, s.Mr, 1, M, b
         md.ld_H, md.ld_N, md.ld_Psi, md.ld_W = Nr * Nt * L, Nr * M, Nt * M, 0
@@ -199,12 +220,14 @@ class TrialPipeline:
         self.eng._bind_stream()
         h.check(lib.jstsp_nmse(h.ptr, dt, _lib.DEVICE, Nr, P, b, _p(S), Nr * P, _p(Zbar), Nr * P, _p(nm)))    # :138-141
         if keep:
-            return dict(nmse=nm, S=S, Zbar=Zbar, subY=subY, Omega=Omega, H=H, tau_Y=tau_Y, tau_Z=tau_Z, rho=rho, pilots=pilots)
+            return dict(nmse=nm, S=S, Zbar=Zbar, subY=subY, Omega=Omega, H=H, tau_Y=tau_Y, tau_Z=tau_Z, rho=rho, pilots=pilots,
+                        normals=normals, uniforms=uniforms, noise=noise, perm=perm)
         return nm
 
     def run(self, batch, snr_db, seed, first_trial=0, imax=100, keep=False):
-        from . import synth
-        return self.run_from_draws(*synth.draw(self.s, batch, snr_db, seed, first_trial, self.device), imax=imax, keep=keep)
+        """One batch of Monte-Carlo trials, draws included, entirely through the library (no torch arithmetic between the calls)."""
+        normals, uniforms, pilots, noise, perm, _ = self.device_draws(batch, snr_db, seed, first_trial)
+        return self._body(normals, uniforms, pilots, noise, perm, imax, keep)
 
 
 def shard_range(n_trials, rank, world):

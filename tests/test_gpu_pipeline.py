@@ -40,6 +40,33 @@ def test_trial_pipeline(name, precision, tol):
     assert abs(float(out["nmse"][0]) - est.nmse(S1.astype(np.complex128), Zb)) < 1e-5 * max(est.nmse(S1.astype(np.complex128), Zb), 1e-3)
 
 
+def test_trial_pipeline_with_device_draws():
+    """The same body fed by the library's own generator (jstsp_draw_trials, what TrialPipeline.run and the bench's pipeline leg use): the draws
+    it produced are read back and handed to the fp64 torch restatement, which must reproduce every intermediate."""
+    from jstsp19_b200 import synth
+    from jstsp19_b200.engine import TrialPipeline
+    shape, imax = synth.METRIC, 20
+    pipe = TrialPipeline(shape, 0, "f32")
+    snr = torch.tensor([5.0, -4.0, 12.0])
+    out = pipe.run(3, snr, seed=77, first_trial=5, imax=imax, keep=True)
+    sigma2 = (10.0 ** (-snr.double() / 10.0)).cuda()
+    coef = torch.complex(out["normals"][..., 0], out["normals"][..., 1]) / 2.0 ** 0.5
+    noise_unit = (out["noise"].to(torch.complex128) / torch.sqrt(sigma2)[:, None, None]).transpose(1, 2)
+    p = out["pilots"].transpose(1, 2)
+    sym = ((p.real < 0).long() + 2 * (p.imag < 0).long())
+    rank = torch.empty_like(out["perm"], dtype=torch.long)
+    rank.scatter_(2, (out["perm"].long() - 1), torch.arange(shape.Nr, device="cuda").expand_as(rank))    # rank[b, m, row] = position in the sampling order
+    ref = synth.build_from_draws(shape, coef, out["uniforms"][..., 0], out["uniforms"][..., 1], noise_unit, sym, rank.transpose(1, 2), sigma2, cdtype=torch.complex128)
+    c = lambda t: t.cpu().numpy()
+    assert np.array_equal(c(out["Omega"]).astype(np.float64), c(ref["Omega"]))
+    assert (c(ref["Omega"]).sum(axis=2) == shape.Mr).all()
+    assert _rel(c(out["Zbar"]), c(ref["Zbar"])) < 3e-6 and _rel(c(out["subY"]), c(ref["subY"])) < 3e-6
+    for k in ("tau_Y", "tau_Z", "rho"):
+        np.testing.assert_allclose(c(out[k]), c(ref[k]), rtol=2e-5)
+    again = pipe.run(3, snr, seed=77, first_trial=5, imax=imax)
+    assert torch.equal(again, out["nmse"])
+
+
 def test_pipeline_is_gpu_count_invariant():
     """Trials are keyed by (seed, first trial): a shard gives the same NMSEs whatever else runs beside it."""
     from jstsp19_b200 import synth
