@@ -18,9 +18,18 @@ $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
 
 clean:
-	rm -rf build/obj $(LIB)
+	rm -rf build/obj build/racecheck $(LIB)
 
-.PHONY: all clean
+# sanitizer build: the streamed-ring kernels release their slots with a CTA barrier (stream_core.cuh), selected by JSTSP_LIB at load time
+RCDIR := build/racecheck
+RCOBJS := $(patsubst $(CSRC)/%.cu,$(RCDIR)/%.o,$(SRCS))
+$(RCDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) include/jstsp_b200.h
+	@mkdir -p $(RCDIR)
+	$(NVCC) $(NVCCFLAGS) -DJSTSP_PIPE_CTA_SYNC -c $< -o $@ 2> $(RCDIR)/$*.ptxas.log || (cat $(RCDIR)/$*.ptxas.log; exit 1)
+racecheck-lib: $(RCOBJS)
+	$(NVCC) $(ARCH) -shared -o $(RCDIR)/libjstsp_b200.so $(RCOBJS) -lcudart
+
+.PHONY: all clean racecheck-lib
 
 # ---- MEX gateways against the in-repo mex.h shim (unit-test build; a MATLAB user runs `mex -R2018a`) ----
 MEXDIR  := jstsp19_b200/mex

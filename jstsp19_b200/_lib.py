@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjstsp_b200.so")
+LIB_PATH = os.environ.get("JSTSP_LIB") or os.path.join(_HERE, "libjstsp_b200.so")      # JSTSP_LIB: another build of the same library (the sanitizer variant of `make racecheck-lib`)
 
 F32, F64 = 0, 1
 HOST, DEVICE = 0, 1

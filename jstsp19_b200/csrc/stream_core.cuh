@@ -143,7 +143,7 @@ template <typename T> __device__ __forceinline__ void store_pair(cx<T>* __restri
 
 // One streaming contraction.  All threads of the CTA must call start() and run().
 //   ring   : shared memory, StreamRing<T>::bytes(width, STAGES), 16-byte aligned
-//   bars   : STAGES mbarriers followed by STAGES int arrival counters - use PipeBars<STAGES> and
+//   bars   : STAGES "full" mbarriers followed by STAGES "empty" mbarriers - use PipeBars<STAGES> and
 //            pipe_bars_init() once per kernel
 //   it0    : running stage counter of this CTA (carried across calls so barrier phases stay consistent)
 //   Big    : global pointer at (first output of this CTA's tile, column 0); ld in elements
@@ -152,7 +152,7 @@ template <typename T> __device__ __forceinline__ void store_pair(cx<T>* __restri
 template <int STAGES>
 struct __align__(8) PipeBars {
     uint64_t full[STAGES];
-    int cnt[STAGES];
+    uint64_t empty[STAGES];     // one arrival per warp per use of the slot
 };
 // Initialise the barriers and zero the ring (so that never-written ring bytes are finite), then make
 // the generic-proxy writes visible to the async proxy before the first bulk copy lands.
@@ -160,7 +160,7 @@ struct __align__(8) PipeBars {
 template <int STAGES>
 __device__ __forceinline__ void pipe_bars_init(PipeBars<STAGES>& pb, void* ring, size_t ring_bytes, bool zero_ring) {
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&pb.full[s], 1); pb.cnt[s] = 0; }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&pb.full[s], 1); mbar_init(&pb.empty[s], kWarps); }
         mbar_fence_init();
     }
     if (zero_ring) {
@@ -175,7 +175,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 template <typename T, int STAGES = kStages>
 struct StreamPipe {
     static constexpr int kSC = stage_cols<T>();
-    cx<T>* ring; uint64_t* bars; int* cnt; const cx<T>* big; long long ld; int width, nvalid, ncols, nst; uint32_t it0;
+    cx<T>* ring; uint64_t* bars; uint64_t* empty; const cx<T>* big; long long ld; int width, nvalid, ncols, nst; uint32_t it0;
     bool contig;    // the reduction columns are back to back in global memory (ld == nvalid): one bulk copy per stage
 
     __device__ __forceinline__ void issue(int t) {   // called by ONE thread
@@ -200,7 +200,7 @@ struct StreamPipe {
     }
     __device__ __forceinline__ void start(cx<T>* ring_, uint64_t* bars_, uint32_t it0_, const cx<T>* big_, long long ld_, int width_, int nvalid_,
                                           int ncols_) {
-        ring = ring_; bars = bars_; cnt = reinterpret_cast<int*>(bars_ + STAGES); it0 = it0_; big = big_; ld = ld_; nvalid = nvalid_; ncols = ncols_;
+        ring = ring_; bars = bars_; empty = bars_ + STAGES; it0 = it0_; big = big_; ld = ld_; nvalid = nvalid_; ncols = ncols_;
         contig = (ld_ == (long long)nvalid_);
         width = contig ? nvalid_ : width_;          // ring row pitch
         nst = (ncols + kSC - 1) / kSC;
@@ -232,21 +232,26 @@ struct StreamPipe {
                     acc.mac(lre + (size_t)c * RP, lim + (size_t)c * RP, b0, b1);
                 }
             }
-            // release the slot: the LAST warp to finish it refills it (no CTA-wide barrier per stage,
-            // warps may run up to STAGES-1 stages apart)
-            // Ordering: the warp's reads of the slot precede the (release) fence, the counter RMWs of all warps form one
-            // modification order, and the refilling thread's (acquire) fence follows its RMW - so every read of the slot
-            // happens before the bulk copy that overwrites it.  compute-sanitizer racecheck does not model this handshake
-            // (it tracks barriers, not atomics) and reports the slot reads against the refill; memcheck is clean.
+            // release the slot: every warp arrives on the slot's "empty" mbarrier once its reads are done (the proxy fence orders those
+            // generic-proxy reads before the async-proxy refill); thread 0 refills a slot one stage late, after waiting for that barrier,
+            // so no CTA-wide barrier is needed per stage and warps may run up to STAGES-1 stages apart.
+#ifdef JSTSP_PIPE_CTA_SYNC
+            // sanitizer build (make racecheck-lib): compute-sanitizer racecheck models CTA barriers but neither mbarriers nor the async proxy, so
+            // it reports every slot read against the refill whatever the handshake.  This variant releases the slot with a CTA-wide barrier, which
+            // the tool does follow: a clean run of it shows that no OTHER shared-memory hazard hides behind those reports.
+            __syncthreads();
+            if (threadIdx.x == 0 && t + STAGES < nst) issue(t + STAGES);
+            continue;
+#endif
             __syncwarp();
             if (lane == 0) {
-                __threadfence_block();
-                const int old = atomicAdd(&cnt[slot], 1);
-                if (old == kWarps - 1) {
-                    __threadfence_block();
-                    cnt[slot] = 0;
-                    if (t + STAGES < nst) issue(t + STAGES);
-                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[slot])) : "memory");
+            }
+            if (threadIdx.x == 0 && t >= 1 && t - 1 + STAGES < nst) {
+                const uint32_t gp = it0 + t - 1;
+                mbar_wait(&empty[gp % STAGES], (gp / STAGES) & 1u);
+                issue(t - 1 + STAGES);
             }
         }
         acc.store(ar, ai);

@@ -5,7 +5,8 @@
 
 Each call is also compared with the fp64 oracle (test infrastructure), so a run that is clean but wrong still fails.
 Groups: dense (proposed_algorithm*, svt family, sparse_admm, OMP, SOMP, VAMP, parameters), tc (the tcgen05 / TMA kernels:
-Psi-domain ADMM at the metric shape, 3xTF32 dense ADMM, Kronecker OMP screen)."""
+Psi-domain ADMM at the metric shape, 3xTF32 dense ADMM, Kronecker OMP screen), large (the large-array route of csrc/admm_large.cuh at a
+small shape, the on-device draws, the tiled measurement kernel)."""
 import os
 import sys
 
@@ -79,7 +80,23 @@ def tc():
     print("tc group ok")
 
 
+def large():
+    import torch
+    from jstsp19_b200 import synth
+    from jstsp19_b200._lib import default_handle
+    from jstsp19_b200.engine import TrialPipeline
+    sh = fx.Shape(Nt=64, Nr=32, L=3, Mr=4, T=8)
+    t = fx.make_trial(sh, 5.0, 99)
+    S0, Y0, _ = est.proposed_algorithm_structured(t["subY"], t["Omega"], t["A"], t["B"], 3, t["tau_Y"], t["tau_Z"], t["rho"], "approximate", want_conv=False)
+    S1, Y1 = jb.proposed_algorithm_pilots(t["subY"], t["Omega"], t["A"], t["Dt"], t["pilots"], sh.L, 3, t["tau_Y"], t["tau_Z"], t["rho"], "approximate", precision="f32", nargout=2)
+    assert default_handle().last_path == 3 and rel(S1, S0) < 5e-5 and rel(Y1, Y0) < 5e-5, (default_handle().last_path, rel(S1, S0), rel(Y1, Y0))
+    pipe = TrialPipeline(synth.Shape(Nt=64, Nr=16, L=2, Mr=4, T=2), 0, "f32")
+    nm = pipe.run(3, 5.0, seed=11, first_trial=2, imax=2)
+    assert bool(torch.isfinite(nm).all())
+    print("large group ok")
+
+
 if __name__ == "__main__":
-    groups = sys.argv[1:] or ["dense", "tc"]
+    groups = sys.argv[1:] or ["dense", "tc", "large"]
     for g in groups:
-        {"dense": dense, "tc": tc}[g]()
+        {"dense": dense, "tc": tc, "large": large}[g]()
