@@ -35,10 +35,9 @@ struct SvtP {
 constexpr int kEigThreads = 256;    // one 2 x 2 block of a 32 x 32 problem per thread and rotation step
 
 template <typename T>
-__global__ void __launch_bounds__(kEigThreads) k_weights(SvtP<T> p) {
-    extern __shared__ __align__(16) unsigned char smem[];
+__device__ __forceinline__ void weights_body(const SvtP<T>& p, int b, unsigned char* smem) {
     JacobiSmem sm; sm.carve(smem, p.N);
-    const int b = blockIdx.x, n = p.N, nn = n * n;
+    const int n = p.N, nn = n * n;
     const double* g = p.gram + (size_t)b * p.nmc * 2 * nn;
     for (int t = threadIdx.x; t < nn; t += blockDim.x) {
         double re = 0.0, im = 0.0;
@@ -61,6 +60,11 @@ __global__ void __launch_bounds__(kEigThreads) k_weights(SvtP<T> p) {
     const double tau = p.rho ? p.tau[b] / p.rho[b] : p.tau[b];
     cx<T>* W = p.W + (size_t)b * nn;
     svt_weights_block(sm, n, tau, [&](int i, int j, double re, double im) { W[i + n * j] = mk<T>((T)re, (T)im); });
+}
+template <typename T>
+__global__ void __launch_bounds__(kEigThreads) k_weights(SvtP<T> p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    weights_body<T>(p, blockIdx.x, smem);
 }
 
 // sigma_max^2 of the summed partial Gram `which` (0: X - Htrue, 1: Htrue); grid (1, batch)
@@ -105,9 +109,8 @@ __global__ void __launch_bounds__(kThreads) k_gram_of(SvtP<T> p, const cx<T>* sr
 }
 
 template <typename T, int MODE>
-__global__ void __launch_bounds__(kThreads) k_svt_step(SvtP<T> p) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int b = blockIdx.y, chunk = blockIdx.x, N = p.N, RP = p.RP, MC = p.MC;
+__device__ __forceinline__ void step_body(const SvtP<T>& p, int b, int chunk, unsigned char* smem) {
+    const int N = p.N, RP = p.RP, MC = p.MC;
     const int c0 = chunk * MC, ncols = (p.M - c0) < MC ? (p.M - c0) : MC;
     const bool conv = (MODE == MODE_MCADMM) && p.convd != nullptr;
     T* Zre = reinterpret_cast<T*>(smem);
@@ -180,6 +183,30 @@ __global__ void __launch_bounds__(kThreads) k_svt_step(SvtP<T> p) {
     __syncthreads();
     gram_partial<T>(Nre, Nim, RP, N, ncols, p.gram + ((size_t)b * p.nmc + chunk) * 2 * N * N);
     if (conv) gram_partial<T>(Ere, Eim, RP, N, ncols, p.cgram + (((size_t)b * 2 + 0) * p.nmc + chunk) * 2 * N * N);
+}
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kThreads) k_svt_step(SvtP<T> p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    step_body<T, MODE>(p, blockIdx.y, blockIdx.x, smem);
+}
+// One CTA per trial runs the whole solve (mc_svt.m:7-10 / mc_admm.m:20-27): per iteration the Jacobi solve of the Mr x Mr Gram matrix in shared
+// memory, then the fused step over the trial's column chunks.  One launch per call instead of two per iteration; the state (a few hundred KB per
+// trial) stays L2-resident between iterations, and co-resident CTAs overlap one trial's latency-bound eigen-solve with another's streaming step.
+// The two phases share the same shared memory; partial Gram matrices and W travel through global memory as in the two-kernel form, so the
+// arithmetic - and every result bit - is the same.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kThreads, 4) k_svt_persist(SvtP<T> p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int b = blockIdx.x;
+    for (int it = 0; it < p.imax; ++it) {
+        p.iter = it;
+        weights_body<T>(p, b, smem);
+        __syncthreads();
+        for (int chunk = 0; chunk < p.nmc; ++chunk) {
+            step_body<T, MODE>(p, b, chunk, smem);
+            __syncthreads();
+        }
+    }
 }
 
 template <typename T>
@@ -280,7 +307,18 @@ static int run_svt_family(Handle* h, int mode, int mem, int N, int M, int batch,
                 JSTSP_LAUNCH(h, PK_OTHER, (k_gram_of<T><<<grid, kThreads, sm_gram, st>>>(q, q.Htrue, q.ld_H, q.cgram, 2, 1)));
                 JSTSP_LAUNCH(h, PK_OTHER, (k_mc_conv<T><<<nb, 128, sm_j, st>>>(q, 1)));
             }
-            for (int it = 0; it < imax; ++it) {
+            const bool persist = !want_conv && imax > 0 && kEigThreads == kThreads && getenv("JSTSP_SVT_PERSIST_OFF") == nullptr;
+            if (persist) {
+                const size_t sm_p = sm_w > sm_step ? sm_w : sm_step;
+                if (mode == MODE_MCSVT) {
+                    if ((rc = set_smem(h, k_svt_persist<T, MODE_MCSVT>, sm_p))) return rc;
+                    JSTSP_LAUNCH(h, PK_SVT_STEP, (k_svt_persist<T, MODE_MCSVT><<<nb, kThreads, sm_p, st>>>(q)));
+                } else {
+                    if ((rc = set_smem(h, k_svt_persist<T, MODE_MCADMM>, sm_p))) return rc;
+                    JSTSP_LAUNCH(h, PK_SVT_STEP, (k_svt_persist<T, MODE_MCADMM><<<nb, kThreads, sm_p, st>>>(q)));
+                }
+            }
+            for (int it = 0; it < imax && !persist; ++it) {
                 q.iter = it;
                 JSTSP_LAUNCH(h, PK_EIG, (k_weights<T><<<nb, kEigThreads, sm_w, st>>>(q)));
                 if (mode == MODE_MCSVT) JSTSP_LAUNCH(h, PK_SVT_STEP, (k_svt_step<T, MODE_MCSVT><<<grid, kThreads, sm_step, st>>>(q)));
