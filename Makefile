@@ -18,7 +18,7 @@ $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
 
 clean:
-	rm -rf build/obj build/racecheck $(LIB)
+	rm -rf build/obj build/racecheck build/debug $(LIB)
 
 # sanitizer build: the streamed-ring kernels release their slots with a CTA barrier (stream_core.cuh), selected by JSTSP_LIB at load time
 RCDIR := build/racecheck
@@ -26,10 +26,18 @@ RCOBJS := $(patsubst $(CSRC)/%.cu,$(RCDIR)/%.o,$(SRCS))
 $(RCDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) include/jstsp_b200.h
 	@mkdir -p $(RCDIR)
 	$(NVCC) $(NVCCFLAGS) -DJSTSP_PIPE_CTA_SYNC -c $< -o $@ 2> $(RCDIR)/$*.ptxas.log || (cat $(RCDIR)/$*.ptxas.log; exit 1)
+# instrumented build of the persistent kernel (phase stamps / beacons / dumps of admm_mega.cuh) for tools/mega_*.py
+DBGDIR := build/debug
+DBGOBJS := $(patsubst $(CSRC)/%.cu,$(DBGDIR)/%.o,$(SRCS))
+$(DBGDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) include/jstsp_b200.h
+	@mkdir -p $(DBGDIR)
+	$(NVCC) $(NVCCFLAGS) -DJSTSP_MEGA_DEBUG=1 -c $< -o $@ 2> $(DBGDIR)/$*.ptxas.log || (cat $(DBGDIR)/$*.ptxas.log; exit 1)
+debug-lib: $(DBGOBJS)
+	$(NVCC) $(ARCH) -shared -o $(DBGDIR)/libjstsp_b200.so $(DBGOBJS) -lcudart
 racecheck-lib: $(RCOBJS)
 	$(NVCC) $(ARCH) -shared -o $(RCDIR)/libjstsp_b200.so $(RCOBJS) -lcudart
 
-.PHONY: all clean racecheck-lib
+.PHONY: all clean racecheck-lib debug-lib
 
 # ---- MEX gateways against the in-repo mex.h shim (unit-test build; a MATLAB user runs `mex -R2018a`) ----
 MEXDIR  := jstsp19_b200/mex

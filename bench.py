@@ -63,6 +63,20 @@ class ClockSampler:
         except Exception:
             self.p = None
 
+    def wait_first_sample(self, timeout_s=4.0):
+        """Block until nvidia-smi has written its first line: its start-up (NVML initialisation, a few hundred ms, longer on a cold box) holds driver
+        locks that stall CUDA launches, so it must be over before anything is timed (seen as 88 ms steps around 74 ms kernels in the first run on a fresh box)."""
+        if self.p is None:
+            return
+        t0 = time.time()
+        while time.time() - t0 < timeout_s:
+            try:
+                if os.path.getsize(self.f.name) > 0:
+                    return
+            except OSError:
+                return
+            time.sleep(0.05)
+
     def stop(self):
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
         if self.p is None:
@@ -360,12 +374,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local)          # started before the warm-up and waited for: its start-up must not fall into the timed region
+    clocks.wait_first_sample()
     for _ in range(warm):
         step()
     barrier()
     eng.h.profile(2)
     l0 = eng.launches
-    clocks = ClockSampler(local)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()

@@ -347,6 +347,14 @@ __device__ __forceinline__ void read_acc(uint32_t acc, uint32_t lane_base, int n
 }
 
 // developer hook (tools/mega_probe.py): clock64 stamps of the first trial of every CTA, 16 iterations x 8 slots per CTA
+// one copy of the 16 x 16 row-mixing product for its three call sites (code size: the kernel is instruction-fetch sensitive)
+__device__ __noinline__ void apply_a_shared(const cx<float>* __restrict__ Mx, const cx<float>* __restrict__ in, cx<float>* __restrict__ out) { psi::apply_a(Mx, in, out, NT); }
+// In-kernel instrumentation (phase stamps, hang beacons, data dumps) is compiled in only with -DJSTSP_MEGA_DEBUG=1 (`make debug-lib`, loaded through JSTSP_LIB
+// by tools/mega_probe.py / mega_beacon.py / mega_dump.py): the product kernel carries none of it (ncu: 14 % of all warp stalls were instruction-fetch stalls).
+#ifndef JSTSP_MEGA_DEBUG
+#define JSTSP_MEGA_DEBUG 0
+#endif
+#if JSTSP_MEGA_DEBUG
 #define MEGA_STAMP(slot, who)                                                                                                      \
     do {                                                                                                                           \
         if (p.dbg && p.dbg_kernel == 7 && (who) && b == (int)blockIdx.x && it < 16) p.dbg[((size_t)blockIdx.x * 16 + it) * 8 + (slot)] = clock64(); \
@@ -367,6 +375,14 @@ __device__ __forceinline__ void read_acc(uint32_t acc, uint32_t lane_base, int n
     do {                                                                                                                           \
         if (p.dbg && p.dbg_kernel == 8 && tid == 0 && c == 3 && b == (int)blockIdx.x && it < 16) p.dbg[((size_t)blockIdx.x * 16 + it) * 8 + (slot)] = clock64(); \
     } while (0)
+#else
+#define MEGA_STAMP(slot, who) do { } while (0)
+#define MEGA_BEACON(slot, value) do { } while (0)
+#define MEGA_STAMP3(kid, slot) do { } while (0)
+#define MEGA_DUMP_ON false
+#define MEGA_DUMP_ADD(idx, val) do { } while (0)
+#define MEGA_STAMP2(slot) do { } while (0)
+#endif
 __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const __grid_constant__ Maps maps, In in, int nb) {
     constexpr int NH = N / 2;
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -564,7 +580,7 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
                 mbar_wait(&gram_ready[w], gr_n[w] & 1); ++gr_n[w];
                 MEGA_STAMP(6, jt == 0);
                 // warm start from the previous eigenvectors of this trial; every 16th iteration (and the first of a trial) restarts cold
-                const bool warm = it > 0 && ((it + 1) % 16) != 0 && !(in.t1_red & 4);
+                const bool warm = it > 0 && ((it + 1) % 16) != 0 && !(JSTSP_MEGA_DEBUG && (in.t1_red & 4));
                 const bool jdbg = p.dbg && p.dbg_kernel == 9 && jt == 0 && b == (int)blockIdx.x && it < 16;
                 long long* jd = p.dbg + ((size_t)blockIdx.x * 16 + it) * 8;
                 if (jdbg) jd[0] = clock64();
@@ -599,7 +615,7 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
         cx<float>* U = reinterpret_cast<cx<float>*>(kop);     // phases R / S: N x NT work matrices (leading dimension LDU) over the idle pass-2 operand
         cx<float>* V = U + LDU * NT;
         uint32_t in_n = 0, accn[2] = {0, 0}, kop_n = 0, t1_n = 0, w_n[NSLOT] = {0, 0};
-        const bool narrow = (in.t1_red & 2) != 0;
+        const bool narrow = JSTSP_MEGA_DEBUG && (in.t1_red & 2) != 0;      // developer switch (instrumented build only): 128-bit stores
         if (tid < NT) { float sn, cs; sincospif(-2.0f * (float)tid / NT, &sn, &cs); tw[tid] = mk<float>(cs, sn); }
         auto in_slot = [&](uint32_t i) { return inr + (i % NIN) * SLOT; };
         auto in_wait = [&](uint32_t i) { mbar_wait(&in_full[i % NIN], (i / NIN) & 1); };
@@ -851,9 +867,9 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
                     tc::tc_fence_before();
                     wsync();
                     MEGA_STAMP3(11, 1);
-                    apply_a(AHs, U, V, NT);                  // A' T1'_l
+                    apply_a_shared(AHs, U, V);                  // A' T1'_l
                     wsync();
-                    apply_a(As, V, U, NT);                   // A A' T1'_l = (A Res_l) Dt' / scale^2 (Dt unitary)
+                    apply_a_shared(As, V, U);                   // A A' T1'_l = (A Res_l) Dt' / scale^2 (Dt unitary)
                     wsync();
                     MEGA_STAMP3(11, 2);
                     {   // operand image of tap l, written where phase G reads it (the state ring is idle between the phases F)
@@ -961,7 +977,7 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
                         if (!more) continue;
                         wsync();
                         MEGA_STAMP3(12, 1);
-                        apply_a(As, U, V, NT);               // A S_l                           (.m:58, left factor)
+                        apply_a_shared(As, U, V);               // A S_l                           (.m:58, left factor)
                         wsync();
                         MEGA_STAMP3(12, 2);
                         fft64<true, WSync>(V, U, tw, 0.125f * sc);    // scale (A S_l) Dt'
