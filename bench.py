@@ -57,6 +57,9 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        if os.environ.get("JSTSP_BENCH_NO_SMI"):      # developer aid: run without the nvidia-smi side process
+            self.p = None
+            return
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(gpu_index)],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
@@ -383,12 +386,24 @@ def main():
     l0 = eng.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    trace = [] if os.environ.get("JSTSP_BENCH_TRACE") else None     # developer aid: host time of every timed call and device time between step boundaries
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)] if trace is not None else None
     e0.record()
-    for _ in range(args.steps):
+    for k in range(args.steps):
+        if trace is not None:
+            evs[k].record(); th = time.perf_counter()
         step()
+        if trace is not None:
+            trace.append(dict(host_call_ms=(time.perf_counter() - th) * 1e3))
+    if trace is not None:
+        evs[args.steps].record()
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if trace is not None:
+        for k in range(args.steps):
+            trace[k]["device_ms_to_next_step"] = evs[k].elapsed_time(evs[k + 1])
+        print("[bench trace] " + json.dumps(trace), file=sys.stderr, flush=True)
     clk = clocks.stop()
     prof = eng.h.profile_read()
     eng.h.profile(0)

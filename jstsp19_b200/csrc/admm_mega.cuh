@@ -639,6 +639,7 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
                 const int b = (int)blockIdx.x + (pr + w) * (int)gridDim.x;
                 const float rho = (float)p.rho[b];
                 const float irho = 1.0f / rho, kap = rho / (rho + 1.0f);
+                const float d_off = 1.0f / (0.0f + 2.0f * rho), d_on = 1.0f / (1.0f + 2.0f * rho);
                 const float thr = (float)(p.tauS[b] / p.rho[b]);
                 const float sc = in.scale[b];
                 const cx<float>* Ws = Wsm + w * N * N;
@@ -735,7 +736,7 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
                             const float wr = xo[r].re - xs_r[r], wi = xo[r].im - xs_i[r];
                             const float cr = kap * (wr - irho * v2[r].re), ci = kap * (wi - irho * v2[r].im);
                             v2[r].re += rho * (cr - wr); v2[r].im += rho * (ci - wi);
-                            const float d = 1.0f / (((ombits >> r) & 1u ? 1.0f : 0.0f) + 2.0f * rho);                                     // iK1 (.m:20)
+                            const float d = ((ombits >> r) & 1u) ? d_on : d_off;                                                          // iK1 (.m:20): 1 / (Omega + 2 rho), Omega in {0, 1}
                             const float xr = (v1[r].re + sy[r].re + v2[r].re + rho * cr + rho * xs_r[r]) * d;                             // .m:38-40
                             const float xi = (v1[r].im + sy[r].im + v2[r].im + rho * ci + rho * xs_i[r]) * d;
                             v1[r].re -= rho * xr; v1[r].im -= rho * xi;                                                                   // .m:64: V1 + rho (Y - X)
@@ -901,6 +902,18 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
                 warp_arrive(r_done, lane);
                 if (tid == 0) MEGA_BEACON(1, it * 1000 + 300);
                 MEGA_STAMP(3, tid == 0);
+                // Res / V of tap 0 for phase S are requested now (V is last iteration's, Res is complete): their L2 latency hides behind phase G
+                const size_t off0 = (size_t)b * G * p.P;
+                cx<float> rn[4], vn[4];                       // Res / V of the next tap travel while this tap is processed
+                const int er = tid % N, ec = tid / N;          // this thread's elements of a tap: row er, columns ec + 16 j
+                auto fetch = [&](int l) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int t = er + G * (ec + 16 * j);
+                        if (er < G) { rn[j] = p.Res[off0 + (size_t)G * NT * l + t]; vn[j] = p.V[off0 + (size_t)G * NT * l + t]; }
+                    }
+                };
+                fetch(0);
                 // ================= phase G: G = (A Res) e per chunk, |G|^2 =================
                 double gg = 0.0;
                 for (int c = 0; c < nch; ++c) {
@@ -942,17 +955,6 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
                     wsync();
                 }
                 {
-                    const size_t off0 = (size_t)b * G * p.P;
-                    cx<float> rn[4], vn[4];                   // Res / V of the next tap travel while this tap is processed
-                    const int er = tid % N, ec = tid / N;      // this thread's elements of a tap: row er, columns ec + 16 j
-                    auto fetch = [&](int l) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int t = er + G * (ec + 16 * j);
-                            if (er < G) { rn[j] = p.Res[off0 + (size_t)G * NT * l + t]; vn[j] = p.V[off0 + (size_t)G * NT * l + t]; }
-                        }
-                    };
-                    fetch(0);
                     for (int l = 0; l < L; ++l) {
                         MEGA_STAMP3(12, 0);
                         const size_t off = off0 + (size_t)G * NT * l;
