@@ -379,10 +379,11 @@ def main():
 
     clocks = ClockSampler(local)          # started before the warm-up and waited for: its start-up must not fall into the timed region
     clocks.wait_first_sample()
+    eng.h.profile(1)                      # on during the warm-up as well: nothing about the profiling path is first-time inside the timed region
     for _ in range(warm):
         step()
     barrier()
-    eng.h.profile(2)
+    eng.h.profile(2)                      # restart the per-kernel sums
     l0 = eng.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

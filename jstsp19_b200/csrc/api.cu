@@ -100,6 +100,9 @@ extern "C" int jstsp_profile(jstsp_handle* h, int enable) {
     if (!h) return JSTSP_E_ARG;
     prof_collect(h);
     h->prof.on = enable != 0;
+    // the event pool is sized here, not at the first profiled launches: creating timing events inside a region that is being timed cost its
+    // first step ~10 ms (bench.py trace)
+    if (enable) while (h->prof.pool.size() < 1024) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) break; h->prof.pool.push_back(e); }
     if (enable == 2) { for (int i = 0; i < PK_COUNT; ++i) { h->prof.total_ms[i] = 0; h->prof.count[i] = 0; } }
     return JSTSP_OK;
 }
