@@ -375,6 +375,12 @@ __device__ __noinline__ void apply_a_shared(const cx<float>* __restrict__ Mx, co
     do {                                                                                                                           \
         if (p.dbg && p.dbg_kernel == 8 && tid == 0 && c == 3 && b == (int)blockIdx.x && it < 16) p.dbg[((size_t)blockIdx.x * 16 + it) * 8 + (slot)] = clock64(); \
     } while (0)
+// cycles thread 0 waits for a pair of state tiles: site 0 X,V1 / 1 V2,subY / 2 XV,G, per chunk, iteration 5 of the CTA's first trial
+#define MEGA_WAIT_BEGIN long long w0_ = (p.dbg && p.dbg_kernel == 15) ? clock64() : 0
+#define MEGA_WAIT_END(site)                                                                                                        \
+    do {                                                                                                                           \
+        if (p.dbg && p.dbg_kernel == 15 && tid == 0 && b == (int)blockIdx.x && it == 5 && c < 8) p.dbg[(size_t)blockIdx.x * 128 + c * 3 + (site)] = clock64() - w0_; \
+    } while (0)
 #else
 #define MEGA_STAMP(slot, who) do { } while (0)
 #define MEGA_BEACON(slot, value) do { } while (0)
@@ -382,6 +388,8 @@ __device__ __noinline__ void apply_a_shared(const cx<float>* __restrict__ Mx, co
 #define MEGA_DUMP_ON false
 #define MEGA_DUMP_ADD(idx, val) do { } while (0)
 #define MEGA_STAMP2(slot) do { } while (0)
+#define MEGA_WAIT_BEGIN do { } while (0)
+#define MEGA_WAIT_END(site) do { } while (0)
 #endif
 __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const __grid_constant__ Maps maps, In in, int nb) {
     constexpr int NH = N / 2;
@@ -663,7 +671,7 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
                     if (tid == 0) MEGA_BEACON(1, it * 1000 + 100 + c);
                     MEGA_STAMP2(0);
                     // ---- X, V1 -> Z = X - V1/rho (SVT input, .m:35) ----
-                    in_wait(in_n); in_wait(in_n + 1);
+                    { MEGA_WAIT_BEGIN; in_wait(in_n); in_wait(in_n + 1); MEGA_WAIT_END(0); }
                     MEGA_STAMP2(1);
                     tile_read8(in_slot(in_n), m, half, xo); tile_read8(in_slot(in_n + 1), m, half, v1);
                     ring_release(&in_empty[in_n % NIN], &in_empty[(in_n + 1) % NIN], lane);
@@ -725,7 +733,7 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
                     cx<float> v2[NH], kt[NH];
                     {
                         cx<float> sy[NH];
-                        in_wait(in_n); in_wait(in_n + 1);
+                        { MEGA_WAIT_BEGIN; in_wait(in_n); in_wait(in_n + 1); MEGA_WAIT_END(1); }
                         tile_read8(in_slot(in_n), m, half, v2); tile_read8(in_slot(in_n + 1), m, half, sy);
                         if (MEGA_DUMP_ON) { float sx = 0.f, sv = 0.f; for (int r = 0; r < NH; ++r) { sx += v2[r].re * v2[r].re + v2[r].im * v2[r].im; sv += sy[r].re * sy[r].re + sy[r].im * sy[r].im; } MEGA_DUMP_ADD(24 + c, sx); MEGA_DUMP_ADD(32 + c, sv); }
                         ring_release(&in_empty[in_n % NIN], &in_empty[(in_n + 1) % NIN], lane);
@@ -753,7 +761,7 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
                     // ---- XV = A V B (carried: XV += alpha G of the previous iteration) -> K - XV, the operand of pass 2 (.m:47) ----
                     {
                         cx<float> xv[NH], g[NH];
-                        in_wait(in_n); in_wait(in_n + 1);
+                        { MEGA_WAIT_BEGIN; in_wait(in_n); in_wait(in_n + 1); MEGA_WAIT_END(2); }
                         tile_read8(in_slot(in_n), m, half, xv); tile_read8(in_slot(in_n + 1), m, half, g);
                         if (MEGA_DUMP_ON) { float sx = 0.f, sv = 0.f; for (int r = 0; r < NH; ++r) { sx += xv[r].re * xv[r].re + xv[r].im * xv[r].im; sv += g[r].re * g[r].re + g[r].im * g[r].im; } MEGA_DUMP_ADD(40 + c, sx); MEGA_DUMP_ADD(48 + c, sv); }
                         ring_release(&in_empty[in_n % NIN], &in_empty[(in_n + 1) % NIN], lane);

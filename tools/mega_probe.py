@@ -9,6 +9,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ.setdefault("JSTSP_DBG_KERNEL", "7")
+os.environ.setdefault("JSTSP_LIB", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "build", "debug", "libjstsp_b200.so"))      # the instrumented build (make debug-lib)
 from jstsp19_b200 import _lib, synth  # noqa: E402
 from jstsp19_b200.engine import AdmmEngine  # noqa: E402
 
@@ -46,6 +47,13 @@ if os.environ["JSTSP_DBG_KERNEL"] in ("11", "12"):
     for it in (0, 1, 2, 5, 10):
         d = np.diff(t[:, it, :len(nm) + 1], axis=1)
         print(f"it {it:2d}: " + " | ".join(f"{n} {np.median(d[:, i]):7.0f}" for i, n in enumerate(nm)) + f" | total {np.median(t[:, it, len(nm)] - t[:, it, 0]):8.0f}")
+    sys.exit(0)
+if os.environ["JSTSP_DBG_KERNEL"] == "15":
+    w = t.reshape(ncta, 128)[:, :24].reshape(ncta, 8, 3)
+    print(f"variant {eng.h.last_variant}; cycles thread 0 waits for state tiles in phase F of iteration 5, median over {ncta} CTAs")
+    for c in range(8):
+        print(f"chunk {c}: X,V1 {np.median(w[:, c, 0]):7.0f} | V2,subY {np.median(w[:, c, 1]):7.0f} | XV,G {np.median(w[:, c, 2]):7.0f}")
+    print(f"sum per item: {np.median(w.sum(axis=(1, 2))):.0f}")
     sys.exit(0)
 if os.environ["JSTSP_DBG_KERNEL"] == "13":
     print(f"variant {eng.h.last_variant}; MMA warp in phase G, cycles, median over {ncta} CTAs")
