@@ -337,6 +337,7 @@ def main():
         return run_reference(args)
 
     import numpy as np
+    import numpy as np
     import torch
     import torch.distributed as dist
     from jstsp19_b200 import _lib, synth
@@ -436,6 +437,25 @@ def main():
         other = dict(entry="jstsp_proposed_algorithm (dense B, the reference function's own argument list)", value=nb * world * 3 / (float(dms.item()) * 1e-3),
                      unit=UNIT, ms_per_step=float(dms.item()) / 3, max_rel_diff_S_between_entries=float(diff.item()))
         del S2
+    # latency of ONE fp64 call of the reference function's own signature with host buffers at batch 1 - what a MEX gateway does per call of
+    # proposed_algorithm(subY, Omega, A, B, 100, tau_Y, tau_Z, rho, 'approximate') (proposed_algorithm.m:1): config 0 (plot_errorVSsnr.m defaults) and the metric shape
+    lat = None
+    if rank == 0 and not args.no_dense:
+        import jstsp19_b200 as jb
+        from jstsp19_b200 import synth as _synth
+        lat = {}
+        for name, shp in (("config0_32x140", _synth.Shape(Nt=4, Nr=32, L=4, Mr=4, T=35)), ("metric_16x1024", s)):
+            one = _synth.make_batch(shp, 1, torch.zeros(1, dtype=torch.float64), seed=5, device=dev)
+            T_ = lambda t: np.swapaxes(t.cpu().numpy(), -1, -2)[0]
+            a = (T_(one["subY"]).astype(np.complex128), T_(one["Omega"]).astype(np.float64), T_(one["A"]).astype(np.complex128), T_(one["B"]).astype(np.complex128), IMAX,
+                 float(one["tau_Y"][0]), float(one["tau_Z"][0]), float(one["rho"][0]), "approximate")
+            jb.proposed_algorithm(*a, precision="f64", nargout=2)
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter(); jb.proposed_algorithm(*a, precision="f64", nargout=2); ts.append((time.perf_counter() - t0) * 1e3)
+            lat[name] = dict(ms_per_call=sorted(ts)[1], shape=[shp.Nr, shp.M, shp.Nr, shp.P])
+            del one
+        lat["note"] = "fp64, JSTSP_HOST buffers, batch 1, Imax = 100, median of 3 calls, host wall clock (H2D, solve, D2H of S and Y inside)"
     data.pop("B", None)
 
     # parity / sanity: NMSE of this rank's trials, reduced over ranks (the one NCCL exchange of a sweep point)
@@ -624,7 +644,7 @@ def main():
                             parallelism=f"trials sharded over {world} GPU(s), one NCCL all-reduce of NMSE sums"),
                 clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu,
                 algorithmic_gflop_per_estimate=F_est / 1e9, achieved_tflops_whole_step=F_est * value / 1e12,
-                nmse=stats, other_entry=other, pipeline=pipeline, secondary=secondary)
+                nmse=stats, other_entry=other, latency_f64_batch1=lat, pipeline=pipeline, secondary=secondary)
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -322,7 +322,8 @@ __global__ void __launch_bounds__(256) k_lg_qimg(const cx<float>* __restrict__ Q
     }
 }
 
-// ---- element-wise state update, W Z, the pass-2 operand and the next Gram matrix (proposed_algorithm.m:37-47,61-62) ------------------
+// ---- element-wise state update (the closing step of the previous iteration - XV += alpha G, C, V2: proposed_algorithm.m:60,62 - folded in; C is never
+//      stored), W Z, the pass-2 operand and the next Gram matrix (proposed_algorithm.m:37-47,61) -------------------------------------------------
 struct StateArgs {
     int N, M, last;
     const cx<float>* subY; long long ld_subY;
@@ -331,18 +332,19 @@ struct StateArgs {
     const cx<float>* W;                    // [b][N*N]
     cx<float> *X, *V1, *Y;                 // [b][M][N]; Y only written when last
     long long ld_Y;
-    const cx<float> *V2, *C, *Xs, *XV;
+    cx<float> *V2, *XV;                     // updated in place: the closing step of the previous iteration (proposed_algorithm.m:60,62 and XV += alpha G) is folded in here
+    const cx<float> *Xs, *Gm; const float* alpha;
     unsigned char* dimg; long long ld_dimg;    // [M / 32][split][m group][2N][8]
     double* gram;                              // [b][M / CPC][N*N][2]
 };
 // grid (M / CPC, nb), block 256: thread (ty, tx) owns rows 4 ty.., columns 4 tx.. of each 64-column tile
-__global__ void __launch_bounds__(256) k_lg_state(StateArgs s) {
+__global__ void __launch_bounds__(256, 2) k_lg_state(StateArgs s) {
     extern __shared__ __align__(16) unsigned char smem[];
     cx<float>* Ws = reinterpret_cast<cx<float>*>(smem);                 // [k][n] = W(n, k), 64 x 64 zero padded
     cx<float>* Zs = Ws + 64 * 64;                                       // [k][m] Z tile, then [i][m] Z' tile
     float* Ds = reinterpret_cast<float*>(Zs + 64 * 64);                 // [2N rows][65]
     const int b = blockIdx.y, N = s.N, N2 = 2 * N, tx = threadIdx.x % 16, ty = threadIdx.x / 16;
-    const float rho = (float)s.rho[b], irho = 1.f / rho;
+    const float rho = (float)s.rho[b], irho = 1.f / rho, kap = rho / (rho + 1.f), al = s.alpha[b];
     const size_t off = (size_t)b * s.M * N;
     for (int t = threadIdx.x; t < 64 * 64; t += 256) { const int n = t % 64, k = t / 64; Ws[t] = (n < N && k < N) ? s.W[(size_t)b * N * N + n + N * k] : mk<float>(0.f, 0.f); }
     double gr[4][4] = {}, gi[4][4] = {};
@@ -382,8 +384,14 @@ __global__ void __launch_bounds__(256) k_lg_state(StateArgs s) {
             for (int j = 0; j < 4; ++j) {
                 const int m = m0 + 4 * tx + j, n0 = 4 * ty;
                 const size_t idx = off + (size_t)m * N + n0;
-                cx<float> v1[4], v2[4], c[4], xs[4], xv[4], sy[4], x[4], y[4], zn[4];
-                ld4(s.V1 + idx, v1); ld4(s.V2 + idx, v2); ld4(s.C + idx, c); ld4(s.Xs + idx, xs); ld4(s.XV + idx, xv);
+                cx<float> v1[4], v2[4], c[4], xs[4], xv[4], sy[4], x[4], y[4], zn[4], gm[4], xp[4];
+                ld4(s.V1 + idx, v1); ld4(s.V2 + idx, v2); ld4(s.Xs + idx, xs); ld4(s.XV + idx, xv); ld4(s.Gm + idx, gm); ld4(s.X + idx, xp);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {             // close the previous iteration: XV += alpha G; C = rho/(rho+1) (X - Xs - V2/rho); V2 += rho (C - X + Xs)   (.m:60,62)
+                    xv[i] = mk<float>(xv[i].re + al * gm[i].re, xv[i].im + al * gm[i].im);
+                    c[i] = mk<float>(kap * (xp[i].re - xs[i].re - v2[i].re * irho), kap * (xp[i].im - xs[i].im - v2[i].im * irho));
+                    v2[i] = mk<float>(v2[i].re + rho * (c[i].re - xp[i].re + xs[i].re), v2[i].im + rho * (c[i].im - xp[i].im + xs[i].im));
+                }
                 ld4(s.subY + (long long)b * s.ld_subY + (size_t)m * N + n0, sy);
                 const float4 om = *reinterpret_cast<const float4*>(s.omega + (long long)b * s.ld_omega + (size_t)m * N + n0);
                 const float omv[4] = {om.x, om.y, om.z, om.w};
@@ -399,7 +407,7 @@ __global__ void __launch_bounds__(256) k_lg_state(StateArgs s) {
                     Ds[(2 * (n0 + i) + 1) * 65 + 4 * tx + j] = x[i].im - v2[i].im * irho - c[i].im - xv[i].im;
                     zn[i] = mk<float>(x[i].re - v1[i].re * irho, x[i].im - v1[i].im * irho);      // next SVT input
                 }
-                st4(s.X + idx, x); st4(s.V1 + idx, v1);
+                st4(s.X + idx, x); st4(s.V1 + idx, v1); st4(s.V2 + idx, v2); st4(s.XV + idx, xv);
                 if (s.last) st4(s.Y + (long long)b * s.ld_Y + (size_t)m * N + n0, y);
                 st4(Zs + (4 * tx + j) * 64 + n0, zn);
             }
@@ -487,22 +495,6 @@ __global__ void __launch_bounds__(256) k_lg_vstep(cx<float>* __restrict__ V, con
     V[i] = v;
     S[i] = mk<float>(soft1<float>(v.re, thr), soft1<float>(v.im, thr));
 }
-// XV += alpha G;  C = rho/(rho+1) (X - Xs - V2/rho);  V2 += rho (C - X + Xs)     (proposed_algorithm.m:60,62)
-__global__ void __launch_bounds__(256) k_lg_cupd(const cx<float>* __restrict__ X, const cx<float>* __restrict__ Xs, const cx<float>* __restrict__ Gm, cx<float>* __restrict__ XV,
-                                                 cx<float>* __restrict__ C, cx<float>* __restrict__ V2, const float* __restrict__ alpha, const double* __restrict__ rho_, size_t per) {
-    const int b = blockIdx.y;
-    const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (t >= per) return;
-    const float al = alpha[b], rho = (float)rho_[b], irho = 1.f / rho, f = rho / (rho + 1.f);
-    const size_t i = (size_t)b * per + t;
-    const cx<float> x = X[i], xs = Xs[i], g = Gm[i];
-    cx<float> xv = XV[i], v2 = V2[i];
-    XV[i] = mk<float>(xv.re + al * g.re, xv.im + al * g.im);
-    const cx<float> c = mk<float>(f * (x.re - xs.re - v2.re * irho), f * (x.im - xs.im - v2.im * irho));
-    C[i] = c;
-    V2[i] = mk<float>(v2.re + rho * (c.re - x.re + xs.re), v2.im + rho * (c.im - x.im + xs.im));
-}
-
 inline bool make_map_e(const unsigned short* E, int Mext, int groups_total, int box_cols, int box_groups, CUtensorMap* map) {
     auto enc = tc::encode_fn();
     if (!enc) return false;
@@ -535,7 +527,7 @@ static int run_large(Handle* h, const jstsp_admm_desc* d, int mem, const void* s
     const size_t SB = (size_t)lg_stage_bytes(N2);
     const size_t dimg_b = (size_t)(M / SC2) * SB, qimg_b = (size_t)L * (nkg / 4) * SB, part_f = (size_t)KS * L * 2 * Nt * N2, e_us = (size_t)nkg * Mext * 8;
     // trials per pass: ~0.3 GB of state and operands per trial at config 4
-    const size_t per_trial = 9 * NM * 8 + NM * 4 + dimg_b + qimg_b + part_f * 4 + e_us * 2 + (size_t)Nt * M * 8 + (size_t)ngram * 2 * N * N * 8 + 8 * GP * 8 + 4 * NLN * 8;
+    const size_t per_trial = 8 * NM * 8 + NM * 4 + dimg_b + qimg_b + part_f * 4 + e_us * 2 + (size_t)Nt * M * 8 + (size_t)ngram * 2 * N * N * 8 + 8 * GP * 8 + 4 * NLN * 8;
     int chunk = batch;
     if (h->max_chunk > 0 && chunk > h->max_chunk) chunk = h->max_chunk;
     size_t freeb = 0, totalb = 0;
@@ -543,10 +535,10 @@ static int run_large(Handle* h, const jstsp_admm_desc* d, int mem, const void* s
     const size_t budget = (freeb + h->ws_bytes) / 2;
     while (chunk > 1 && (size_t)chunk * per_trial > budget) chunk = (chunk + 1) / 2;
     if (chunk > 16) chunk = 16;
-    cx<float> *X, *V1, *V2, *C, *Xs, *XV, *Gm, *Yb, *sY, *dA, *dDt, *dPil, *T1c, *R1, *Res, *V, *S, *AR, *Q, *W;
+    cx<float> *X, *V1, *V2, *Xs, *XV, *Gm, *Yb, *sY, *dA, *dDt, *dPil, *T1c, *R1, *Res, *V, *S, *AR, *Q, *W;
     float *om, *scale, *part, *alpha; unsigned short* E; unsigned char *dimg, *qimg; double *rr, *gg, *gram, *Uprev, *dtau, *dtaus, *drho; int* bad;
     auto layout = [&](Arena& a, int nb) {
-        X = a.take<cx<float>>(NM * nb); V1 = a.take<cx<float>>(NM * nb); V2 = a.take<cx<float>>(NM * nb); C = a.take<cx<float>>(NM * nb);
+        X = a.take<cx<float>>(NM * nb); V1 = a.take<cx<float>>(NM * nb); V2 = a.take<cx<float>>(NM * nb);
         Xs = a.take<cx<float>>(NM * nb); XV = a.take<cx<float>>(NM * nb); Gm = a.take<cx<float>>(NM * nb);
         Yb = host ? a.take<cx<float>>(NM * nb) : nullptr;
         sY = host ? a.take<cx<float>>(NM * nb) : nullptr; om = host ? a.take<float>(NM * nb) : nullptr;
@@ -618,7 +610,8 @@ static int run_large(Handle* h, const jstsp_admm_desc* d, int mem, const void* s
         if (bad_h) return fail(h, JSTSP_E_UNSUPPORTED, "large-array route needs 4-QAM pilot sequences (entries +-a +-ja, exact in bf16 after the common scaling)");
         CUtensorMap map0, map1;
         if (!make_map_e(E, Mext, nkg * nE, WIN, nkg, &map0) || !make_map_e(E, Mext, nkg * nE, SC2, nkg, &map1)) return fail(h, JSTSP_E_CUDA, "cuTensorMapEncodeTiled failed for the pilot image");
-        for (cx<float>* z : {X, V1, V2, C, Xs, XV}) JSTSP_CUDA(h, cudaMemsetAsync(z, 0, 8 * NM * nb, st));
+        for (cx<float>* z : {X, V1, V2, Xs, XV, Gm}) JSTSP_CUDA(h, cudaMemsetAsync(z, 0, 8 * NM * nb, st));
+        JSTSP_CUDA(h, cudaMemsetAsync(alpha, 0, sizeof(float) * nb, st));
         JSTSP_CUDA(h, cudaMemsetAsync(V, 0, 8 * GP * nb, st));
         JSTSP_CUDA(h, cudaMemsetAsync(S, 0, 8 * GP * nb, st));
         JSTSP_CUDA(h, cudaMemsetAsync(gram, 0, sizeof(double) * (size_t)ngram * 2 * N * N * nb, st));
@@ -629,7 +622,7 @@ static int run_large(Handle* h, const jstsp_admm_desc* d, int mem, const void* s
             // hidden behind the three products of the previous iteration (one CTA per trial, ~1.7 ms at 64 rows)
             if (it == 0) JSTSP_LAUNCH(h, PK_EIG, (k_svt_weights<float><<<nb, 128, sm_j, st>>>(qe)));
             else JSTSP_CUDA(h, cudaStreamWaitEvent(st, h->ev_join, 0));
-            StateArgs sa{N, M, it + 1 == imax ? 1 : 0, pY, ldY_in, pO, ldO, pRho, W, X, V1, Yd, ldYd, V2, C, Xs, XV, dimg, (long long)dimg_b, gram};
+            StateArgs sa{N, M, it + 1 == imax ? 1 : 0, pY, ldY_in, pO, ldO, pRho, W, X, V1, Yd, ldYd, V2, XV, Xs, Gm, alpha, dimg, (long long)dimg_b, gram};
             if (!Yd) sa.last = 0;
             { dim3 g(ngram, nb); JSTSP_LAUNCH(h, PK_LG_STATE, (k_lg_state<<<g, 256, sm_state, st>>>(sa))); }
             if (it + 1 < imax) {
@@ -660,7 +653,6 @@ static int run_large(Handle* h, const jstsp_admm_desc* d, int mem, const void* s
             { dim3 g(ceil_div(L * nkg * N2, 256), nb); JSTSP_LAUNCH(h, PK_LG_SMALL, (k_lg_qimg<<<g, 256, 0, st>>>(Q, qimg, (long long)qimg_b, scale, N, Nt, L))); }
             MmaArgs m2 = m0; m2.out = reinterpret_cast<float*>(Xs); m2.gg = nullptr;
             { dim3 g(ntile, nb); JSTSP_LAUNCH(h, PK_LG_PASS1, (k_lg_mma<0><<<g, MMA_THREADS, sm0, st>>>(map0, m2))); }
-            if (it + 1 < imax) { dim3 g(ceil_div((int)NM, 256), nb); JSTSP_LAUNCH(h, PK_LG_STATE, (k_lg_cupd<<<g, 256, 0, st>>>(X, Xs, Gm, XV, C, V2, alpha, pRho, NM))); }
         }
         JSTSP_CUDA(h, cudaGetLastError());
         JSTSP_LAUNCH(h, PK_OTHER, (k_count_nonfinite<float><<<nb, 128, 0, st>>>(S, GP, nb, h->d_flag)));
