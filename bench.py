@@ -490,7 +490,9 @@ def main():
     # ---- BASELINE configs 2 and 3, trial-sharded like the headline (every rank its own trials, device time, max over ranks) ----
     secondary = None
     if not args.no_secondary:
+        sclk = ClockSampler(local); sclk.wait_first_sample()
         secondary = secondary_configs(torch, dist, _lib, dev, local, rank, world, pk_hbm=peaks()["hbm"])
+        secondary["clocks"] = sclk.stop()          # the secondary legs run after ~30 s of sustained load: their clocks are reported next to them
 
     # ---- end-to-end through the HOST-buffer C ABI (pinned host memory) ----
     e2e = None
