@@ -305,6 +305,17 @@ int jstsp_capacity(jstsp_handle* h, int dtype, int mem, int Nr, int T, int Wc, i
                    const void* Y, long long ld_Y, const void* W, long long ld_W, const int* cols, long long ld_cols,
                    const double* scale, double* rate);
 
+/* The loop body of plot_capacity.m:35-66 / plot_ee.m:36-66 for a whole Mr range in one call: the four receiver designs on the same noiseless blocks Y.
+ *   design 0 digital beamforming (all Nr columns of W_zc, plot_capacity.m:45-47), 1 conventional HBF with phase shifters (W_q(:, 1:Mr), :50-52),
+ *   2 conventional HBF with ZC (W_zc(:, 1:Mr), :55-57), 3 proposed (W_q(:, ind(1:Mr)) with ind = randperm(Mr_e), :61-64).
+ * mr_range: n_mr host integers (Mr_range, plot_capacity.m:16); W_zc / W_q: the Nr x Nr codebooks createBeamformer(Nr,'ZC') / (Nr,'quantized'), shared by the batch;
+ * ind: 1-based permutations, at least max(Mr) entries per trial, trial stride ld_ind (0: shared); scale[b] = 1/(square_noise_variance * Nt).
+ * out[(i_mr * 4 + design) * batch + b] (doubles in `mem` space); mean over b gives mean_Capacity_*(mr_index), and rate ./ jstsp_power_model the energy efficiency
+ * (plot_ee.m:84-87). */
+int jstsp_capacity_sweep(jstsp_handle* h, int dtype, int mem, int Nr, int T, int batch, int n_mr, const int* mr_range,
+                         const void* Y, long long ld_Y, const void* W_zc, const void* W_q, const int* ind, long long ld_ind,
+                         const double* scale, double* out);
+
 /* Power consumption of the four receiver designs of plot_ee.m:69-77 (Pcirc = 0, Psw = 5 mW, Pps = 15 mW, Plna = 20 mW, Pps_zc = 60 mW):
  * power4 = { digital beamforming, conventional HBF with phase shifters, conventional HBF with ZC, proposed }.  Energy efficiency is
  * mean(rate) / power (plot_ee.m:84-87).  Host arithmetic, no handle. */

@@ -14,8 +14,8 @@ B200-class GPU every solver call raises.
 """
 from . import _lib  # noqa: F401  (raises if the CUDA library is missing)
 from . import api  # noqa: F401
-from .api import (ls_estimate, capacity, power_model, energy_efficiency, OMP, OMP_kron, somp, createBeamformer, qam4mod, admm_parameters, hbf, log2det_rate, mc_admm, mc_svt, nmse, proposed_algorithm, proposed_algorithm_angles,  # noqa: F401
+from .api import (ls_estimate, capacity, capacity_sweep, power_model, energy_efficiency, OMP, OMP_kron, somp, createBeamformer, qam4mod, admm_parameters, hbf, log2det_rate, mc_admm, mc_svt, nmse, proposed_algorithm, proposed_algorithm_angles,  # noqa: F401
                   proposed_algorithm_pilots, proposed_algorithm_psi, proposed_hbf, sparse_admm, svt, vamp, wideband_hybBF_comm_system_training, wideband_mmwave_channel)
 
-__all__ = ["ls_estimate", "capacity", "power_model", "energy_efficiency", "proposed_algorithm", "proposed_algorithm_angles", "proposed_algorithm_psi", "proposed_algorithm_pilots", "svt", "mc_svt", "mc_admm", "OMP", "OMP_kron", "somp", "createBeamformer", "qam4mod", "sparse_admm", "vamp",
+__all__ = ["ls_estimate", "capacity", "capacity_sweep", "power_model", "energy_efficiency", "proposed_algorithm", "proposed_algorithm_angles", "proposed_algorithm_psi", "proposed_algorithm_pilots", "svt", "mc_svt", "mc_admm", "OMP", "OMP_kron", "somp", "createBeamformer", "qam4mod", "sparse_admm", "vamp",
            "wideband_mmwave_channel", "proposed_hbf", "hbf", "wideband_hybBF_comm_system_training", "nmse", "admm_parameters", "log2det_rate"]

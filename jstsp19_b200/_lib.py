@@ -73,6 +73,7 @@ def _load():
     lib.jstsp_ls_estimate.argtypes = [vp, i, i, i, i, i, i, i, vp, ll, vp, ll, vp, ll, vp, ll, vp, ll]
     lib.jstsp_capacity.argtypes = [vp, i, i, i, i, i, i, i, vp, ll, vp, ll, vp, ll, vp, vp]
     lib.jstsp_power_model.argtypes = [i, i, i, vp]
+    lib.jstsp_capacity_sweep.argtypes = [vp, i, i, i, i, i, i, vp, vp, ll, vp, vp, vp, ll, vp, vp]
     lib.jstsp_draw_trials.argtypes = [vp, i, C.c_ulonglong, ll, i, i, i, i, i, i, vp, vp, vp, vp, vp, vp]
     lib.jstsp_philox4x32_10.argtypes = [vp, vp, vp]
     lib.jstsp_philox4x32_10.restype = None
@@ -102,7 +103,7 @@ EXPORTED = [
     "jstsp_synchronize", "jstsp_launch_count", "jstsp_set_chunk", "jstsp_profile", "jstsp_profile_read", "jstsp_debug_buffer",
     "jstsp_proposed_algorithm", "jstsp_proposed_algorithm_angles", "jstsp_proposed_algorithm_psi", "jstsp_proposed_algorithm_pilots", "jstsp_last_path", "jstsp_last_variant", "jstsp_nonfinite_count", "jstsp_ls_estimate", "jstsp_capacity", "jstsp_power_model",
     "jstsp_svt", "jstsp_mc_svt", "jstsp_mc_admm", "jstsp_omp", "jstsp_omp_kron", "jstsp_somp", "jstsp_sparse_admm", "jstsp_vamp",
-    "jstsp_wideband_mmwave_channel", "jstsp_measure", "jstsp_create_beamformer", "jstsp_qam4mod", "jstsp_nmse", "jstsp_admm_parameters", "jstsp_log2det_rate", "jstsp_draw_trials", "jstsp_philox4x32_10",
+    "jstsp_wideband_mmwave_channel", "jstsp_measure", "jstsp_create_beamformer", "jstsp_qam4mod", "jstsp_nmse", "jstsp_admm_parameters", "jstsp_log2det_rate", "jstsp_draw_trials", "jstsp_philox4x32_10", "jstsp_capacity_sweep",
 ]
 
 

@@ -604,6 +604,27 @@ def capacity(Y, W, Mr, scale, cols=None, *, precision="f64", handle=None):
     return float(out[0]) if bs is None else out
 
 
+def capacity_sweep(Y, W_zc, W_q, Mr_range, ind, scale, *, precision="f64", handle=None):
+    """Spectral efficiency of the four receiver designs of plot_capacity.m:45-64 for every Mr of ``Mr_range`` on a batch of noiseless blocks ``Y`` (b, Nr, T):
+    returns (len(Mr_range), 4, b) = [digital BF, conventional HBF with phase shifters, conventional HBF with ZC, proposed].  ``ind`` holds the 1-based
+    permutations ind = randperm(Mr_e) of the proposed design, one row per trial (or one shared row); ``scale`` = 1/(square_noise_variance*Nt)."""
+    h = handle or default_handle()
+    cd = _CD[precision]
+    Ym = _cm(Y, cd)
+    if Ym.ndim == 2:
+        Ym = Ym[None]
+    batch, T, Nr = Ym.shape
+    Wz, Wq = _cm(W_zc, cd), _cm(W_q, cd)
+    mr = np.ascontiguousarray(np.asarray(Mr_range), dtype=np.int32)
+    ci = np.ascontiguousarray(np.asarray(ind), dtype=np.int32)
+    ldi = ci.shape[-1] if ci.ndim == 2 and ci.shape[0] == batch and batch > 1 else 0
+    sc = _per_trial(scale, batch)
+    out = np.empty((mr.size, 4, batch), dtype=np.float64)
+    h.check(_lib.lib.jstsp_capacity_sweep(h.ptr, _DT[precision], _lib.HOST, Nr, T, batch, int(mr.size), _ptr(mr), _ptr(Ym), Nr * T, _ptr(Wz), _ptr(Wq),
+                                          _ptr(ci), ldi, _ptr(sc), _ptr(out)))
+    return out
+
+
 def power_model(Nr, Mr, Mr_e):
     """(power_dbf, power_hbf, power_hbf_zc, power_proposed) of plot_ee.m:69-77."""
     out = np.empty(4, dtype=np.float64)

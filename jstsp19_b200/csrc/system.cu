@@ -722,6 +722,35 @@ extern "C" int jstsp_capacity(jstsp_handle* h, int dtype, int mem, int Nr, int T
     return fail(h, JSTSP_E_ARG, "unknown dtype");
 }
 
+// One call for the loop body of plot_capacity.m:35-66 / plot_ee.m:36-66 over an Mr range: the four receiver designs on the same noiseless blocks.
+//   design 0 digital BF (all Nr columns of W_zc), 1 conventional HBF with phase shifters (W_q(:, 1:Mr)), 2 conventional HBF with ZC (W_zc(:, 1:Mr)),
+//   3 proposed (W_q(:, ind(1:Mr)), ind = randperm(Mr_e) per trial).   out[(i_mr * 4 + design) * batch + b]
+template <typename T>
+static int run_capacity_sweep(Handle* h, int mem, int Nr, int T_, int batch, int n_mr, const int* mr_range, const void* Y, long long ld_Y, const void* Wzc, const void* Wq,
+                              const int* ind, long long ld_ind, const double* scale, double* out) {
+    if (n_mr <= 0 || !mr_range || !out || !ind) return fail(h, JSTSP_E_ARG, "bad argument");
+    for (int i = 0; i < n_mr; ++i) {
+        const int Mr = mr_range[i];
+        if (Mr <= 0 || Mr > Nr) return fail(h, JSTSP_E_ARG, "Mr outside 1..Nr");
+        double* o = out + (size_t)i * 4 * batch;
+        int rc;
+        if ((rc = run_capacity<T>(h, mem, Nr, T_, Nr, Nr, batch, Y, ld_Y, Wzc, 0, nullptr, 0, scale, o))) return rc;                       // plot_capacity.m:45-47
+        if ((rc = run_capacity<T>(h, mem, Nr, T_, Nr, Mr, batch, Y, ld_Y, Wq, 0, nullptr, 0, scale, o + batch))) return rc;                // :50-52
+        if ((rc = run_capacity<T>(h, mem, Nr, T_, Nr, Mr, batch, Y, ld_Y, Wzc, 0, nullptr, 0, scale, o + 2 * (size_t)batch))) return rc;   // :55-57
+        if ((rc = run_capacity<T>(h, mem, Nr, T_, Nr, Mr, batch, Y, ld_Y, Wq, 0, ind, ld_ind, scale, o + 3 * (size_t)batch))) return rc;   // :61-64
+    }
+    return JSTSP_OK;
+}
+extern "C" int jstsp_capacity_sweep(jstsp_handle* h, int dtype, int mem, int Nr, int T, int batch, int n_mr, const int* mr_range,
+                                    const void* Y, long long ld_Y, const void* W_zc, const void* W_q, const int* ind, long long ld_ind,
+                                    const double* scale, double* out) {
+    if (!h) return JSTSP_E_ARG;
+    JSTSP_CUDA(h, cudaSetDevice(h->device));
+    if (dtype == JSTSP_F32) return run_capacity_sweep<float>(h, mem, Nr, T, batch, n_mr, mr_range, Y, ld_Y, W_zc, W_q, ind, ld_ind, scale, out);
+    if (dtype == JSTSP_F64) return run_capacity_sweep<double>(h, mem, Nr, T, batch, n_mr, mr_range, Y, ld_Y, W_zc, W_q, ind, ld_ind, scale, out);
+    return fail(h, JSTSP_E_ARG, "unknown dtype");
+}
+
 template <typename T>
 static int run_params(Handle* h, int mem, int N, int M, int G, int P, int batch, int kth, const void* Y, long long ld_Y, const void* Z, long long ld_Z,
                       double* tauY, double* tauZ, double* rho) {

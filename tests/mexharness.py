@@ -13,7 +13,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "jstsp19_b200", "mex", "build")
 GATEWAYS = ["wideband_mmwave_channel", "wideband_hybBF_comm_system_training", "proposed_hbf", "hbf", "proposed_algorithm",
-            "proposed_algorithm_angles", "proposed_algorithm_psi", "svt", "mc_svt", "mc_admm", "sparse_admm", "OMP", "vamp", "OMP_kron", "jstsp_somp", "proposed_algorithm_pilots", "createBeamformer", "qam4mod"]
+            "proposed_algorithm_angles", "proposed_algorithm_psi", "svt", "mc_svt", "mc_admm", "sparse_admm", "OMP", "vamp", "OMP_kron", "jstsp_somp", "proposed_algorithm_pilots", "createBeamformer", "qam4mod", "ls_estimate", "capacity_sweep"]
 
 _CB = C.CFUNCTYPE(C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p), C.c_char_p)
 

@@ -90,6 +90,36 @@ def test_capacity_designs_and_column_selection(precision, tol):
         assert abs(c_dbf[k] - est.capacity_literal(Ys[k], Ws[k], np.arange(1, Nr + 1), scale)) <= tol * 50
 
 
+@pytest.mark.parametrize("precision,tol", [("f64", 1e-9), ("f32", 2e-4)])
+def test_capacity_sweep_all_designs(precision, tol):
+    """jstsp_capacity_sweep = the loop body of plot_capacity.m:35-66 for a whole Mr range in one call: the four receiver designs against the literal
+    restatement, then the energy efficiency of plot_ee.m:84-87 from the mean rates and the power model."""
+    import jstsp19_b200 as jb
+    from oracle.matlab_compat import RefRandom, toeplitz_hermitian
+    rng = RefRandom(9)
+    Nt, Nr, L, T, Mr_e = 16, 32, 4, 5, 32
+    scale = 1.0 / 10 ** (-15 / 10) / Nt
+    nb, mr_range = 3, list(range(1, Mr_e + 1, 5))
+    Wz, Wq = sm.create_beamformer(Nr, "ZC"), sm.create_beamformer(Nr, "quantized")
+    Ys, inds = [], []
+    for k in range(nb):
+        H = sm.wideband_mmwave_channel(L, Nr, Nt, 2, 3, Nr, Nt, rng)[0]
+        Psi_i = np.stack([toeplitz_hermitian(sm.qam4mod(T, rng)) for _ in range(Nt)], axis=2)
+        Ys.append(sm.hbf(H, np.zeros((Nr, T)), Psi_i, T, Nr, Wz)[3]); inds.append(rng.randperm(Mr_e))
+    Ys, inds = np.stack(Ys), np.stack(inds)
+    out = jb.capacity_sweep(Ys, Wz, Wq, mr_range, inds, scale, precision=precision)
+    assert out.shape == (len(mr_range), 4, nb)
+    for i, Mr in enumerate(mr_range):
+        for k in range(nb):
+            ref = [est.capacity_literal(Ys[k], Wz, np.arange(1, Nr + 1), scale), est.capacity_literal(Ys[k], Wq, np.arange(1, Mr + 1), scale),
+                   est.capacity_literal(Ys[k], Wz, np.arange(1, Mr + 1), scale), est.capacity_literal(Ys[k], Wq, inds[k][:Mr], scale)]
+            for dsg in range(4):
+                assert abs(out[i, dsg, k] - ref[dsg]) <= tol * max(1.0, abs(ref[dsg])) * (50 if dsg == 0 else 1), (Mr, dsg, k, out[i, dsg, k], ref[dsg])
+        ee = jb.energy_efficiency(out[i].mean(axis=1), Nr, Mr, Mr_e)
+        pw = est.ee_power_model(Nr, Mr, Mr_e)
+        np.testing.assert_allclose(ee, out[i].mean(axis=1) / np.asarray(pw), rtol=1e-12)
+
+
 def test_energy_efficiency_power_model():
     """plot_ee.m:69-87: the four power formulas and ee = mean capacity / power, over Mr_range = 1:3:Mr_e at Nr = 64."""
     import jstsp19_b200 as jb

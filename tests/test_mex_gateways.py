@@ -286,3 +286,32 @@ def test_vamp_gateway_uses_matlab_svd():
     (x1,) = g(1, yt, At, 1.0, 3)
     x0 = ovamp.vamp_literal(yt, At, 1.0, 3)
     assert _rel(x1.reshape(-1), np.asarray(x0).reshape(-1)) < 1e-6
+
+
+@pytest.mark.gpu
+def test_ls_estimate_and_capacity_sweep_gateways():
+    """The two gateways without a same-named reference function: ls_estimate (plot_errorVSsnr.m:83,117) and capacity_sweep (plot_capacity.m:45-64)."""
+    from oracle import system_model as sm
+    from oracle.matlab_compat import RefRandom, toeplitz_hermitian
+    rng = np.random.default_rng(12)
+    N, G, M, P = 8, 6, 40, 12
+    A = rng.standard_normal((N, G)) + 1j * rng.standard_normal((N, G))
+    B = rng.standard_normal((P, M)) + 1j * rng.standard_normal((P, M))
+    Y = rng.standard_normal((N, M)) + 1j * rng.standard_normal((N, M))
+    S, YpB = mh.Gateway("ls_estimate")(2, A, Y, B)
+    assert _rel(S, est.ls_estimate(A, Y, B)) < 1e-9 and _rel(YpB, est.y_pinv_b(Y, B)) < 1e-9
+    rr = RefRandom(3)
+    Nt, Nr, L, T, Mr_e = 8, 16, 2, 6, 16
+    H = sm.wideband_mmwave_channel(L, Nr, Nt, 2, 3, Nr, Nt, rr)[0]
+    Psi_i = np.stack([toeplitz_hermitian(sm.qam4mod(T, rr)) for _ in range(Nt)], axis=2)
+    Wz, Wq = sm.create_beamformer(Nr, "ZC"), sm.create_beamformer(Nr, "quantized")
+    Yn = sm.hbf(H, np.zeros((Nr, T)), Psi_i, T, Nr, Wz)[3]
+    ind = rr.randperm(Mr_e)
+    scale = 1.0 / 10 ** (-15 / 10) / Nt
+    mr_range = np.array([1.0, 4.0, 7.0, 10.0])
+    (Cm,) = mh.Gateway("capacity_sweep")(1, Yn, Wz, Wq, mr_range, np.asarray(ind, dtype=np.float64), scale)
+    assert Cm.shape == (4, 4)
+    for i, Mr in enumerate(mr_range.astype(int)):
+        ref = [est.capacity_literal(Yn, Wz, np.arange(1, Nr + 1), scale), est.capacity_literal(Yn, Wq, np.arange(1, Mr + 1), scale),
+               est.capacity_literal(Yn, Wz, np.arange(1, Mr + 1), scale), est.capacity_literal(Yn, Wq, np.asarray(ind)[:Mr], scale)]
+        assert np.allclose(Cm[i].real, ref, rtol=1e-8, atol=1e-8), (Mr, Cm[i], ref)
