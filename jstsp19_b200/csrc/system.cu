@@ -204,32 +204,72 @@ __global__ void __launch_bounds__(256) k_measure_tiled(MeasP<T> p) {
     const int b = blockIdx.y, Nr = p.Nr, Nt = p.Nt, L = p.L, TT = p.T_, Wc = p.Wc;
     const int RG = Nr / 8, CTc = 256 / RG, WP = CTc + L - 1;
     cx<T>* sH = reinterpret_cast<cx<T>*>(smem);                  // [(l * Nt + k)][Nr]
-    cx<T>* sW = sH + (size_t)L * Nt * Nr;                        // [Nr][Wc]
-    cx<T>* sP = sW + (size_t)Nr * Wc;                            // [k][WP]; reused as R [column][Nr]
+    cx<T>* sW = sH + (size_t)L * Nt * Nr;                        // [r][Wc + 1]: W(r, q) at r (Wc + 1) + q (lanes run over q: the padding spreads the banks)
+    cx<T>* sP = sW + (size_t)Nr * (Wc + 1);                      // [k][WP]; reused as R [row][CTc + 1]
     const cx<T>* H = p.H + (long long)b * p.ld_H;
     const cx<T>* Pil = p.Psi + (long long)b * p.ld_Psi;
     const cx<T>* W = p.W + (long long)b * p.ld_W;
     const int t0 = blockIdx.x * CTc;
-    for (int e = threadIdx.x; e < L * Nt * Nr; e += 256) sH[e] = H[e];                       // H(r, k, l) at r + Nr k + Nr Nt l
-    for (int e = threadIdx.x; e < Nr * Wc; e += 256) sW[e] = W[e];
-    for (int e = threadIdx.x; e < Nt * WP; e += 256) {
-        const int k = e % Nt, w = e / Nt, tau = t0 - (L - 1) + w;
-        cx<T> v = mk<T>(T(0), T(0));
-        if (tau >= 0 && tau < TT) v = Pil[k + (size_t)Nt * tau];
-        else if (tau < 0 && -tau < TT) v = conj(Pil[k + (size_t)Nt * (-tau)]);                // row l of toeplitz(s_k) below the diagonal
-        sP[(size_t)k * WP + w] = v;
+    if constexpr (sizeof(T) == 4) {      // fp32: planar re | im so that row pairs are 64-bit operands of the packed FMA below
+        float* hre = reinterpret_cast<float*>(sH); float* him = hre + (size_t)L * Nt * Nr;
+#pragma unroll 8
+        for (int e = threadIdx.x; e < L * Nt * Nr; e += 256) { const cx<T> v = H[e]; hre[e] = v.re; him[e] = v.im; }
+    } else {
+        for (int e = threadIdx.x; e < L * Nt * Nr; e += 256) sH[e] = H[e];                   // H(r, k, l) at r + Nr k + Nr Nt l
+    }
+    for (int e = threadIdx.x; e < Nr * Wc; e += 256) sW[(e % Nr) * (Wc + 1) + e / Nr] = W[e];
+    if (t0 - (L - 1) >= 0 && t0 + CTc <= TT) {           // interior tile: a straight copy, eight loads in flight per thread
+#pragma unroll 8
+        for (int e = threadIdx.x; e < Nt * WP; e += 256) sP[(size_t)(e % Nt) * WP + e / Nt] = Pil[(size_t)Nt * (t0 - (L - 1)) + e];
+    } else {
+        for (int e = threadIdx.x; e < Nt * WP; e += 256) {
+            const int k = e % Nt, w = e / Nt, tau = t0 - (L - 1) + w;
+            cx<T> v = mk<T>(T(0), T(0));
+            if (tau >= 0 && tau < TT) v = Pil[k + (size_t)Nt * tau];
+            else if (tau < 0 && -tau < TT) v = conj(Pil[k + (size_t)Nt * (-tau)]);            // row l of toeplitz(s_k) below the diagonal
+            sP[(size_t)k * WP + w] = v;
+        }
     }
     __syncthreads();
     const int c = threadIdx.x % CTc, rg = threadIdx.x / CTc, t = t0 + c;
     T ar[8] = {}, ai[8] = {};
-    for (int l = 0; l < L; ++l) {
-        const cx<T>* pw = sP + (c + (L - 1) - l);
-        const cx<T>* hh = sH + (size_t)l * Nt * Nr + 8 * rg;
-        for (int k = 0; k < Nt; ++k) {
-            const cx<T> ps = pw[(size_t)k * WP];
-            const cx<T>* hv = hh + (size_t)k * Nr;
+    if constexpr (sizeof(T) == 4) {
+        // packed fp32x2 FMAs (Blackwell FFMA2) on row pairs: R += Hre * p.re ; R += Him * (-p.im) ; I += Hre * p.im ; I += Him * p.re - the same
+        // operations in the same order as cmac(), two rows per instruction (rounds exactly like the scalar form)
+        const float* hre = reinterpret_cast<const float*>(sH); const float* him = hre + (size_t)L * Nt * Nr;
+        uint64_t R[4] = {0, 0, 0, 0}, I[4] = {0, 0, 0, 0};
+        auto pk = [](float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; };
+        auto f2 = [](uint64_t& d, uint64_t a, uint64_t b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b)); };
+        for (int l = 0; l < L; ++l) {
+            const cx<T>* pw = sP + (c + (L - 1) - l);
+            const size_t h0 = (size_t)l * Nt * Nr + 8 * rg;
+#pragma unroll 4
+            for (int k = 0; k < Nt; ++k) {
+                const cx<T> ps = pw[(size_t)k * WP];
+                const uint64_t PR = pk(ps.re, ps.re), PI = pk(ps.im, ps.im), PN = pk(-ps.im, -ps.im);
+                const ulonglong2 a0 = *reinterpret_cast<const ulonglong2*>(hre + h0 + (size_t)k * Nr), a1 = *reinterpret_cast<const ulonglong2*>(hre + h0 + (size_t)k * Nr + 4);
+                const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(him + h0 + (size_t)k * Nr), b1 = *reinterpret_cast<const ulonglong2*>(him + h0 + (size_t)k * Nr + 4);
+                const uint64_t HR[4] = {a0.x, a0.y, a1.x, a1.y}, HI[4] = {b0.x, b0.y, b1.x, b1.y};
 #pragma unroll
-            for (int u = 0; u < 8; ++u) cmac<T>(ar[u], ai[u], hv[u].re, hv[u].im, ps.re, ps.im);
+                for (int q = 0; q < 4; ++q) { f2(R[q], HR[q], PR); f2(R[q], HI[q], PN); f2(I[q], HR[q], PI); f2(I[q], HI[q], PR); }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float lo, hi;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(R[q])); ar[2 * q] = lo; ar[2 * q + 1] = hi;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(I[q])); ai[2 * q] = lo; ai[2 * q + 1] = hi;
+        }
+    } else {
+        for (int l = 0; l < L; ++l) {
+            const cx<T>* pw = sP + (c + (L - 1) - l);
+            const cx<T>* hh = sH + (size_t)l * Nt * Nr + 8 * rg;
+            for (int k = 0; k < Nt; ++k) {
+                const cx<T> ps = pw[(size_t)k * WP];
+                const cx<T>* hv = hh + (size_t)k * Nr;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) cmac<T>(ar[u], ai[u], hv[u].re, hv[u].im, ps.re, ps.im);
+            }
         }
     }
     __syncthreads();                                             // the pilot window is dead: its space takes R
@@ -241,7 +281,7 @@ __global__ void __launch_bounds__(256) k_measure_tiled(MeasP<T> p) {
             T re = ar[u], im = ai[u];
             if (p.Ynl) p.Ynl[(size_t)b * Nr * TT + (size_t)t * Nr + r] = mk<T>(re, im);       // noiseless Y (proposed_hbf.m:14-20)
             if (p.N) { const cx<T> nv = p.N[(long long)b * p.ld_N + r + (size_t)Nr * t]; re += nv.re; im += nv.im; }   // R = Y + N (:22)
-            sR[(size_t)c * Nr + r] = mk<T>(re, im);
+            sR[(size_t)r * (CTc + 1) + c] = mk<T>(re, im);
         }
     }
     __syncthreads();
@@ -249,7 +289,7 @@ __global__ void __launch_bounds__(256) k_measure_tiled(MeasP<T> p) {
         const int q = e % Wc, cc = e / Wc, tt = t0 + cc;
         if (tt >= TT) break;
         T re = 0, im = 0;
-        for (int r = 0; r < Nr; ++r) { const cx<T> w = sW[r + (size_t)Nr * q], x = sR[(size_t)cc * Nr + r]; cmac<T>(re, im, w.re, -w.im, x.re, x.im); }
+        for (int r = 0; r < Nr; ++r) { const cx<T> w = sW[r * (Wc + 1) + q], x = sR[(size_t)r * (CTc + 1) + cc]; cmac<T>(re, im, w.re, -w.im, x.re, x.im); }
         T om = T(1);
         if (p.perm) {          // Omega(indices(1:Lr), t) = 1 with indices = randperm(Wc)  (proposed_hbf.m:36-41)
             om = T(0);
@@ -288,11 +328,11 @@ __global__ void __launch_bounds__(256) k_nmse(const cx<T>* S, long long ld_S, co
     const cx<T>* s = S + (long long)b * ld_S; const cx<T>* z = Z + (long long)b * ld_Z;
     double num = 0.0, den = 0.0;
     gram_rows<T>(sm, s, z, G, P);
-    jacobi_hermitian_block(sm, G);
+    jacobi_hermitian_block(sm, G, 24, false, sizeof(T) == 4 ? 1e-10 : 1e-20);      // fp32 callers: eigenvalues to 1e-10 relative are beyond their inputs
     for (int k = 0; k < G; ++k) num = fmax(num, sm.Are[k + G * k]);
     __syncthreads();
     gram_rows<T>(sm, z, nullptr, G, P);
-    jacobi_hermitian_block(sm, G);
+    jacobi_hermitian_block(sm, G, 24, false, sizeof(T) == 4 ? 1e-10 : 1e-20);
     for (int k = 0; k < G; ++k) den = fmax(den, sm.Are[k + G * k]);
     if (threadIdx.x == 0) { double e = num / den; out[b] = e > 1.0 ? 1.0 : e; }     // clipped at 1 (plot_errorVSsnr.m:139-141)
 }
@@ -309,7 +349,7 @@ __global__ void __launch_bounds__(256) k_params(const cx<T>* Y, long long ld_Y, 
     double fy = 0.0;                                         // ||Y||_F^2 = trace of the Gram matrix
     for (int k = 0; k < N; ++k) fy += sm.Are[k + N * k];
     __syncthreads();
-    jacobi_hermitian_block(sm, N);
+    jacobi_hermitian_block(sm, N, 24, false, sizeof(T) == 4 ? 1e-10 : 1e-20);
     if (threadIdx.x == 0) {
         // eigs(Y'Y): the kth largest eigenvalue (6 by default -> min(eigs), 1 -> max) (plot_errorVSsnr.m:129-130)
         double ev[64];
@@ -436,7 +476,7 @@ static int run_measure(Handle* h, int mem, const jstsp_meas_desc* d, const void*
         p.Ynl = Ynl ? (host ? ar.take<cx<T>>(nYn) : (cx<T>*)Ynl) : nullptr;
         if (!pass) { int rc = ensure_workspace(h, ar.off); if (rc) return rc; continue; }
         const int RG = Nr / 8, CTc = (Nr % 8 == 0 && RG >= 1 && 256 % RG == 0) ? 256 / RG : 0;
-        const size_t sm_t = CTc ? sizeof(cx<T>) * ((size_t)L * Nt * Nr + (size_t)Nr * Wc + std::max((size_t)Nt * (CTc + L - 1), (size_t)CTc * Nr)) : 0;
+        const size_t sm_t = CTc ? sizeof(cx<T>) * ((size_t)L * Nt * Nr + (size_t)Nr * (Wc + 1) + std::max((size_t)Nt * (CTc + L - 1), (size_t)(CTc + 1) * Nr)) : 0;
         if (CTc && d->psi_mode == 1 && !Psibar && !We && sm_t <= h->smem_optin && getenv("JSTSP_MEASURE_SIMPLE") == nullptr) {
             { int rc = set_smem(h, k_measure_tiled<T>, sm_t); if (rc) return rc; }
             dim3 grid(ceil_div(TT, CTc), batch);
