@@ -266,7 +266,7 @@ __device__ inline void jac16_weights(Jac16& sm, int jt, double tau, double fro2,
             const double ar = sm.Ure[i + LDJ * k], ai = sm.Uim[i + LDJ * k], br = sm.Ure[j + LDJ * k], bi = -sm.Uim[j + LDJ * k];
             wr += f * (ar * br - ai * bi); wi += f * (ar * bi + ai * br);
         }
-        W[i + N * j] = mk<float>((float)wr, (float)wi);
+        reinterpret_cast<float*>(W)[i + N * j] = (float)wr; reinterpret_cast<float*>(W)[N * N + i + N * j] = (float)wi;      // planar: re plane | im plane
     }
 }
 
@@ -393,6 +393,8 @@ __device__ __noinline__ void apply_a_shared(const cx<float>* __restrict__ Mx, co
 #endif
 __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const __grid_constant__ Maps maps, In in, int nb) {
     constexpr int NH = N / 2;
+    // launched before the host has seen the structure check's flags (run_admm, speculative pass): a failed check leaves everything untouched
+    if (in.bad[0] != 0 || in.bad[1] != 0) return;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* etile = smem + OFF_E;
     unsigned char* inr = smem + OFF_IN;
@@ -677,29 +679,33 @@ __global__ void __launch_bounds__(MTHREADS, 1) k_psi_mega(AdmmP<float> p, const 
                     ring_release(&in_empty[in_n % NIN], &in_empty[(in_n + 1) % NIN], lane);
                     in_n += 2;
                     if (MEGA_DUMP_ON) { float sx = 0.f, sv = 0.f; for (int r = 0; r < NH; ++r) { sx += xo[r].re * xo[r].re + xo[r].im * xo[r].im; sv += v1[r].re * v1[r].re + v1[r].im * v1[r].im; } MEGA_DUMP_ADD(0 + c, sx); MEGA_DUMP_ADD(8 + c, sv); }
-                    if (MEGA_DUMP_ON && c == 0 && tid < 256) { reinterpret_cast<float*>(p.dbg)[(size_t)b * 1024 + 512 + 2 * tid] = Ws[tid].re; reinterpret_cast<float*>(p.dbg)[(size_t)b * 1024 + 512 + 2 * tid + 1] = Ws[tid].im; if (tid == 0) { reinterpret_cast<float*>(p.dbg)[(size_t)b * 1024 + 100] = alpha_prev; reinterpret_cast<float*>(p.dbg)[(size_t)b * 1024 + 101] = rho; } }
+                    if (MEGA_DUMP_ON && c == 0 && tid < 256) { reinterpret_cast<float*>(p.dbg)[(size_t)b * 1024 + 512 + 2 * tid] = reinterpret_cast<const float*>(Ws)[tid]; reinterpret_cast<float*>(p.dbg)[(size_t)b * 1024 + 512 + 2 * tid + 1] = reinterpret_cast<const float*>(Ws)[N * N + tid]; if (tid == 0) { reinterpret_cast<float*>(p.dbg)[(size_t)b * 1024 + 100] = alpha_prev; reinterpret_cast<float*>(p.dbg)[(size_t)b * 1024 + 101] = rho; } }
                     wsync();                                  // the Gram of the previous chunk has read Z
 #pragma unroll
                     for (int r = 0; r < NH; ++r) { Zre[(n0 + r) * MZP + m] = xo[r].re - irho * v1[r].re; Zim[(n0 + r) * MZP + m] = xo[r].im - irho * v1[r].im; }
                     wsync();
                     // ---- Y = W Z ; u = V1 + rho Y ----
                     {
+                        // packed fp32x2 FMAs on row pairs (W is held planar, so (re_r, re_r+1) is one 64-bit operand): per k
+                        //   YR += WR * zr ; YR += WI * (-zi) ; YI += WR * zi ; YI += WI * zr   - the operations and order of cmac(), two rows per instruction
                         float y_r[NH], y_i[NH];
+                        {
+                            const float* WR = reinterpret_cast<const float*>(Ws) + n0; const float* WI = WR + N * N;
+                            uint64_t YR[NH / 2], YI[NH / 2];
 #pragma unroll
-                        for (int r = 0; r < NH; ++r) { y_r[r] = 0.f; y_i[r] = 0.f; }
+                            for (int q = 0; q < NH / 2; ++q) { YR[q] = 0ull; YI[q] = 0ull; }
 #pragma unroll 4
-                        for (int k = 0; k < N; ++k) {
-                            const float zr = Zre[k * MZP + m], zi = Zim[k * MZP + m];
-                            cx<float> w[NH];
+                            for (int k = 0; k < N; ++k) {
+                                const float zr = Zre[k * MZP + m], zi = Zim[k * MZP + m];
+                                const uint64_t ZR = pack2(zr, zr), ZI = pack2(zi, zi), ZN = pack2(-zi, -zi);
+                                const ulonglong2 r0 = *reinterpret_cast<const ulonglong2*>(WR + N * k), r1 = *reinterpret_cast<const ulonglong2*>(WR + N * k + 4);
+                                const ulonglong2 i0 = *reinterpret_cast<const ulonglong2*>(WI + N * k), i1 = *reinterpret_cast<const ulonglong2*>(WI + N * k + 4);
+                                const uint64_t wr[4] = {r0.x, r0.y, r1.x, r1.y}, wi[4] = {i0.x, i0.y, i1.x, i1.y};
 #pragma unroll
-                            for (int hf = 0; hf < NH / 4; ++hf) {
-                                cx<float> t[4];
-                                ld4c<float>(Ws + N * k + n0 + 4 * hf, t);
-#pragma unroll
-                                for (int u = 0; u < 4; ++u) w[4 * hf + u] = t[u];
+                                for (int q = 0; q < NH / 2; ++q) { ffma2(YR[q], wr[q], ZR); ffma2(YR[q], wi[q], ZN); ffma2(YI[q], wr[q], ZI); ffma2(YI[q], wi[q], ZR); }
                             }
 #pragma unroll
-                            for (int r = 0; r < NH; ++r) cmac<float>(y_r[r], y_i[r], w[r].re, w[r].im, zr, zi);
+                            for (int q = 0; q < NH / 2; ++q) { unpack2(YR[q], y_r[2 * q], y_r[2 * q + 1]); unpack2(YI[q], y_i[2 * q], y_i[2 * q + 1]); }
                         }
                         if (!more && p.Yout != nullptr) {
 #pragma unroll

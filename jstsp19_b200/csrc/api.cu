@@ -30,6 +30,8 @@ extern "C" int jstsp_create(jstsp_handle** out, int device) {
     if (cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking) != cudaSuccess) { delete h; return JSTSP_E_CUDA; }
     for (int k = 0; k < 2; ++k) { cudaEventCreateWithFlags(&h->ev_in[k], cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_done[k], cudaEventDisableTiming); }
     cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_check, cudaEventDisableTiming);
+    if (cudaHostAlloc(reinterpret_cast<void**>(&h->flags_host), 2 * sizeof(int), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); delete h; return JSTSP_E_CUDA; }
     cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     if (cudaMalloc(&h->d_flag, sizeof(int)) != cudaSuccess) { delete h; return JSTSP_E_CUDA; }
     *out = h;
@@ -44,6 +46,8 @@ extern "C" void jstsp_destroy(jstsp_handle* h) {
     if (h->d_flag) cudaFree(h->d_flag);
     for (auto e : h->prof.pool) cudaEventDestroy(e);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_check) cudaEventDestroy(h->ev_check);
+    if (h->flags_host) cudaFreeHost(h->flags_host);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->side) cudaStreamDestroy(h->side);
     if (h->copy) cudaStreamDestroy(h->copy);

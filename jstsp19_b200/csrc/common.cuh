@@ -69,6 +69,8 @@ struct Handle {
     cudaStream_t side = nullptr;        // side stream for the eigen-solves (forked/joined by events)
     bool own_stream = false;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_check = nullptr;     // the structure-check flags of the current pass have landed in flags_host
+    int* flags_host = nullptr;          // pinned, 2 ints
     cudaStream_t copy = nullptr;        // H2D stream of the HOST-buffer path (next pass's inputs travel while this pass computes)
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     std::string err;
