@@ -133,18 +133,29 @@ __global__ void __launch_bounds__(256) k_matvec(MvP<T> q) {
     const T* s1 = q.s1 ? q.s1 + (long long)b * q.ld_s1 : nullptr;
     const T* s2 = q.s2 ? q.s2 + (long long)b * q.ld_s2 : nullptr;
     if (!q.trans) {
-        // lanes along the output rows: Mat(:, k) is read coalesced, x[k] is a broadcast
-        const int i = blockIdx.x * blockDim.x + threadIdx.x;
-        if (i >= q.rows) return;
+        // 32 output rows per CTA: lanes along the rows (Mat(:, k) is read coalesced, x[k] is a broadcast), the eight warps take every eighth column and
+        // their partial sums are added in warp order through shared memory - 8 x rows/32 CTAs per trial instead of one thread per row looping over all columns
+        __shared__ T part[8][32][2];
+        const int lane = threadIdx.x % 32, w = threadIdx.x / 32, i = blockIdx.x * 32 + lane;
         T re = 0, im = 0;
-        for (int k = 0; k < q.cols; ++k) {
-            const cx<T> a = M[i + (size_t)q.rows * k];
-            cx<T> v = xv[k];
-            if (s1) { T s = s1[k]; if (s2) s *= s2[k]; v = mk<T>(v.re * s, v.im * s); }
-            cmac<T>(re, im, a.re, a.im, v.re, v.im);
+        if (i < q.rows) {
+#pragma unroll 4
+            for (int k = w; k < q.cols; k += 8) {
+                const cx<T> a = M[i + (size_t)q.rows * k];
+                cx<T> v = xv[k];
+                if (s1) { T s = s1[k]; if (s2) s *= s2[k]; v = mk<T>(v.re * s, v.im * s); }
+                cmac<T>(re, im, a.re, a.im, v.re, v.im);
+            }
         }
-        if (q.add) { const cx<T> a = q.add[(long long)b * q.ld_add + i]; if (q.sub_from) { re = a.re - re; im = a.im - im; } else { re += a.re; im += a.im; } }
-        q.out[(long long)b * q.ld_out + i] = mk<T>(re, im);
+        part[w][lane][0] = re; part[w][lane][1] = im;
+        __syncthreads();
+        if (w == 0 && i < q.rows) {
+            re = 0; im = 0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { re += part[u][lane][0]; im += part[u][lane][1]; }
+            if (q.add) { const cx<T> a = q.add[(long long)b * q.ld_add + i]; if (q.sub_from) { re = a.re - re; im = a.im - im; } else { re += a.re; im += a.im; } }
+            q.out[(long long)b * q.ld_out + i] = mk<T>(re, im);
+        }
         return;
     }
     // conjugate-transposed product: one warp per output, lanes along the (contiguous) column
@@ -249,7 +260,7 @@ static int run_vamp(Handle* h, int mem, int m, int n, int batch, int nit, double
     auto mv = [&](const cx<T>* Mat, long long ldm, int rows, int cols, int trans, const cx<T>* x, long long ldx, cx<T>* out, long long ldo,
                   const cx<T>* add, long long lda, int sub, const T* s1, long long lds1, const T* s2, long long lds2) {
         MvP<T> q{Mat, ldm, rows, cols, trans, x, ldx, out, ldo, add, lda, sub, s1, lds1, s2, lds2};
-        dim3 g(trans ? (cols + 7) / 8 : (rows + 255) / 256, batch);
+        dim3 g(trans ? (cols + 7) / 8 : (rows + 31) / 32, batch);
         JSTSP_LAUNCH(h, PK_OTHER, (k_matvec<T><<<g, 256, 0, st>>>(q)));
     };
     for (int it = 0; it < nit; ++it) {
