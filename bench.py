@@ -383,6 +383,20 @@ def main():
     eng.h.profile(1)                      # on during the warm-up as well: nothing about the profiling path is first-time inside the timed region
     for _ in range(warm):
         step()
+    # settle: beyond the W warm-up steps, keep stepping (untimed, at most 40 steps) until two consecutive steps take the same time as the fastest one seen.
+    # Right after another GPU process has exited, or on a box that has just come up, the first second of a run has shown steps of 95-116 ms around a 72 ms
+    # kernel (driver-side teardown / start-up work sharing the device); the K timed steps below must not start inside such a transient.
+    settle = 0
+    if not os.environ.get("JSTSP_BENCH_NO_SETTLE"):
+        best, prev = float("inf"), None
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        while settle < 40:
+            s0.record(); step(); s1.record(); torch.cuda.synchronize()
+            t = s0.elapsed_time(s1); settle += 1
+            best = min(best, t)
+            if prev is not None and settle >= 2 and abs(t - prev) < 0.03 * best and t < 1.03 * best:
+                break
+            prev = t
     barrier()
     eng.h.profile(2)                      # restart the per-kernel sums
     l0 = eng.launches
@@ -541,7 +555,7 @@ def main():
 
         if args.e2e_pass:
             eng.h.set_chunk(args.e2e_pass)
-        ksteps = max(3, args.steps // 2 + 1)
+        ksteps = max(5, args.steps // 2 + 1)
         esz = 8 if args.precision == "f32" else 16
 
         def e2e_run(entry, ne=ne):
@@ -550,17 +564,19 @@ def main():
             for _ in range(3):
                 host_step()
             barrier()
-            t0 = time.perf_counter()
-            for _ in range(ksteps):
+            calls = []                            # every call is synchronous (the result is in host memory when it returns) and is timed on its own;
+            for _ in range(ksteps):               # the MEDIAN call is reported: one call that meets a host-side hiccup must not decide an average of three
+                t0 = time.perf_counter()
                 host_step()
+                calls.append(time.perf_counter() - t0)
             torch.cuda.synchronize()
-            dt_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            dt_s = torch.tensor([sorted(calls)[len(calls) // 2] * ksteps], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(dt_s, op=dist.ReduceOp.MAX)
             dict_bytes = {"pilots": s.Nt * M * esz, "psi": s.Nt * M * s.L * esz, "dense": P * M * esz}[entry]
             h2d = ne * (N * M * esz + N * M * esz // 2 + dict_bytes + 24) + N * G * esz + (s.Nt * s.Nt * esz if entry != "dense" else 0)
             return dict(value=ne * world * ksteps / float(dt_s.item()), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=ne * G * P * esz,
-                        trials_per_step=ne, timing="host wall clock around the synchronous C-ABI call, max over ranks",
+                        trials_per_step=ne, timing="host wall clock around the synchronous C-ABI call, median call, max over ranks", calls_ms=[round(c * 1e3, 2) for c in calls],
                         entry={"pilots": "jstsp_proposed_algorithm_pilots (pilot sequences s_k, Nt x M per trial)",
                                "psi": "jstsp_proposed_algorithm_psi (Psi_bar, Nt x M x L per trial)", "dense": "jstsp_proposed_algorithm (dense B)"}[entry])
 
@@ -637,7 +653,7 @@ def main():
                 cpu["literal_recorded"] = dict(value=lit["metric_literal_admm"]["per_s"], unit=UNIT, cores=lit.get("cores"), host=lit.get("host"),
                                                note="the reference's own formulation (dense K1, K2 = kron(B.',A), R = K2'K2, proposed_algorithm.m:14-25) restated in NumPy; "
                                                     "tools/literal_baseline.py, profiles/r01_cpu_literal.json")
-    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=warm, ms_per_step=ms / args.steps,
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=warm, settle_steps=settle, ms_per_step=ms / args.steps,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32" if args.precision == "f32" else "f64",
                 data="synthetic",
                 config=dict(workload=WORKLOAD, entry="jstsp_proposed_algorithm_psi (Dt, Psi_bar)" if use_psi else "jstsp_proposed_algorithm (dense B)",

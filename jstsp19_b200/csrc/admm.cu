@@ -896,8 +896,13 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
     JSTSP_CUDA(h, cudaMemsetAsync(h->d_flag, 0, sizeof(int), st));
     const size_t esz = sizeof(cx<T>);
     int pass_idx = -1;
-    for (int b0 = 0; b0 < batch; b0 += chunk_trials) {
-        const int nb = (batch - b0) < chunk_trials ? (batch - b0) : chunk_trials;
+    // HOST buffers in several passes: the first pass is a short one (two trials per SM), so that the solve starts after a third of a pass's input has crossed the
+    // bus instead of a whole pass's (the first copy is the only one that nothing overlaps)
+    const int first_pass = (pingpong && chunk_trials >= 6 * h->sm_count && getenv("JSTSP_EVEN_PASSES") == nullptr) ? 2 * h->sm_count : chunk_trials;
+    for (int b0 = 0, nb_prev = 0; b0 < batch; b0 += nb_prev) {
+        const int want = b0 == 0 ? first_pass : chunk_trials;
+        const int nb = (batch - b0) < want ? (batch - b0) : want;
+        nb_prev = nb;
         ++pass_idx;
         stage_set = pass_idx & 1;
         Arena ar(h->ws, h->ws_bytes);
