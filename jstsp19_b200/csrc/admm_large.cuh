@@ -346,7 +346,13 @@ __global__ void __launch_bounds__(256, 2) k_lg_state(StateArgs s) {
     const int b = blockIdx.y, N = s.N, N2 = 2 * N, tx = threadIdx.x % 16, ty = threadIdx.x / 16;
     const float rho = (float)s.rho[b], irho = 1.f / rho, kap = rho / (rho + 1.f), al = s.alpha[b];
     const size_t off = (size_t)b * s.M * N;
-    for (int t = threadIdx.x; t < 64 * 64; t += 256) { const int n = t % 64, k = t / 64; Ws[t] = (n < N && k < N) ? s.W[(size_t)b * N * N + n + N * k] : mk<float>(0.f, 0.f); }
+    // operands of the two FMA loops are held PLANAR (re plane | im plane) so that two neighbouring rows / columns are one 64-bit operand of the packed fp32x2 FMA
+    float* Wre = reinterpret_cast<float*>(Ws); float* Wim = Wre + 64 * 64;      // [k][n]
+    float* Zre = reinterpret_cast<float*>(Zs); float* Zim = Zre + 64 * 64;      // [k][m], then Z' as [m][n]
+    auto pk = [](float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; };
+    auto f2 = [](uint64_t& d, uint64_t a, uint64_t bb) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(bb)); };
+    auto up = [](uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); };
+    for (int t = threadIdx.x; t < 64 * 64; t += 256) { const int n = t % 64, k = t / 64; const cx<float> w = (n < N && k < N) ? s.W[(size_t)b * N * N + n + N * k] : mk<float>(0.f, 0.f); Wre[t] = w.re; Wim[t] = w.im; }
     double gr[4][4] = {}, gi[4][4] = {};
     for (int tile = 0; tile < CPC / CT; ++tile) {
         const int m0 = blockIdx.x * CPC + tile * CT;
@@ -355,20 +361,25 @@ __global__ void __launch_bounds__(256, 2) k_lg_state(StateArgs s) {
             const int k = t % 64, m = t / 64;
             cx<float> z = mk<float>(0.f, 0.f);
             if (k < N) { const size_t i = off + (size_t)(m0 + m) * N + k; const cx<float> x = s.X[i], v = s.V1[i]; z = mk<float>(x.re - v.re * irho, x.im - v.im * irho); }
-            Zs[k * 64 + m] = z;
+            Zre[k * 64 + m] = z.re; Zim[k * 64 + m] = z.im;
         }
         __syncthreads();
-        float yr[4][4] = {}, yi[4][4] = {};
-        for (int k = 0; k < N; ++k) {
-            cx<float> wv[4], zv[4];
-            *reinterpret_cast<float4*>(&wv[0]) = *reinterpret_cast<const float4*>(&Ws[k * 64 + 4 * ty]);
-            *reinterpret_cast<float4*>(&wv[2]) = *reinterpret_cast<const float4*>(&Ws[k * 64 + 4 * ty + 2]);
-            *reinterpret_cast<float4*>(&zv[0]) = *reinterpret_cast<const float4*>(&Zs[k * 64 + 4 * tx]);
-            *reinterpret_cast<float4*>(&zv[2]) = *reinterpret_cast<const float4*>(&Zs[k * 64 + 4 * tx + 2]);
+        float yr[4][4], yi[4][4];
+        {   // Y = W Z: accumulators pair two columns; per k and row i: YR += w.re zr ; YR += (-w.im) zi ; YI += w.re zi ; YI += w.im zr  (cmac()'s operations and order)
+            uint64_t YR[4][2] = {}, YI[4][2] = {};
+            for (int k = 0; k < N; ++k) {
+                const float4 wr = *reinterpret_cast<const float4*>(Wre + k * 64 + 4 * ty), wi = *reinterpret_cast<const float4*>(Wim + k * 64 + 4 * ty);
+                const ulonglong2 zr = *reinterpret_cast<const ulonglong2*>(Zre + k * 64 + 4 * tx), zi = *reinterpret_cast<const ulonglong2*>(Zim + k * 64 + 4 * tx);
+                const float wrs[4] = {wr.x, wr.y, wr.z, wr.w}, wis[4] = {wi.x, wi.y, wi.z, wi.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 4; ++i) {
+                    const uint64_t WR = pk(wrs[i], wrs[i]), WI = pk(wis[i], wis[i]), WN = pk(-wis[i], -wis[i]);
+                    f2(YR[i][0], WR, zr.x); f2(YR[i][0], WN, zi.x); f2(YI[i][0], WR, zi.x); f2(YI[i][0], WI, zr.x);
+                    f2(YR[i][1], WR, zr.y); f2(YR[i][1], WN, zi.y); f2(YI[i][1], WR, zi.y); f2(YI[i][1], WI, zr.y);
+                }
+            }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) cmac<float>(yr[i][j], yi[i][j], wv[i].re, wv[i].im, zv[j].re, zv[j].im);
+            for (int i = 0; i < 4; ++i) { up(YR[i][0], yr[i][0], yr[i][1]); up(YR[i][1], yr[i][2], yr[i][3]); up(YI[i][0], yi[i][0], yi[i][1]); up(YI[i][1], yi[i][2], yi[i][3]); }
         }
         __syncthreads();                                               // Zs is rewritten with Z' ([m][n]) below
         if (4 * ty < N) {
@@ -409,12 +420,12 @@ __global__ void __launch_bounds__(256, 2) k_lg_state(StateArgs s) {
                 }
                 st4(s.X + idx, x); st4(s.V1 + idx, v1); st4(s.V2 + idx, v2); st4(s.XV + idx, xv);
                 if (s.last) st4(s.Y + (long long)b * s.ld_Y + (size_t)m * N + n0, y);
-                st4(Zs + (4 * tx + j) * 64 + n0, zn);
+                *reinterpret_cast<float4*>(Zre + (4 * tx + j) * 64 + n0) = make_float4(zn[0].re, zn[1].re, zn[2].re, zn[3].re);
+                *reinterpret_cast<float4*>(Zim + (4 * tx + j) * 64 + n0) = make_float4(zn[0].im, zn[1].im, zn[2].im, zn[3].im);
             }
         } else {
-            const cx<float> z0[4] = {mk<float>(0.f, 0.f), mk<float>(0.f, 0.f), mk<float>(0.f, 0.f), mk<float>(0.f, 0.f)};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { *reinterpret_cast<float4*>(Zs + (4 * tx + j) * 64 + 4 * ty) = *reinterpret_cast<const float4*>(&z0[0]); *reinterpret_cast<float4*>(Zs + (4 * tx + j) * 64 + 4 * ty + 2) = *reinterpret_cast<const float4*>(&z0[2]); }
+            for (int j = 0; j < 4; ++j) { *reinterpret_cast<float4*>(Zre + (4 * tx + j) * 64 + 4 * ty) = make_float4(0.f, 0.f, 0.f, 0.f); *reinterpret_cast<float4*>(Zim + (4 * tx + j) * 64 + 4 * ty) = make_float4(0.f, 0.f, 0.f, 0.f); }
         }
         __syncthreads();
         // pass-2 operand: unit = (32-column block, 8-column group, row); three bf16 terms
@@ -434,17 +445,22 @@ __global__ void __launch_bounds__(256, 2) k_lg_state(StateArgs s) {
             }
         }
         // Gram of the next SVT input over this tile: fp32 inside the tile, fp64 across tiles
-        float tr[4][4] = {}, ti[4][4] = {};
-        for (int m = 0; m < 64; ++m) {
-            cx<float> av[4], bv[4];
-            *reinterpret_cast<float4*>(&av[0]) = *reinterpret_cast<const float4*>(&Zs[m * 64 + 4 * ty]);
-            *reinterpret_cast<float4*>(&av[2]) = *reinterpret_cast<const float4*>(&Zs[m * 64 + 4 * ty + 2]);
-            *reinterpret_cast<float4*>(&bv[0]) = *reinterpret_cast<const float4*>(&Zs[m * 64 + 4 * tx]);
-            *reinterpret_cast<float4*>(&bv[2]) = *reinterpret_cast<const float4*>(&Zs[m * 64 + 4 * tx + 2]);
+        float tr[4][4], ti[4][4];
+        {   // G += Z' Z'^H over the tile's columns: accumulators pair two rows i; per column and j: TR += a.re b.re ; TR += a.im b.im ; TI += a.re (-b.im) ; TI += a.im b.re
+            uint64_t TR[2][4] = {}, TI[2][4] = {};
+            for (int m = 0; m < 64; ++m) {
+                const ulonglong2 ar = *reinterpret_cast<const ulonglong2*>(Zre + m * 64 + 4 * ty), ai = *reinterpret_cast<const ulonglong2*>(Zim + m * 64 + 4 * ty);
+                const float4 br = *reinterpret_cast<const float4*>(Zre + m * 64 + 4 * tx), bi = *reinterpret_cast<const float4*>(Zim + m * 64 + 4 * tx);
+                const float brs[4] = {br.x, br.y, br.z, br.w}, bis[4] = {bi.x, bi.y, bi.z, bi.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+                for (int j = 0; j < 4; ++j) {
+                    const uint64_t BR = pk(brs[j], brs[j]), BI = pk(bis[j], bis[j]), BN = pk(-bis[j], -bis[j]);
+                    f2(TR[0][j], ar.x, BR); f2(TR[0][j], ai.x, BI); f2(TI[0][j], ar.x, BN); f2(TI[0][j], ai.x, BR);
+                    f2(TR[1][j], ar.y, BR); f2(TR[1][j], ai.y, BI); f2(TI[1][j], ar.y, BN); f2(TI[1][j], ai.y, BR);
+                }
+            }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) cmac<float>(tr[i][j], ti[i][j], av[i].re, av[i].im, bv[j].re, -bv[j].im);
+            for (int j = 0; j < 4; ++j) { up(TR[0][j], tr[0][j], tr[1][j]); up(TR[1][j], tr[2][j], tr[3][j]); up(TI[0][j], ti[0][j], ti[1][j]); up(TI[1][j], ti[2][j], ti[3][j]); }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
