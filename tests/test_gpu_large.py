@@ -43,7 +43,7 @@ def _config4_trials():
     return _C4["t"]
 
 
-@pytest.mark.parametrize("Nt,Nr,L,T,snr", [(64, 32, 4, 8, 5.0), (128, 64, 8, 4, 15.0), (256, 48, 3, 2, -5.0), (64, 64, 1, 8, 0.0)])
+@pytest.mark.parametrize("Nt,Nr,L,T,snr", [(64, 32, 4, 8, 5.0), (128, 64, 8, 4, 15.0), (256, 48, 3, 2, -5.0), (64, 64, 1, 8, 0.0), (128, 16, 2, 4, 10.0), (192, 24, 5, 8, 3.0)])
 def test_large_route_shapes_against_oracle(Nt, Nr, L, T, snr):
     sh = fx.Shape(Nt=Nt, Nr=Nr, L=L, Mr=4, T=T)
     trials = [fx.make_trial(sh, snr, 7100 + k, rho_rule="sigma1" if k % 2 else "sigma6") for k in range(3)]
