@@ -688,12 +688,13 @@ static int run_admm(Handle* h, const jstsp_admm_desc* d, int mem, const void* su
         }
     }
     if (N <= 0 || M <= 0 || G <= 0 || P <= 0 || batch <= 0 || imax < 0) return fail(h, JSTSP_E_ARG, "non-positive dimension");
-    // large-array route (admm_large.cuh): pilots entry, fp32, 'approximate', no diagnostics / ranking; B is never formed
+    // large-array route (admm_large.cuh): pilots entry, fp32, 'approximate', no diagnostics; B is never formed
     if constexpr (std::is_same<T, float>::value) {
-        if (ps && ps->pilots && !recovered && d->type == JSTSP_APPROXIMATE && !conv_ && !angles && getenv("JSTSP_NO_LARGE") == nullptr &&
+        if (ps && ps->pilots && !recovered && d->type == JSTSP_APPROXIMATE && !conv_ && getenv("JSTSP_NO_LARGE") == nullptr &&
             ps->L * ps->Gt == P && lg::large_shape(N, M, G, ps->Nt, ps->Gt, ps->L)) {
             if (!subY_ || !omega_ || !A_ || !ps->Dt || !ps->Psi || !tauY_ || !tauS_ || !rho_ || !S_) return fail(h, JSTSP_E_ARG, "NULL buffer");
-            return lg::run_large(h, d, mem, subY_, omega_, A_, ps, tauY_, tauS_, rho_, S_, Y_);
+            if (angles && (!indx_ || d->n_indx <= 0)) return fail(h, JSTSP_E_ARG, "indx_S missing");
+            return lg::run_large(h, d, mem, subY_, omega_, A_, ps, tauY_, tauS_, rho_, S_, Y_, angles ? indx_ : nullptr);
         }
     }
     if (!subY_ || !omega_ || !A_ || (!B_ && !ps) || !tauY_ || !tauS_ || !rho_ || !S_) return fail(h, JSTSP_E_ARG, "NULL buffer");

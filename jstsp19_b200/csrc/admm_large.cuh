@@ -500,7 +500,7 @@ __global__ void k_lg_alpha(const double* __restrict__ rr, int nrr, const double*
 }
 // V += alpha Res; S = soft(V, tau_S / rho) on real and imaginary parts (proposed_algorithm.m:50,56)
 __global__ void __launch_bounds__(256) k_lg_vstep(cx<float>* __restrict__ V, const cx<float>* __restrict__ Res, cx<float>* __restrict__ S, const float* __restrict__ alpha,
-                                                  const double* __restrict__ tauS, const double* __restrict__ rho, size_t per) {
+                                                  const double* __restrict__ tauS, const double* __restrict__ rho, size_t per, const unsigned char* __restrict__ mask) {
     const int b = blockIdx.y;
     const size_t t = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (t >= per) return;
@@ -509,7 +509,9 @@ __global__ void __launch_bounds__(256) k_lg_vstep(cx<float>* __restrict__ V, con
     cx<float> v = V[i]; const cx<float> r = Res[i];
     v = mk<float>(v.re + al * r.re, v.im + al * r.im);
     V[i] = v;
-    S[i] = mk<float>(soft1<float>(v.re, thr), soft1<float>(v.im, thr));
+    cx<float> sv = mk<float>(soft1<float>(v.re, thr), soft1<float>(v.im, thr));
+    if (mask && !mask[i]) sv = mk<float>(0.f, 0.f);                  // K3 * s: the support ranking of proposed_algorithm_angles.m:36,68
+    S[i] = sv;
 }
 inline bool make_map_e(const unsigned short* E, int Mext, int groups_total, int box_cols, int box_groups, CUtensorMap* map) {
     auto enc = tc::encode_fn();
@@ -528,7 +530,7 @@ inline bool large_shape(int N, int M, int G, int Nt, int Gt, int L) {
 
 // ---- host driver ----------------------------------------------------------------------------------------------------------------
 static int run_large(Handle* h, const jstsp_admm_desc* d, int mem, const void* subY_, const void* omega_, const void* A_, const PsiArgs* ps,
-                     const double* tauY_, const double* tauS_, const double* rho_, void* S_, void* Y_) {
+                     const double* tauY_, const double* tauS_, const double* rho_, void* S_, void* Y_, const int* indx_ = nullptr) {
     const int N = d->N, M = d->M, G = d->G, P = d->P, batch = d->batch, imax = d->imax, Nt = ps->Nt, Gt = ps->Gt, L = ps->L;
     const int N2 = 2 * N, nkg = Nt / 4, Mext = M + 8;
     const int cps = M % 2048 == 0 ? 2048 : CPC, KS = M / cps, ngram = M / CPC, ntile = M / 128;
@@ -552,7 +554,9 @@ static int run_large(Handle* h, const jstsp_admm_desc* d, int mem, const void* s
     while (chunk > 1 && (size_t)chunk * per_trial > budget) chunk = (chunk + 1) / 2;
     if (chunk > 16) chunk = 16;
     cx<float> *X, *V1, *V2, *Xs, *XV, *Gm, *Yb, *sY, *dA, *dDt, *dPil, *T1c, *R1, *Res, *V, *S, *AR, *Q, *W;
-    float *om, *scale, *part, *alpha; unsigned short* E; unsigned char *dimg, *qimg; double *rr, *gg, *gram, *Uprev, *dtau, *dtaus, *drho; int* bad;
+    float *om, *scale, *part, *alpha; unsigned short* E; unsigned char *dimg, *qimg, *smask = nullptr; double *rr, *gg, *gram, *Uprev, *dtau, *dtaus, *drho; int *bad, *dindx = nullptr;
+    const bool angles = indx_ != nullptr;
+    const bool shI = d->ld_indx == 0;
     auto layout = [&](Arena& a, int nb) {
         X = a.take<cx<float>>(NM * nb); V1 = a.take<cx<float>>(NM * nb); V2 = a.take<cx<float>>(NM * nb);
         Xs = a.take<cx<float>>(NM * nb); XV = a.take<cx<float>>(NM * nb); Gm = a.take<cx<float>>(NM * nb);
@@ -568,6 +572,7 @@ static int run_large(Handle* h, const jstsp_admm_desc* d, int mem, const void* s
         rr = a.take<double>((size_t)64 * nb); gg = a.take<double>((size_t)ntile * nb);
         gram = a.take<double>((size_t)ngram * 2 * N * N * nb); Uprev = a.take<double>((size_t)2 * N * N * nb); W = a.take<cx<float>>((size_t)N * N * nb);
         dtau = a.take<double>(nb); dtaus = a.take<double>(nb); drho = a.take<double>(nb);
+        if (angles) { smask = a.take<unsigned char>(GP * nb); dindx = host ? a.take<int>((size_t)d->n_indx * (shI ? 1 : nb)) : nullptr; }
     };
     { Arena probe(nullptr, 0); layout(probe, chunk); int rc = ensure_workspace(h, probe.off); if (rc) return rc; }
     const size_t sm_j = JacobiSmem::bytes(N) + 2 * sizeof(double) * (size_t)N * N + 16;
@@ -607,6 +612,7 @@ static int run_large(Handle* h, const jstsp_admm_desc* d, int mem, const void* s
             pY = sY; ldY_in = (d->ld_subY || batch == 1) ? (long long)NM : 0; pO = om; ldO = (d->ld_omega || batch == 1) ? (long long)NM : 0;
             pA = dA; ldA = shA ? 0 : (long long)N * G; pDt = dDt; ldDt = shD ? 0 : (long long)Nt * Gt; pPil = dPil; ldPil = shP ? 0 : (long long)Nt * M;
             pTauY = dtau; pTauS = dtaus; pRho = drho;
+            if (angles) JSTSP_CUDA(h, up(dindx, indx_, (size_t)d->n_indx, d->ld_indx, sizeof(int)));
         } else {
             pY = (const cx<float>*)subY_ + (long long)b0 * d->ld_subY; ldY_in = d->ld_subY; pO = (const float*)omega_ + (long long)b0 * d->ld_omega; ldO = d->ld_omega;
             pA = (const cx<float>*)A_ + (long long)b0 * d->ld_A; ldA = d->ld_A; pDt = (const cx<float>*)ps->Dt + (long long)b0 * ps->ld_Dt; ldDt = ps->ld_Dt;
@@ -628,6 +634,9 @@ static int run_large(Handle* h, const jstsp_admm_desc* d, int mem, const void* s
         if (!make_map_e(E, Mext, nkg * nE, WIN, nkg, &map0) || !make_map_e(E, Mext, nkg * nE, SC2, nkg, &map1)) return fail(h, JSTSP_E_CUDA, "cuTensorMapEncodeTiled failed for the pilot image");
         for (cx<float>* z : {X, V1, V2, Xs, XV, Gm}) JSTSP_CUDA(h, cudaMemsetAsync(z, 0, 8 * NM * nb, st));
         JSTSP_CUDA(h, cudaMemsetAsync(alpha, 0, sizeof(float) * nb, st));
+        if (angles) JSTSP_CUDA(h, cudaMemsetAsync(smask, 0, GP * nb, st));
+        const int* pIndx = angles ? (host ? dindx : indx_ + (long long)b0 * d->ld_indx) : nullptr;
+        const long long ldIndx = angles ? (host ? (shI ? 0 : (long long)d->n_indx) : d->ld_indx) : 0;
         JSTSP_CUDA(h, cudaMemsetAsync(V, 0, 8 * GP * nb, st));
         JSTSP_CUDA(h, cudaMemsetAsync(S, 0, 8 * GP * nb, st));
         JSTSP_CUDA(h, cudaMemsetAsync(gram, 0, sizeof(double) * (size_t)ngram * 2 * N * N * nb, st));
@@ -662,7 +671,12 @@ static int run_large(Handle* h, const jstsp_admm_desc* d, int mem, const void* s
             MmaArgs m0{qimg, (long long)qimg_b, reinterpret_cast<float*>(Gm), (long long)NM * 2, gg, N2, L, nkg, shP ? 1 : 0, 0, M};
             { dim3 g(ntile, nb); JSTSP_LAUNCH(h, PK_LG_PASS1, (k_lg_mma<0><<<g, MMA_THREADS, sm0, st>>>(map0, m0))); }
             JSTSP_LAUNCH(h, PK_LG_SMALL, (k_lg_alpha<<<nb, 1, 0, st>>>(rr, 64, gg, ntile, alpha)));
-            { dim3 g(ceil_div((int)GP, 256), nb); JSTSP_LAUNCH(h, PK_LG_SMALL, (k_lg_vstep<<<g, 256, 0, st>>>(V, Res, S, alpha, pTauS, pRho, GP))); }
+            if (angles) {      // Omega_S(indx_S(1 : min(10 + 5 i, G P))) = 1 (proposed_algorithm_angles.m:36), the mask kernel of the dense route
+                AdmmP<float> qm{};
+                qm.G = G; qm.P = P; qm.iter = it; qm.n_indx = d->n_indx; qm.indx = pIndx; qm.ld_indx = ldIndx; qm.smask = smask;
+                dim3 g(1, nb); JSTSP_LAUNCH(h, PK_LG_SMALL, (k_mask_grow<float><<<g, 64, 0, st>>>(qm)));
+            }
+            { dim3 g(ceil_div((int)GP, 256), nb); JSTSP_LAUNCH(h, PK_LG_SMALL, (k_lg_vstep<<<g, 256, 0, st>>>(V, Res, S, alpha, pTauS, pRho, GP, smask))); }
             // Xs = (A S_l Dt') e
             gemm(PK_LG_SMALL, N, P, G, nb, 1, pA, ldA, 0, N, OPN, S, (long long)GP, 0, G, OPN, AR, (long long)NP, 0, N);
             gemm(PK_LG_SMALL, N, Nt, Gt, nb * L, L, AR, (long long)NP, (long long)N * Gt, N, OPN, pDt, ldDt, 0, Nt, OPH, Q, (long long)NLN, (long long)N * Nt, N);

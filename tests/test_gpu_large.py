@@ -106,3 +106,23 @@ def test_large_route_shared_and_per_trial_pilots_agree():
     S_b, Y_b = jb.proposed_algorithm_pilots(np.stack([t["subY"], t2["subY"]]), np.stack([t["Omega"], t2["Omega"]]), t["A"], t["Dt"], t["pilots"], 4, 20, *par,
                                             precision="f32", nargout=2)
     assert np.array_equal(S_a, S_b) and np.array_equal(Y_a, Y_b)
+
+
+def test_large_route_with_support_ranking():
+    """proposed_algorithm_angles on the large-array route: the growing support mask Omega_S(indx_S(1:min(10+5i, G P))) (proposed_algorithm_angles.m:36,68),
+    one ranking per trial, against the oracle; and a ranking shared by the batch."""
+    sh = fx.Shape(Nt=64, Nr=32, L=4, Mr=4, T=8)
+    trials = [fx.make_trial(sh, 8.0, 7400 + k) for k in range(2)]
+    st = lambda key: np.stack([t[key] for t in trials])
+    par = ([t["tau_Y"] for t in trials], [t["tau_Z"] for t in trials], [t["rho"] for t in trials], "approximate")
+    imax = 40
+    S, Y = jb.proposed_algorithm_pilots(st("subY"), st("Omega"), st("A"), trials[0]["Dt"], st("pilots"), sh.L, imax, *par, np.stack([t["indx_S"] for t in trials]),
+                                        precision="f32", nargout=2)
+    assert default_handle().last_path == 3
+    for k, t in enumerate(trials):
+        S0, Y0, _ = est.proposed_algorithm_structured(t["subY"], t["Omega"], t["A"], t["B"], imax, t["tau_Y"], t["tau_Z"], t["rho"], "approximate", indx_S=t["indx_S"], want_conv=False)
+        assert np.count_nonzero(S0) <= 10 + 5 * imax
+        assert np.array_equal(S[k] != 0, S0 != 0) or _rel(S[k], S0) < TOL          # same support (entries inside the mask that the threshold zeroes may differ at rounding level)
+        assert _rel(S[k], S0) < TOL and _rel(Y[k], Y0) < TOL
+    S1, _ = jb.proposed_algorithm_pilots(st("subY"), st("Omega"), st("A"), trials[0]["Dt"], st("pilots"), sh.L, imax, *par, trials[0]["indx_S"], precision="f32", nargout=2)
+    assert np.array_equal(S1[0], S[0])
