@@ -52,11 +52,49 @@ def _config2_trials(rng, n, nnz=12, noise=0.02):
     return A, Bs, np.stack(Ys)
 
 
-@pytest.mark.parametrize("m,ntrials", [(30, 32), (100, 8)])
+def _near_tie_gap(A, B, Y, picks, cand_a, cand_b):
+    """Relative gap between the fp64 correlations of two candidates at the step that follows the 1-based picks `picks` (OMP.m:15-17 on the Kronecker
+    dictionary: residual of the least-squares fit on the picked atoms, C = A^H R B^H)."""
+    N, M = Y.shape
+    G = A.shape[1]
+    R = Y.copy()
+    if picks:
+        Phi = np.stack([np.outer(A[:, (i - 1) % G], B[(i - 1) // G, :]).reshape(-1, order="F") for i in picks], axis=1)
+        x = np.linalg.lstsq(Phi, Y.reshape(-1, order="F"), rcond=None)[0]
+        R = Y - (Phi @ x).reshape(N, M, order="F")
+    C = np.abs(A.conj().T @ R @ B.conj().T)
+    ca, cb = C[(cand_a - 1) % G, (cand_a - 1) // G], C[(cand_b - 1) % G, (cand_b - 1) // G]
+    return abs(ca - cb) / max(ca, cb)
+
+
+def _assert_supports(A, B, Y, got, want, tol):
+    """Pick for pick equal to the oracle's.  The f32 entry receives inputs rounded to fp32, so two candidates whose fp64 correlations agree to better than the input
+    resolution cannot be ordered like the fp64 oracle orders them: an ADJACENT swap of two picks is accepted only if that gap, recomputed here in fp64 from the oracle's
+    own state, is below `tol` (stated: 1e-5 relative); anything else fails.  Returns the number of such swaps."""
+    got, want = [int(v) for v in got], [int(v) for v in want]
+    t, swaps = 0, 0
+    while t < len(want):
+        if got[t] == want[t]:
+            t += 1
+            continue
+        assert t + 1 < len(want) and got[t] == want[t + 1] and got[t + 1] == want[t], (t, got[t:t + 3], want[t:t + 3])
+        gap = _near_tie_gap(A, B, Y, want[:t], want[t], want[t + 1])
+        assert gap < tol, (t, gap)
+        swaps += 1
+        t += 2
+    return swaps
+
+
+_ORACLE_CACHE = {}
+
+
+@pytest.mark.parametrize("m,ntrials", [(30, 32), (100, 32)])
 @pytest.mark.parametrize("tc", ["1", "0"])
 def test_kron_omp_config2_supports_every_trial(m, ntrials, tc, monkeypatch):
     """BASELINE config 2 (Phi would be 8192 x 262144) at the benchmarked iteration counts, m = 30 and m = 100 (numOfnz of
-    plot_errorVSsnr.m:20): the support of EVERY trial equals the fp64 oracle's, in order (OMP.m:17, first maximum), through the
+    plot_errorVSsnr.m:20), 32 trials each: the support of every trial equals the fp64 oracle's, in order (OMP.m:17, first maximum) - up to adjacent swaps of picks
+    whose fp64 correlations agree to better than 1e-5 relative, i.e. below the resolution of the fp32 inputs this entry receives (checked pick by pick in fp64,
+    _assert_supports; measured: at most a few such swaps per 32 trials at m = 100, none at m = 30) - through the
     tcgen05 tf32 screen (JSTSP_OMP_TC=1) and through the fp32 FMA pass (JSTSP_OMP_TC=0).  Both passes only nominate candidates;
     the decision among in-band candidates is an fp64 re-evaluation, so there is no "ambiguous" escape: the flag now counts exact
     fp64 ties only and must be zero here.  With m = 100 most picks fit noise (12 true atoms): the hard case for a low-precision screen."""
@@ -66,14 +104,24 @@ def test_kron_omp_config2_supports_every_trial(m, ntrials, tc, monkeypatch):
     monkeypatch.setenv("JSTSP_OMP_TC", tc)
     X, I, XS, R, amb = jb.OMP_kron(A, Bs, Ys, m, precision="f32", want_x_hat=False, return_ambiguous=True)
     assert int(np.sum(amb)) == 0
+    nswap = 0
+    if m not in _ORACLE_CACHE:                      # the same seeded trials serve both settings of the screen: the fp64 oracle (4 s per trial at m = 100) runs once
+        _ORACLE_CACHE[m] = [est.omp_kron_structured(A, Bs[k], Ys[k], m) for k in range(ntrials)]
     for k in range(ntrials):
-        x0, i0, xs0, r0 = est.omp_kron_structured(A, Bs[k], Ys[k], m)
-        assert list(I[k]) == i0, (k, [(t, a, b) for t, (a, b) in enumerate(zip(I[k], i0)) if a != b][:3])
-        assert _rel(XS[k], xs0) < 5e-4
+        x0, i0, xs0, r0 = _ORACLE_CACHE[m][k]
+        swaps = _assert_supports(A, Bs[k], Ys[k], I[k], i0, 1e-5)
+        nswap += swaps
+        if swaps == 0:
+            assert _rel(XS[k], xs0) < 5e-4
+        else:                                       # same atoms in another order: compare the coefficients atom by atom
+            a = dict(zip([int(v) for v in I[k]], XS[k])); b = dict(zip(i0, xs0))
+            assert _rel(np.array([a[i] for i in i0]), np.array([b[i] for i in i0])) < 5e-4
+    print(f"m = {m}, screen {'tcgen05' if tc == '1' else 'FMA'}: {ntrials} trials, {nswap} adjacent swaps of near-tied picks (fp64 gap < 1e-5)")
+    assert nswap <= ntrials // 8
     if m == 30 and tc == "1":
         X64, I64, XS64, R64 = jb.OMP_kron(A, Bs[:2], Ys[:2], m, precision="f64")
         for k in range(2):
-            x0, i0, xs0, r0 = est.omp_kron_structured(A, Bs[k], Ys[k], m)
+            x0, i0, xs0, r0 = _ORACLE_CACHE[m][k]
             assert list(I64[k]) == i0 and _rel(XS64[k], xs0) < 1e-9 and _rel(X64[k], x0) < 1e-9
 
 
